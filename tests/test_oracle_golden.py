@@ -1,0 +1,82 @@
+"""The oracle restatement (oracle/dpa_oracle.py) against the reference's own outputs.
+
+tests/golden/*.npz were produced by oracle/gen_golden.py from the AST-lifted, unmodified
+/root/reference/llava/train/halva_trainer.py:392-592 (forward + autograd backward).
+"""
+import numpy as np
+import pytest
+
+from oracle import dpa_oracle
+from dpa_testutil import golden_path, rel
+
+
+def _run(g, mode):
+    return dpa_oracle.dpa_loss(g["h_pair"], g["labels_pair"], g["signs_pair"], g["h_ref_pol"], g["h_ref_frz"],
+                               g["labels_ref"], g["W"], g["W_ref"], float(g["alpha"]), mode=mode)
+
+
+def test_oracle_matches_reference_fp32_maths(golden):
+    """fp64 restatement vs the reference run in fp32 on the same values: <= 1e-5 loss, <= 1e-4 grads."""
+    o = _run(golden, "fp64")
+    assert abs(o["loss"] - golden["ref32_loss"]) <= 1e-5 * abs(golden["ref32_loss"])
+    assert abs(o["align"] - golden["ref32_align"]) <= 1e-5 * abs(golden["ref32_align"])
+    assert rel(o["dH_pair"], golden["ref32_dH_pair"]) <= 1e-4
+    assert rel(o["dH_ref"], golden["ref32_dH_ref"]) <= 1e-4
+    assert rel(o["dW"], golden["ref32_dW"]) <= 1e-4
+    # structural zeros: last position and inactive rows get exactly no gradient in the reference
+    assert np.all(golden["ref32_dH_pair"][:, -1] == 0) and np.all(o["dH_pair"][:, -1] == 0)
+    inactive = ~o["active_pair"]
+    assert np.all(o["dH_pair"][:, :-1][inactive] == 0)
+    assert np.abs(golden["ref32_dH_pair"][:, :-1][inactive]).max() == 0
+
+
+def test_oracle_bf16_mode_matches_reference_bf16(golden):
+    """bf16 emulation (rounded logits / dLogits / outputs) vs the reference run in bf16 as the trainer does."""
+    if str(golden["dtype"]) != "bf16":
+        pytest.skip("fp32 case")
+    o = _run(golden, "bf16")
+    assert abs(o["loss"] - golden["ref_loss"]) <= 1e-3 * abs(golden["ref_loss"])
+    assert abs(o["align"] - golden["ref_align"]) <= 1e-3 * abs(golden["ref_align"])
+    assert rel(o["dH_pair"], golden["ref_dH_pair"]) <= 1e-2
+    assert rel(o["dH_ref"], golden["ref_dH_ref"]) <= 1e-2
+    assert rel(o["dW"], golden["ref_dW"]) <= 1e-2
+
+
+def test_divergence_component(golden):
+    o = _run(golden, "fp64")
+    a = float(golden["alpha"])
+    if a == 0:
+        assert o["loss"] == o["align"]
+        return
+    ref_div = (golden["ref32_loss"] - golden["ref32_align"]) / a
+    assert abs(o["div"] - ref_div) <= 2e-4 * abs(ref_div) + 1e-6     # fp32 cancellation in (loss - align)
+
+
+def test_quirks_recorded_from_reference():
+    q = np.load(golden_path("quirks"))
+    assert bool(q["k0_is_nan"]) and bool(q["kmismatch_raises"])
+    g = dict(np.load(golden_path("tiny_fp32")))
+    with pytest.raises(dpa_oracle.PhraseShapeError):
+        dpa_oracle.dpa_loss(g["h_pair"], g["labels_pair"], np.zeros_like(g["signs_pair"]), g["h_ref_pol"],
+                            g["h_ref_frz"], g["labels_ref"], g["W"], g["W_ref"], 0.4)
+
+
+def test_bf16_round_is_rne():
+    import torch
+    x = np.random.default_rng(0).standard_normal(10000).astype(np.float32) * 37.0
+    want = torch.from_numpy(x).to(torch.bfloat16).float().numpy()
+    assert np.array_equal(dpa_oracle.bf16_round(x).astype(np.float32), want)
+
+
+def test_live_reference_if_present():
+    """When /root/reference is mounted (build container), re-run the lift and compare -- guards the fixtures."""
+    from oracle.lift_reference import reference_available, run_reference
+    if not reference_available():
+        pytest.skip("no /root/reference here")
+    import torch
+    g = dict(np.load(golden_path("tiny_fp32")))
+    t = lambda k: torch.from_numpy(g[k])
+    r = run_reference(t("h_pair"), t("labels_pair"), t("signs_pair"), t("h_ref_pol"), t("h_ref_frz"),
+                      t("labels_ref"), t("W"), t("W_ref"), alpha=float(g["alpha"]))
+    assert abs(r["loss"].item() - g["ref_loss"]) < 1e-6
+    assert rel(r["dW"].numpy(), g["ref_dW"]) < 1e-5
