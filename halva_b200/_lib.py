@@ -1,0 +1,88 @@
+"""ctypes binding of libhalva_dpa.so (include/halva_dpa.h).  No CPU fallback: a missing library is an error."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libhalva_dpa.so")
+
+DPA_BF16 = 0
+DPA_I64, DPA_I32 = 0, 1
+FLAG_ROUND_LOGITS, FLAG_NEED_DW, FLAG_DENSE = 1, 2, 4
+STATUS_BAD_SIGN, STATUS_K_MISMATCH, STATUS_K_ZERO, STATUS_BAD_LABEL = 1, 2, 4, 8
+EXPORTS = ["dpa_version", "dpa_last_error", "dpa_query_workspace", "dpa_forward", "dpa_backward",
+           "dpa_forward_stats", "dpa_forward_finish", "dpa_row_stats_view", "dpa_debug_gemm",
+           "dpa_profile_enable", "dpa_profile_collect", "dpa_profile_kind_name"]
+
+
+class Shape(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("B", "T", "B_ref", "T_ref", "H", "V", "V_local", "v_offset", "dtype",
+                                         "index_dtype", "flags", "chunk_rows")]
+
+
+class Workspace(C.Structure):
+    _fields_ = [("state_bytes", C.c_size_t), ("fwd_bytes", C.c_size_t), ("bwd_bytes", C.c_size_t)]
+
+
+class Args(C.Structure):
+    _fields_ = [("shape", Shape), ("alpha", C.c_float),
+                ("h_pair", C.c_void_p), ("labels_pair", C.c_void_p), ("signs_pair", C.c_void_p),
+                ("h_ref_pol", C.c_void_p), ("h_ref_frz", C.c_void_p), ("labels_ref", C.c_void_p),
+                ("W", C.c_void_p), ("W_ref", C.c_void_p),
+                ("state", C.c_void_p), ("state_bytes", C.c_size_t),
+                ("scratch", C.c_void_p), ("scratch_bytes", C.c_size_t),
+                ("losses", C.c_void_p), ("status", C.c_void_p),
+                ("d_loss", C.c_void_p), ("dH_pair", C.c_void_p), ("dH_ref", C.c_void_p), ("dW", C.c_void_p)]
+
+
+class DPAError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library; raise (never fall back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DPAError(f"{LIB_PATH} is missing: build it with `python -m halva_b200.build` "
+                       "(nvcc, sm_100a). There is no CPU or PyTorch fallback for the DPA-loss path.")
+    lib = C.CDLL(LIB_PATH)
+    lib.dpa_version.restype = C.c_int
+    lib.dpa_last_error.restype = C.c_char_p
+    lib.dpa_query_workspace.argtypes = [C.POINTER(Shape), C.POINTER(Workspace)]
+    for name in ("dpa_forward", "dpa_backward", "dpa_forward_stats"):
+        getattr(lib, name).argtypes = [C.POINTER(Args), C.c_void_p]
+    lib.dpa_forward_finish.argtypes = [C.POINTER(Args), C.c_void_p, C.c_int, C.c_void_p]
+    lib.dpa_row_stats_view.argtypes = [C.POINTER(Args), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    lib.dpa_debug_gemm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_int, C.c_void_p]
+    lib.dpa_profile_enable.argtypes = [C.c_int]
+    lib.dpa_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]
+    lib.dpa_profile_kind_name.argtypes = [C.c_int]
+    lib.dpa_profile_kind_name.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().dpa_last_error().decode(errors="replace")
+        raise DPAError(f"{what} failed ({rc}): {msg}")
+
+
+def profile_enable(on: bool):
+    load().dpa_profile_enable(1 if on else 0)
+
+
+def profile_collect():
+    """-> {kernel class: (milliseconds, kernel launches)} accumulated since the last collect (synchronises)."""
+    lib = load()
+    ms = (C.c_double * 16)()
+    ln = (C.c_int * 16)()
+    n = lib.dpa_profile_collect(ms, ln, 16)
+    return {lib.dpa_profile_kind_name(k).decode(): (ms[k], ln[k]) for k in range(n)}

@@ -1,0 +1,584 @@
+// C ABI of libhalva_dpa.so (include/halva_dpa.h): workspace layout, TMA descriptors, launch sequences.
+#include <cstdio>
+#include <cstring>
+#include <cstdarg>
+#include <mutex>
+#include <algorithm>
+#include <vector>
+
+#include "dpa_kernels.cuh"
+
+using namespace dpa;
+
+namespace {
+
+thread_local char g_err[512] = "";
+int fail(int code, const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+  return code;
+}
+#define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(DPA_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); } while (0)
+#define LAUNCH_CHECK(what) do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return fail(DPA_ERR_CUDA, "launch %s: %s", what, cudaGetErrorString(e_)); } while (0)
+
+// ---------------------------------------------------------------------------------- optional per-kernel timing
+// bench.py asks for live CUDA-event timings of the individual kernels (they are launched inside this library,
+// so the caller cannot bracket them). Off by default; when on, every launch group is bracketed by two events.
+enum ProfKind { PK_META = 0, PK_GATHER, PK_FWD_PAIR, PK_FWD_REF, PK_REDUCE, PK_COEF, PK_DZ_PAIR, PK_DZ_REF, PK_DH, PK_DW, PK_MISC, PK_COUNT };
+struct ProfSpan { int kind; int launches; cudaEvent_t a, b; };
+std::vector<ProfSpan> g_spans;
+std::mutex g_prof_mu;
+bool g_prof_on = false;
+struct ProfScope {
+  cudaStream_t st; bool on; ProfSpan sp;
+  ProfScope(int kind, int launches, cudaStream_t s) : st(s), on(g_prof_on) {
+    if (!on) return;
+    sp.kind = kind; sp.launches = launches;
+    cudaEventCreate(&sp.a); cudaEventCreate(&sp.b);
+    cudaEventRecord(sp.a, st);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(sp.b, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_spans.push_back(sp);
+  }
+};
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline int round_up_i(int x, int a) { return (x + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------- device / driver entry
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+struct DeviceInfo { int sms = 0; int cc_major = 0; EncodeTiledFn encode = nullptr; bool ok = false; char why[128] = ""; };
+DeviceInfo g_dev[16];
+std::mutex g_mu;
+
+int device_info(DeviceInfo** out) {
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 16) return fail(DPA_ERR_CUDA, "device index %d unsupported", dev);
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceInfo& d = g_dev[dev];
+  if (!d.ok) {
+    CUDA_TRY(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (d.cc_major != 10) return fail(DPA_ERR_ARCH, "libhalva_dpa needs an sm_100 GPU (found compute capability %d.x)", d.cc_major);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(DPA_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    d.encode = reinterpret_cast<EncodeTiledFn>(fn);
+    d.ok = true;
+  }
+  *out = &d;
+  return DPA_OK;
+}
+
+// 2-D bf16 tensor map, 128-byte swizzle. inner = contiguous dimension.
+int make_tmap(const DeviceInfo* d, CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+              uint32_t box_inner, uint32_t box_outer) {
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstr[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = d->encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(DPA_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%llu outer=%llu stride=%llu box=%ux%u", (int)r, ptr,
+                (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)row_stride_bytes, box_inner, box_outer);
+  return DPA_OK;
+}
+// operand tile maps: K-major = [rows][K] row-major, box {64 k, rows}; MN-major = [K][mn] row-major, box {64 mn, 64 k}
+int make_operand_tmap(const DeviceInfo* d, CUtensorMap* tm, const void* ptr, int major, uint64_t mn_extent, uint64_t k_extent,
+                      uint64_t ld_elems, uint32_t tile_rows) {
+  if (major == KMAJOR) return make_tmap(d, tm, ptr, k_extent, mn_extent, ld_elems * 2, BK, tile_rows);
+  return make_tmap(d, tm, ptr, mn_extent, k_extent, ld_elems * 2, 64, BK);
+}
+
+template <class Cfg, class Epi>
+int launch_gemm(cudaStream_t st, int grid, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA2,
+                const CUtensorMap& tmB2, const GemmWork& work, const typename Epi::Params& ep, const char* what) {
+  auto kern = dpa_gemm_kernel<Cfg, Epi>;
+  static std::once_flag once[16];
+  int dev = 0; cudaGetDevice(&dev);
+  cudaError_t attr_err = cudaSuccess;
+  std::call_once(once[dev & 15], [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES); });
+  if (attr_err != cudaSuccess) return fail(DPA_ERR_CUDA, "cudaFuncSetAttribute(%s): %s", what, cudaGetErrorString(attr_err));
+  kern<<<grid, kNumThreads, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmA2, tmB2, work, ep);
+  LAUNCH_CHECK(what);
+  return DPA_OK;
+}
+
+// ---------------------------------------------------------------------------------- workspace layout
+constexpr int kTpuPair = 5;     // 256-wide column tiles per unit  (V=32000: 125 tiles -> 25 groups)
+constexpr int kTpuRef = 10;     // 128-wide column tiles per unit  (V=32000: 250 tiles -> 25 groups)
+constexpr int kBnPair = 256, kBnRef = 128;
+
+struct Layout {
+  int n_pos_pair, n_pos_ref, cap_pair, cap_ref, nblk_pair, nblk_ref, ng_pair, ng_ref, ldz, chunk_rows, n_chunks;
+  // state offsets
+  size_t meta, bitmap, block_counts, src_pair, lab_pair, col_pair, src_ref, act_ref, stats_pair, stats_ref, stats_u,
+      lse_pair, logp_pair, lse_ref_p, lse_ref_r, kl_row, PN, sigma, coef_pair, coef_ref, state_total;
+  size_t row_stats_bytes;
+  // forward scratch offsets
+  size_t f_Hp, f_Hf, f_part_pair, f_part_ref, f_part_u, fwd_total;
+  // backward scratch offsets
+  size_t b_Hp, b_Hf, b_dz, b_dW32, bwd_total;
+};
+
+int make_layout(const dpa_shape_t& s, Layout& L) {
+  if (s.B < 1 || s.T < 2 || s.B_ref < 1 || s.T_ref < 2) return fail(DPA_ERR_BAD_SHAPE, "need B>=1, T>=2, B_ref>=1, T_ref>=2");
+  if (s.H < 64 || s.H % 64) return fail(DPA_ERR_BAD_SHAPE, "H=%d must be a positive multiple of 64", s.H);
+  if (s.V_local < 8 || s.V_local % 8) return fail(DPA_ERR_BAD_SHAPE, "V_local=%d must be a positive multiple of 8 (16-byte TMA rows)", s.V_local);
+  if (s.v_offset < 0 || s.v_offset + s.V_local > s.V) return fail(DPA_ERR_BAD_SHAPE, "vocab shard [%d,%d) outside V=%d", s.v_offset, s.v_offset + s.V_local, s.V);
+  if (s.dtype != DPA_BF16) return fail(DPA_ERR_DTYPE, "only bf16 hidden states / weights are supported by the tensor-core path");
+  if (s.index_dtype != DPA_I64 && s.index_dtype != DPA_I32) return fail(DPA_ERR_DTYPE, "labels/signs must be int64 or int32");
+  if ((long long)2 * s.B * s.T >= (1ll << 31) / 2 || 2 * s.B >= 32768) return fail(DPA_ERR_BAD_SHAPE, "batch too large for 32-bit row ids");
+  L.n_pos_pair = 2 * s.B * (s.T - 1);
+  L.n_pos_ref = s.B_ref * (s.T_ref - 1);
+  L.cap_pair = round_up_i(L.n_pos_pair, BM);
+  L.cap_ref = round_up_i(L.n_pos_ref, BM);
+  L.nblk_pair = (L.n_pos_pair + kScanBlock - 1) / kScanBlock;
+  L.nblk_ref = (L.n_pos_ref + kScanBlock - 1) / kScanBlock;
+  L.ng_pair = ((s.V_local + kBnPair - 1) / kBnPair + kTpuPair - 1) / kTpuPair;
+  L.ng_ref = ((s.V_local + kBnRef - 1) / kBnRef + kTpuRef - 1) / kTpuRef;
+  L.ldz = round_up_i(s.V_local, 64);
+  L.chunk_rows = s.chunk_rows > 0 ? s.chunk_rows : 16384;
+  if (L.chunk_rows % BM) return fail(DPA_ERR_BAD_SHAPE, "chunk_rows=%d must be a multiple of 128", L.chunk_rows);
+  const int cap_tot = L.cap_pair + L.cap_ref;
+  L.chunk_rows = std::min(L.chunk_rows, cap_tot);
+  L.n_chunks = (cap_tot + L.chunk_rows - 1) / L.chunk_rows;
+
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+  L.meta = take(sizeof(DpaMeta));
+  L.bitmap = take(16 * 4);
+  L.block_counts = take((size_t)(L.nblk_pair + L.nblk_ref) * 4);
+  L.src_pair = take((size_t)L.cap_pair * 4); L.lab_pair = take((size_t)L.cap_pair * 4); L.col_pair = take((size_t)L.cap_pair * 4);
+  L.src_ref = take((size_t)L.cap_ref * 4); L.act_ref = take((size_t)L.cap_ref * 4);
+  // the three statistics arrays are contiguous: they are the vocab-parallel exchange record
+  L.stats_pair = o; o += (size_t)L.cap_pair * 16;
+  L.stats_ref = o; o += (size_t)L.cap_ref * 16;
+  L.stats_u = o; o += (size_t)L.cap_ref * 4;
+  L.row_stats_bytes = o - L.stats_pair;
+  o = align_up(o, 256);
+  L.lse_pair = take((size_t)L.cap_pair * 4); L.logp_pair = take((size_t)L.cap_pair * 4);
+  L.lse_ref_p = take((size_t)L.cap_ref * 4); L.lse_ref_r = take((size_t)L.cap_ref * 4); L.kl_row = take((size_t)L.cap_ref * 4);
+  L.PN = take((size_t)2 * s.B * (kMaxSign + 1) * 4);
+  L.sigma = take((size_t)s.B * (kMaxSign + 1) * 4);
+  L.coef_pair = take((size_t)L.cap_pair * 4); L.coef_ref = take((size_t)L.cap_ref * 4);
+  L.state_total = o;
+
+  o = 0;
+  L.f_Hp = take((size_t)cap_tot * s.H * 2);
+  L.f_Hf = take((size_t)L.cap_ref * s.H * 2);
+  L.f_part_pair = take((size_t)L.ng_pair * L.cap_pair * 16);
+  L.f_part_ref = take((size_t)L.ng_ref * L.cap_ref * 16);
+  L.f_part_u = take((size_t)L.ng_ref * L.cap_ref * 4);
+  L.fwd_total = o;
+
+  o = 0;
+  L.b_Hp = take((size_t)cap_tot * s.H * 2);
+  L.b_Hf = take((size_t)L.cap_ref * s.H * 2);
+  L.b_dz = take((size_t)L.chunk_rows * L.ldz * 2);
+  L.b_dW32 = (s.flags & DPA_FLAG_NEED_DW) ? take((size_t)s.V_local * s.H * 4) : o;
+  L.bwd_total = o;
+  return DPA_OK;
+}
+
+template <class T> T* at(void* base, size_t off) { return reinterpret_cast<T*>(static_cast<char*>(base) + off); }
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int check_common(const dpa_args_t* a, Layout& L, DeviceInfo** dev) {
+  if (!a) return fail(DPA_ERR_ARG, "args is NULL");
+  int rc = make_layout(a->shape, L);
+  if (rc) return rc;
+  rc = device_info(dev);
+  if (rc) return rc;
+  const void* ptrs[] = {a->h_pair, a->labels_pair, a->signs_pair, a->h_ref_pol, a->h_ref_frz, a->labels_ref, a->W, a->W_ref};
+  const char* names[] = {"h_pair", "labels_pair", "signs_pair", "h_ref_pol", "h_ref_frz", "labels_ref", "W", "W_ref"};
+  for (int i = 0; i < 8; ++i) {
+    if (!ptrs[i]) return fail(DPA_ERR_ARG, "%s is NULL", names[i]);
+    if (!aligned16(ptrs[i])) return fail(DPA_ERR_ALIGN, "%s must be 16-byte aligned", names[i]);
+  }
+  if (!a->state || a->state_bytes < L.state_total) return fail(DPA_ERR_WORKSPACE, "state workspace: need %zu bytes, got %zu", L.state_total, a->state_bytes);
+  if (!aligned16(a->state) || (a->scratch && !aligned16(a->scratch))) return fail(DPA_ERR_ALIGN, "workspaces must be 16-byte aligned (256 recommended)");
+  return DPA_OK;
+}
+
+MetaArgs meta_args(const dpa_args_t* a, const Layout& L) {
+  MetaArgs m{};
+  m.labels_pair = a->labels_pair; m.signs_pair = a->signs_pair; m.labels_ref = a->labels_ref;
+  m.B = a->shape.B; m.T = a->shape.T; m.B_ref = a->shape.B_ref; m.T_ref = a->shape.T_ref; m.V = a->shape.V;
+  m.dense = (a->shape.flags & DPA_FLAG_DENSE) ? 1 : 0;
+  m.n_pos_pair = L.n_pos_pair; m.n_pos_ref = L.n_pos_ref; m.nblk_pair = L.nblk_pair; m.nblk_ref = L.nblk_ref;
+  m.cap_pair = L.cap_pair; m.cap_ref = L.cap_ref;
+  m.meta = at<DpaMeta>(a->state, L.meta); m.bitmap = at<unsigned>(a->state, L.bitmap);
+  m.block_counts = at<int>(a->state, L.block_counts);
+  m.src_pair = at<int>(a->state, L.src_pair); m.lab_pair = at<int>(a->state, L.lab_pair); m.col_pair = at<int>(a->state, L.col_pair);
+  m.src_ref = at<int>(a->state, L.src_ref); m.act_ref = at<int>(a->state, L.act_ref);
+  m.status = a->status;
+  return m;
+}
+
+int run_gather(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, void* scratch, size_t oHp, size_t oHf, cudaStream_t st) {
+  GatherArgs g{};
+  g.meta = at<DpaMeta>(a->state, L.meta);
+  g.src_pair = at<int>(a->state, L.src_pair); g.src_ref = at<int>(a->state, L.src_ref);
+  g.h_pair = static_cast<const __nv_bfloat16*>(a->h_pair);
+  g.h_ref_pol = static_cast<const __nv_bfloat16*>(a->h_ref_pol);
+  g.h_ref_frz = static_cast<const __nv_bfloat16*>(a->h_ref_frz);
+  g.Hp = at<__nv_bfloat16>(scratch, oHp); g.Hf = at<__nv_bfloat16>(scratch, oHf); g.H = a->shape.H;
+  ProfScope ps(PK_GATHER, 1, st);
+  gather_rows_kernel<<<d->sms * 8, 256, 0, st>>>(g);
+  LAUNCH_CHECK("gather_rows");
+  return DPA_OK;
+}
+
+template <bool ROUND>
+int run_forward_gemms(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, cudaStream_t st) {
+  const dpa_shape_t& s = a->shape;
+  const int cap_tot = L.cap_pair + L.cap_ref;
+  CUtensorMap tmHp, tmHpD, tmHf, tmW256, tmW128, tmWr128;
+  int rc;
+  if ((rc = make_operand_tmap(d, &tmHp, at<char>(a->scratch, L.f_Hp), KMAJOR, cap_tot, s.H, s.H, BM))) return rc;
+  if ((rc = make_operand_tmap(d, &tmHf, at<char>(a->scratch, L.f_Hf), KMAJOR, L.cap_ref, s.H, s.H, BM))) return rc;
+  if ((rc = make_operand_tmap(d, &tmW256, a->W, KMAJOR, s.V_local, s.H, s.H, kBnPair))) return rc;
+  if ((rc = make_operand_tmap(d, &tmW128, a->W, KMAJOR, s.V_local, s.H, s.H, kBnRef))) return rc;
+  if ((rc = make_operand_tmap(d, &tmWr128, a->W_ref, KMAJOR, s.V_local, s.H, s.H, kBnRef))) return rc;
+  tmHpD = tmHp;
+  const DpaMeta* meta = at<DpaMeta>(a->state, L.meta);
+  {
+    using Cfg = GemmCfg<kBnPair, false, KMAJOR, KMAJOR>;
+    using Epi = EpiStatsPair<kBnPair, ROUND>;
+    GemmWork w{meta, KIND_FWD_PAIR, 0, 0, 0, s.V_local, s.H, kTpuPair};
+    typename Epi::Params ep{at<int>(a->state, L.lab_pair), at<float4>(a->scratch, L.f_part_pair), L.cap_pair, s.V_local, s.v_offset};
+    ProfScope ps(PK_FWD_PAIR, 1, st);
+    if ((rc = launch_gemm<Cfg, Epi>(st, d->sms, tmHp, tmW256, tmHp, tmW256, w, ep, "fwd_pair"))) return rc;
+  }
+  {
+    using Cfg = GemmCfg<kBnRef, true, KMAJOR, KMAJOR>;
+    using Epi = EpiStatsRef<kBnRef, ROUND>;
+    GemmWork w{meta, KIND_FWD_REF, 0, 0, 0, s.V_local, s.H, kTpuRef};
+    typename Epi::Params ep{at<float4>(a->scratch, L.f_part_ref), at<float>(a->scratch, L.f_part_u), L.cap_ref, s.V_local};
+    ProfScope ps(PK_FWD_REF, 1, st);
+    if ((rc = launch_gemm<Cfg, Epi>(st, d->sms, tmHpD, tmW128, tmHf, tmWr128, w, ep, "fwd_ref"))) return rc;
+  }
+  return DPA_OK;
+}
+
+int run_merge(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, const float4* part_pair, const float4* part_ref,
+              const float* part_u, int n_pair, int n_ref, size_t stride_pair, size_t stride_ref, size_t stride_u, cudaStream_t st);
+
+}  // namespace
+
+// merge kernel with explicit strides lives here so that local partials and gathered shard records share it
+namespace dpa {
+struct MergeStrided {
+  const DpaMeta* meta;
+  const float4* part_pair; const float4* part_ref; const float* part_u;
+  int n_parts_pair, n_parts_ref;
+  size_t stride_pair, stride_ref, stride_u;     // element strides between partial records
+  float4* stats_pair; float4* stats_ref; float* stats_u;
+};
+__global__ void merge_strided_kernel(MergeStrided a) {
+  const int p0 = a.meta->p0, nr_pad = a.meta->n_tot - p0;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < p0 + nr_pad; r += gridDim.x * blockDim.x) {
+    if (r < p0) {
+      float m = -INFINITY;
+      for (int g = 0; g < a.n_parts_pair; ++g) m = fmaxf(m, a.part_pair[g * a.stride_pair + r].x);
+      float s = 0.f, zy = 0.f;
+      for (int g = 0; g < a.n_parts_pair; ++g) {
+        const float4 p = a.part_pair[g * a.stride_pair + r];
+        s += p.y * expf(p.x - m); zy += p.z;
+      }
+      a.stats_pair[r] = make_float4(m, s, zy, 0.f);
+    } else {
+      const int j = r - p0;
+      float mp = -INFINITY, mr = -INFINITY;
+      for (int g = 0; g < a.n_parts_ref; ++g) {
+        const float4 p = a.part_ref[g * a.stride_ref + j];
+        mp = fmaxf(mp, p.x); mr = fmaxf(mr, p.z);
+      }
+      float sp = 0.f, sr = 0.f, u = 0.f;
+      for (int g = 0; g < a.n_parts_ref; ++g) {
+        const float4 p = a.part_ref[g * a.stride_ref + j];
+        const float wr = expf(p.z - mr);
+        sp += p.y * expf(p.x - mp); sr += p.w * wr; u += a.part_u[g * a.stride_u + j] * wr;
+      }
+      a.stats_ref[j] = make_float4(mp, sp, mr, sr);
+      a.stats_u[j] = u;
+    }
+  }
+}
+}  // namespace dpa
+
+namespace {
+
+int run_merge(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, const float4* part_pair, const float4* part_ref,
+              const float* part_u, int n_pair, int n_ref, size_t stride_pair, size_t stride_ref, size_t stride_u, cudaStream_t st) {
+  MergeStrided m{at<DpaMeta>(a->state, L.meta), part_pair, part_ref, part_u, n_pair, n_ref, stride_pair, stride_ref, stride_u,
+                 at<float4>(a->state, L.stats_pair), at<float4>(a->state, L.stats_ref), at<float>(a->state, L.stats_u)};
+  ProfScope ps(PK_REDUCE, 1, st);
+  merge_strided_kernel<<<d->sms * 2, 256, 0, st>>>(m);
+  LAUNCH_CHECK("merge_partials");
+  return DPA_OK;
+}
+
+int run_finish(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, cudaStream_t st) {
+  const DpaMeta* meta = at<DpaMeta>(a->state, L.meta);
+  FinishArgs f{meta, at<float4>(a->state, L.stats_pair), at<float4>(a->state, L.stats_ref), at<float>(a->state, L.stats_u),
+               at<int>(a->state, L.act_ref), at<float>(a->state, L.lse_pair), at<float>(a->state, L.logp_pair),
+               at<float>(a->state, L.lse_ref_p), at<float>(a->state, L.lse_ref_r), at<float>(a->state, L.kl_row)};
+  ProfScope ps(PK_REDUCE, 3, st);
+  finish_rows_kernel<<<d->sms * 2, 256, 0, st>>>(f);
+  LAUNCH_CHECK("finish_rows");
+  PhraseArgs p{meta, at<int>(a->state, L.src_pair), at<int>(a->state, L.col_pair), at<float>(a->state, L.logp_pair),
+               at<float>(a->state, L.PN), a->shape.T};
+  phrase_sums_kernel<<<2 * a->shape.B, 256, 0, st>>>(p);
+  LAUNCH_CHECK("phrase_sums");
+  LossArgs l{meta, at<float>(a->state, L.PN), at<float>(a->state, L.kl_row), at<float>(a->state, L.sigma), a->losses,
+             a->shape.B, a->shape.B_ref, a->alpha};
+  loss_kernel<<<1, 1024, 0, st>>>(l);
+  LAUNCH_CHECK("loss");
+  return DPA_OK;
+}
+
+int forward_stats_impl(const dpa_args_t* a, cudaStream_t st, Layout& L, DeviceInfo** dev) {
+  int rc = check_common(a, L, dev);
+  if (rc) return rc;
+  DeviceInfo* d = *dev;
+  if (!a->scratch || a->scratch_bytes < L.fwd_total) return fail(DPA_ERR_WORKSPACE, "forward scratch: need %zu bytes, got %zu", L.fwd_total, a->scratch_bytes);
+  if (!a->losses || !a->status) return fail(DPA_ERR_ARG, "losses/status is NULL");
+  CUDA_TRY(cudaMemsetAsync(at<char>(a->state, L.meta), 0, L.block_counts - L.meta, st));   // DpaMeta + bitmap
+  MetaArgs m = meta_args(a, L);
+  const bool i64 = a->shape.index_dtype == DPA_I64;
+  const int nblk = L.nblk_pair + L.nblk_ref;
+  const int bm_grid = std::min((L.n_pos_pair + 255) / 256, d->sms * 4);
+  {
+  ProfScope ps(PK_META, 4, st);
+  if (i64) {
+    meta_bitmap_kernel<true><<<bm_grid, 256, 0, st>>>(m);
+    meta_count_kernel<true><<<nblk, kScanBlock, 0, st>>>(m);
+    meta_fill_kernel<true><<<nblk, kScanBlock, 0, st>>>(m);
+  } else {
+    meta_bitmap_kernel<false><<<bm_grid, 256, 0, st>>>(m);
+    meta_count_kernel<false><<<nblk, kScanBlock, 0, st>>>(m);
+    meta_fill_kernel<false><<<nblk, kScanBlock, 0, st>>>(m);
+  }
+  meta_pad_kernel<<<1, 256, 0, st>>>(m);
+  LAUNCH_CHECK("meta");
+  }
+  if ((rc = run_gather(a, L, d, a->scratch, L.f_Hp, L.f_Hf, st))) return rc;
+  rc = (a->shape.flags & DPA_FLAG_ROUND_LOGITS) ? run_forward_gemms<true>(a, L, d, st) : run_forward_gemms<false>(a, L, d, st);
+  if (rc) return rc;
+  return run_merge(a, L, d, at<float4>(a->scratch, L.f_part_pair), at<float4>(a->scratch, L.f_part_ref),
+                   at<float>(a->scratch, L.f_part_u), L.ng_pair, L.ng_ref, L.cap_pair, L.cap_ref, L.cap_ref, st);
+}
+
+template <bool ROUND>
+int run_backward(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, cudaStream_t st) {
+  const dpa_shape_t& s = a->shape;
+  const bool need_dw = (s.flags & DPA_FLAG_NEED_DW) != 0;
+  const int cap_tot = L.cap_pair + L.cap_ref;
+  const DpaMeta* meta = at<DpaMeta>(a->state, L.meta);
+  int rc;
+  CoefArgs c{meta, at<int>(a->state, L.col_pair), at<int>(a->state, L.act_ref), at<float>(a->state, L.sigma), a->d_loss,
+             at<float>(a->state, L.coef_pair), at<float>(a->state, L.coef_ref), s.B, s.B_ref, a->alpha};
+  {
+    ProfScope ps(PK_COEF, 1, st);
+    coef_kernel<<<d->sms * 2, 256, 0, st>>>(c);
+    LAUNCH_CHECK("coef");
+  }
+  if ((rc = run_gather(a, L, d, a->scratch, L.b_Hp, L.b_Hf, st))) return rc;
+  float* dW32 = need_dw ? at<float>(a->scratch, L.b_dW32) : nullptr;
+  {
+    ProfScope ps(PK_MISC, 0, st);
+    CUDA_TRY(cudaMemsetAsync(a->dH_pair, 0, (size_t)2 * s.B * s.T * s.H * 2, st));
+    CUDA_TRY(cudaMemsetAsync(a->dH_ref, 0, (size_t)s.B_ref * s.T_ref * s.H * 2, st));
+    if (need_dw) CUDA_TRY(cudaMemsetAsync(dW32, 0, (size_t)s.V_local * s.H * 4, st));
+  }
+
+  __nv_bfloat16* dz = at<__nv_bfloat16>(a->scratch, L.b_dz);
+  CUtensorMap tmHp, tmHf, tmW256, tmW128, tmWr128, tmDzK, tmWmn, tmDzMN, tmHpMN;
+  if ((rc = make_operand_tmap(d, &tmHp, at<char>(a->scratch, L.b_Hp), KMAJOR, cap_tot, s.H, s.H, BM))) return rc;
+  if ((rc = make_operand_tmap(d, &tmHf, at<char>(a->scratch, L.b_Hf), KMAJOR, L.cap_ref, s.H, s.H, BM))) return rc;
+  if ((rc = make_operand_tmap(d, &tmW256, a->W, KMAJOR, s.V_local, s.H, s.H, kBnPair))) return rc;
+  if ((rc = make_operand_tmap(d, &tmW128, a->W, KMAJOR, s.V_local, s.H, s.H, kBnRef))) return rc;
+  if ((rc = make_operand_tmap(d, &tmWr128, a->W_ref, KMAJOR, s.V_local, s.H, s.H, kBnRef))) return rc;
+  // dH = dZ[rows x V] * W[V x H]:  A = dz K-major (K = vocab), B = W MN-major (N = hidden contiguous)
+  if ((rc = make_operand_tmap(d, &tmDzK, dz, KMAJOR, L.chunk_rows, s.V_local, L.ldz, BM))) return rc;
+  if ((rc = make_operand_tmap(d, &tmWmn, a->W, MNMAJOR, s.H, s.V_local, s.H, 0))) return rc;
+  // dW = dZ^T[V x rows] * H[rows x H]: A = dz MN-major (M = vocab contiguous), B = packed hidden rows MN-major
+  if ((rc = make_operand_tmap(d, &tmDzMN, dz, MNMAJOR, s.V_local, L.chunk_rows, L.ldz, 0))) return rc;
+  if ((rc = make_operand_tmap(d, &tmHpMN, at<char>(a->scratch, L.b_Hp), MNMAJOR, s.H, cap_tot, s.H, 0))) return rc;
+
+  for (int ch = 0; ch < L.n_chunks; ++ch) {
+    {
+      using Cfg = GemmCfg<kBnPair, false, KMAJOR, KMAJOR>;
+      using Epi = EpiDzPair<kBnPair, ROUND>;
+      GemmWork w{meta, KIND_DZ_PAIR, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair};
+      typename Epi::Params ep{at<int>(a->state, L.lab_pair), at<float>(a->state, L.lse_pair), at<float>(a->state, L.coef_pair),
+                              dz, L.ldz, ch * L.chunk_rows, s.V_local, s.v_offset};
+      ProfScope ps(PK_DZ_PAIR, 1, st);
+      if ((rc = launch_gemm<Cfg, Epi>(st, d->sms, tmHp, tmW256, tmHp, tmW256, w, ep, "dz_pair"))) return rc;
+    }
+    {
+      using Cfg = GemmCfg<kBnRef, true, KMAJOR, KMAJOR>;
+      using Epi = EpiDzRef<kBnRef, ROUND>;
+      GemmWork w{meta, KIND_DZ_REF, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuRef};
+      typename Epi::Params ep{meta, at<float>(a->state, L.lse_ref_p), at<float>(a->state, L.lse_ref_r), at<float>(a->state, L.coef_ref),
+                              dz, L.ldz, ch * L.chunk_rows, s.V_local};
+      ProfScope ps(PK_DZ_REF, 1, st);
+      if ((rc = launch_gemm<Cfg, Epi>(st, d->sms, tmHp, tmW128, tmHf, tmWr128, w, ep, "dz_ref"))) return rc;
+    }
+    {
+      using Cfg = GemmCfg<256, false, KMAJOR, MNMAJOR>;
+      using Epi = EpiStoreRows<256>;
+      GemmWork w{meta, KIND_DH, ch, L.chunk_rows, 0, s.H, s.V_local, 1};
+      typename Epi::Params ep{meta, at<int>(a->state, L.src_pair), at<int>(a->state, L.src_ref),
+                              static_cast<__nv_bfloat16*>(a->dH_pair), static_cast<__nv_bfloat16*>(a->dH_ref), s.H};
+      ProfScope ps(PK_DH, 1, st);
+      if ((rc = launch_gemm<Cfg, Epi>(st, d->sms, tmDzK, tmWmn, tmDzK, tmWmn, w, ep, "dH"))) return rc;
+    }
+    if (need_dw) {
+      using Cfg = GemmCfg<256, false, MNMAJOR, MNMAJOR>;
+      using Epi = EpiAccumF32<256>;
+      GemmWork w{meta, KIND_DW, ch, L.chunk_rows, s.V_local, s.H, 0, 1};
+      typename Epi::Params ep{dW32, s.H, s.V_local, s.H, 1};
+      ProfScope ps(PK_DW, 1, st);
+      if ((rc = launch_gemm<Cfg, Epi>(st, d->sms, tmDzMN, tmHpMN, tmDzMN, tmHpMN, w, ep, "dW"))) return rc;
+    }
+  }
+  if (need_dw) {
+    const size_t n = (size_t)s.V_local * s.H;
+    ProfScope ps(PK_MISC, 1, st);
+    f32_to_bf16_kernel<<<d->sms * 8, 256, 0, st>>>(dW32, static_cast<__nv_bfloat16*>(a->dW), n);
+    LAUNCH_CHECK("dW convert");
+  }
+  return DPA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dpa_version(void) { return DPA_ABI_VERSION; }
+const char* dpa_last_error(void) { return g_err; }
+
+int dpa_query_workspace(const dpa_shape_t* shape, dpa_workspace_t* out) {
+  if (!shape || !out) return fail(DPA_ERR_ARG, "NULL argument");
+  Layout L;
+  int rc = make_layout(*shape, L);
+  if (rc) return rc;
+  out->state_bytes = L.state_total; out->fwd_bytes = L.fwd_total; out->bwd_bytes = L.bwd_total;
+  return DPA_OK;
+}
+
+int dpa_forward_stats(const dpa_args_t* a, void* stream) {
+  Layout L; DeviceInfo* d;
+  return forward_stats_impl(a, static_cast<cudaStream_t>(stream), L, &d);
+}
+
+int dpa_row_stats_view(const dpa_args_t* a, void** ptr, size_t* bytes) {
+  if (!a || !ptr || !bytes) return fail(DPA_ERR_ARG, "NULL argument");
+  Layout L;
+  int rc = make_layout(a->shape, L);
+  if (rc) return rc;
+  *ptr = at<char>(a->state, L.stats_pair); *bytes = L.row_stats_bytes;
+  return DPA_OK;
+}
+
+int dpa_forward_finish(const dpa_args_t* a, const void* gathered, int n_shards, void* stream) {
+  Layout L; DeviceInfo* d;
+  int rc = check_common(a, L, &d);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (gathered && n_shards > 1) {
+    // records of all vocab shards, each laid out like this rank's [stats_pair | stats_ref | stats_u]
+    const char* g = static_cast<const char*>(gathered);
+    const size_t rec = L.row_stats_bytes;
+    if (rec % 16) return fail(DPA_ERR_BAD_SHAPE, "row-stats record not 16-byte sized");
+    rc = run_merge(a, L, d, reinterpret_cast<const float4*>(g), reinterpret_cast<const float4*>(g + (L.stats_ref - L.stats_pair)),
+                   reinterpret_cast<const float*>(g + (L.stats_u - L.stats_pair)), n_shards, n_shards, rec / 16, rec / 16, rec / 4, st);
+    if (rc) return rc;
+  }
+  return run_finish(a, L, d, st);
+}
+
+int dpa_forward(const dpa_args_t* a, void* stream) {
+  Layout L; DeviceInfo* d;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = forward_stats_impl(a, st, L, &d);
+  if (rc) return rc;
+  return run_finish(a, L, d, st);
+}
+
+int dpa_backward(const dpa_args_t* a, void* stream) {
+  Layout L; DeviceInfo* d;
+  int rc = check_common(a, L, &d);
+  if (rc) return rc;
+  if (!a->scratch || a->scratch_bytes < L.bwd_total) return fail(DPA_ERR_WORKSPACE, "backward scratch: need %zu bytes, got %zu", L.bwd_total, a->scratch_bytes);
+  if (!a->dH_pair || !a->dH_ref) return fail(DPA_ERR_ARG, "dH_pair/dH_ref is NULL");
+  if ((a->shape.flags & DPA_FLAG_NEED_DW) && !a->dW) return fail(DPA_ERR_ARG, "DPA_FLAG_NEED_DW set but dW is NULL");
+  if (!aligned16(a->dH_pair) || !aligned16(a->dH_ref) || (a->dW && !aligned16(a->dW))) return fail(DPA_ERR_ALIGN, "gradient buffers must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return (a->shape.flags & DPA_FLAG_ROUND_LOGITS) ? run_backward<true>(a, L, d, st) : run_backward<false>(a, L, d, st);
+}
+
+int dpa_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = on != 0;
+  return DPA_OK;
+}
+
+// Synchronises on the recorded events. ms[k] / launches[k] are summed per kernel class (see dpa_profile_kind_name).
+int dpa_profile_collect(double* ms, int* launches, int n) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (int i = 0; i < n; ++i) { ms[i] = 0.0; launches[i] = 0; }
+  for (auto& sp : g_spans) {
+    float t = 0.f;
+    cudaEventSynchronize(sp.b);
+    cudaEventElapsedTime(&t, sp.a, sp.b);
+    if (sp.kind < n) { ms[sp.kind] += t; launches[sp.kind] += sp.launches; }
+    cudaEventDestroy(sp.a); cudaEventDestroy(sp.b);
+  }
+  g_spans.clear();
+  return PK_COUNT;
+}
+
+const char* dpa_profile_kind_name(int k) {
+  static const char* names[PK_COUNT] = {"meta", "gather", "fwd_pair", "fwd_ref", "reduce", "coef", "dz_pair", "dz_ref", "dH", "dW", "misc"};
+  return (k >= 0 && k < PK_COUNT) ? names[k] : "";
+}
+
+int dpa_debug_gemm(const void* A, const void* B, float* D, int M, int N, int K, int a_major, int b_major, int bn, void* stream) {
+  DeviceInfo* d;
+  int rc = device_info(&d);
+  if (rc) return rc;
+  if (N % 32 || K % 8 || M % 8) return fail(DPA_ERR_BAD_SHAPE, "debug gemm: N%%32, K%%8, M%%8 required");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUtensorMap tmA, tmB;
+  if ((rc = make_operand_tmap(d, &tmA, A, a_major, M, K, a_major == KMAJOR ? K : M, BM))) return rc;
+  if ((rc = make_operand_tmap(d, &tmB, B, b_major, N, K, b_major == KMAJOR ? K : N, bn))) return rc;
+  GemmWork w{nullptr, KIND_STATIC, 0, 0, M, N, K, 1};
+#define DBG_CASE(BN_, AM, BMJ)                                                                        \
+  if (bn == BN_ && a_major == AM && b_major == BMJ) {                                                 \
+    using Cfg = GemmCfg<BN_, false, AM, BMJ>;                                                         \
+    using Epi = EpiAccumF32<BN_>;                                                                     \
+    typename Epi::Params ep{D, N, M, N, 0};                                                           \
+    return launch_gemm<Cfg, Epi>(st, d->sms, tmA, tmB, tmA, tmB, w, ep, "debug_gemm");                \
+  }
+  DBG_CASE(256, KMAJOR, KMAJOR)
+  DBG_CASE(128, KMAJOR, KMAJOR)
+  DBG_CASE(256, KMAJOR, MNMAJOR)
+  DBG_CASE(256, MNMAJOR, MNMAJOR)
+  DBG_CASE(256, MNMAJOR, KMAJOR)
+#undef DBG_CASE
+  return fail(DPA_ERR_ARG, "debug gemm: unsupported (bn=%d, a_major=%d, b_major=%d)", bn, a_major, b_major);
+}
+
+}  // extern "C"

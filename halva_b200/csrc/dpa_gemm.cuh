@@ -1,0 +1,513 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a with pluggable fused epilogues.
+//
+//   D[128 x BN] (+)= A[128 x K] * B[BN x K]^T      bf16 operands, fp32 accumulators in TMEM
+//
+//   warp 0 (one lane)  TMA producer: cp.async.bulk.tensor -> 128B-swizzled smem ring (mbarrier full/empty)
+//   warp 1 (one lane)  tcgen05.mma issuer; tcgen05.commit frees smem slots and publishes accumulators
+//   warp 2             TMEM allocator (all 512 columns: two accumulator stages)
+//   warps 4..7         epilogue: tcgen05.ld (thread == accumulator row) -> fused maths -> HBM
+//
+// The DPA loss uses it six ways (see dpa_api.cu): forward row statistics for pair rows and for
+// reference-sample rows (DUAL: policy and frozen-model logits of the same tile side by side in TMEM),
+// the recompute pass that turns logits into dLogits, and the two backward GEMMs dH = dZ*W, dW = dZ^T*H.
+// A work "unit" is (row tile, group of consecutive column tiles); row counts live in device memory
+// (DpaMeta) so that nothing on the path needs a host synchronisation.
+#pragma once
+#include "dpa_ptx.cuh"
+
+namespace dpa {
+
+constexpr int BM = 128;      // rows per tile == TMEM lanes == epilogue threads
+constexpr int BK = 64;       // K per smem stage: 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;   // K per tcgen05.mma (bf16)
+constexpr int kNumThreads = 256;
+constexpr int kEpiWarp0 = 4;
+constexpr int kSuperM = 16;  // row tiles per L2 super-block of the unit order
+
+enum : int { KMAJOR = 0, MNMAJOR = 1 };
+
+// Device-resident bookkeeping written by the metadata kernels (dpa_kernels.cu). All int32.
+struct DpaMeta {
+  int n_pair;    // active pair rows (packed order: sequence-major, pos sequences first)
+  int n_ref;     // active reference-sample rows
+  int p0;        // round_up(n_pair, 128): first packed row of the reference-sample segment
+  int n_tot;     // p0 + round_up(n_ref, 128): padded rows of the packed policy space
+  int K;         // phrase columns (K_pos == K_neg)
+  int K_pos, K_neg;
+  int status;    // 0 = ok, else DPA_STATUS_* bits
+  int pad[8];
+};
+
+enum : int {
+  KIND_STATIC = 0,   // debug GEMM: static M
+  KIND_FWD_PAIR,     // rows [0, p0)
+  KIND_FWD_REF,      // rows [p0, n_tot) of the policy buffer + rows [0, ..) of the frozen buffer
+  KIND_DZ_PAIR,      // chunk ∩ [0, p0)
+  KIND_DZ_REF,       // chunk ∩ [p0, n_tot)
+  KIND_DH,           // chunk rows x H, K = V
+  KIND_DW,           // V x H, K = chunk rows
+};
+
+struct GemmWork {
+  const DpaMeta* meta;
+  int kind;
+  int chunk;           // backward chunk index
+  int chunk_rows;      // rows per backward chunk (multiple of 128)
+  int m_static;        // KIND_STATIC / KIND_DW: M extent
+  int n_cols;          // N extent
+  int k_static;        // K extent unless KIND_DW
+  int tiles_per_unit;  // consecutive column tiles per work unit
+};
+
+struct TileRange {
+  int m_tiles;   // row tiles of this launch
+  int a_row0;    // A  row coordinate of tile 0
+  int a2_row0;   // A2 row coordinate of tile 0 (DUAL)
+  int e_row0;    // epilogue's logical row of tile 0
+  int k_blocks;  // BK-blocks along K
+  int a_k0, b_k0;
+};
+
+__device__ __forceinline__ TileRange compute_range(const GemmWork& w) {
+  TileRange r;
+  r.a2_row0 = 0; r.a_k0 = 0; r.b_k0 = 0;
+  r.k_blocks = (w.k_static + BK - 1) / BK;
+  if (w.kind == KIND_STATIC) {
+    r.m_tiles = (w.m_static + BM - 1) / BM; r.a_row0 = 0; r.e_row0 = 0;
+    return r;
+  }
+  const int p0 = w.meta->p0, n_tot = w.meta->n_tot;
+  const int c_lo = w.chunk * w.chunk_rows, c_hi = c_lo + w.chunk_rows;
+  int lo = 0, hi = 0;
+  switch (w.kind) {
+    case KIND_FWD_PAIR: lo = 0; hi = p0; r.a_row0 = 0; r.e_row0 = 0; break;
+    case KIND_FWD_REF: lo = p0; hi = n_tot; r.a_row0 = p0; r.a2_row0 = 0; r.e_row0 = 0; break;
+    case KIND_DZ_PAIR: lo = c_lo; hi = min(c_hi, p0); r.a_row0 = lo; r.e_row0 = lo; break;
+    case KIND_DZ_REF: lo = max(c_lo, p0); hi = min(c_hi, n_tot); r.a_row0 = lo; r.a2_row0 = lo - p0; r.e_row0 = lo; break;
+    case KIND_DH: lo = c_lo; hi = min(c_hi, n_tot); r.a_row0 = 0; r.e_row0 = lo; break;
+    case KIND_DW: {
+      lo = c_lo; hi = min(c_hi, n_tot);
+      const int rows = max(hi - lo, 0);
+      r.m_tiles = rows > 0 ? (w.m_static + BM - 1) / BM : 0;
+      r.a_row0 = 0; r.e_row0 = 0; r.k_blocks = rows / BK; r.a_k0 = 0; r.b_k0 = lo;
+      return r;
+    }
+  }
+  r.m_tiles = max(hi - lo, 0) / BM;
+  return r;
+}
+
+template <int BN_, bool DUAL_, int AMAJ_, int BMAJ_>
+struct GemmCfg {
+  static constexpr int BN = BN_;
+  static constexpr bool DUAL = DUAL_;
+  static constexpr int AMAJ = AMAJ_, BMAJ = BMAJ_;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (DUAL ? 2 : 1);
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;   // 4 x 48 KiB or 3 x 64 KiB
+  static constexpr int ACC_COLS = DUAL ? 2 * BN : BN;          // TMEM columns per accumulator stage
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(2 * ACC_COLS <= 512, "two accumulator stages must fit TMEM");
+  static_assert(BN % 64 == 0 && BN <= 256, "BN");
+};
+
+// issue the TMA loads of one operand tile for one K block
+template <int MAJ, int ROWS>
+__device__ __forceinline__ void load_operand(uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int row, int k) {
+  if constexpr (MAJ == KMAJOR) {
+    tma_load_2d(dst, tm, bar, k, row);                       // box {64 k, ROWS}
+  } else {
+#pragma unroll
+    for (int j = 0; j < ROWS / 64; ++j)                        // box {64 mn, 64 k}: [atom][k][64 mn]
+      tma_load_2d(dst + j * (BK * 128), tm, bar, row + j * 64, k);
+  }
+}
+template <int MAJ>
+__device__ __forceinline__ uint64_t operand_desc(uint32_t saddr, int kstep) {
+  if constexpr (MAJ == KMAJOR)     // rows of 128 B, 8-row swizzle atoms 1024 B apart; K advances inside the row
+    return make_smem_desc_sw128(saddr + kstep * (UMMA_K * 2), 0, 1024);
+  else                             // atoms [64 mn x 8 k] 1024 B apart along K, BK*128 B apart along MN
+    return make_smem_desc_sw128(saddr + kstep * (UMMA_K * 128), BK * 128, 1024);
+}
+
+template <class Cfg, class Epi>
+__global__ void __launch_bounds__(kNumThreads, 1)
+dpa_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                const GemmWork work, const typename Epi::Params ep) {
+  constexpr int BN = Cfg::BN, STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + STAGES * Cfg::A_BYTES;
+  uint8_t* sA2 = sB + STAGES * Cfg::B_BYTES;
+  uint8_t* sB2 = sA2 + (Cfg::DUAL ? STAGES * Cfg::A_BYTES : 0);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const TileRange tr = compute_range(work);
+  const int n_tiles = (work.n_cols + BN - 1) / BN;
+  const int tpu = work.tiles_per_unit;
+  const int n_groups = (n_tiles + tpu - 1) / tpu;
+  const int n_units = tr.k_blocks > 0 ? tr.m_tiles * n_groups : 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], BM); }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
+    if (Cfg::DUAL) { tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); }
+  }
+  if (warp == 2) { tmem_alloc<1>(tmem_slot, 512); tmem_relinquish<1>(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // unit -> (row tile, column group): super-blocks of kSuperM row tiles walk the column groups together
+  auto decode = [&](int u, int& mt, int& ng) {
+    const int per_sb = kSuperM * n_groups;
+    const int sb = u / per_sb, r = u - sb * per_sb;
+    const int sb_m = min(kSuperM, tr.m_tiles - sb * kSuperM);
+    ng = r / sb_m;
+    mt = sb * kSuperM + (r - ng * sb_m);
+  };
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------- TMA producer
+    int st = 0; uint32_t ph = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      int mt, ng; decode(u, mt, ng);
+      const int nt_end = min((ng + 1) * tpu, n_tiles);
+      for (int nt = ng * tpu; nt < nt_end; ++nt) {
+        for (int kb = 0; kb < tr.k_blocks; ++kb) {
+          mbar_wait(&empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&full[st], Cfg::STAGE_BYTES);
+          load_operand<Cfg::AMAJ, BM>(sA + st * Cfg::A_BYTES, &tmA, &full[st], tr.a_row0 + mt * BM, tr.a_k0 + kb * BK);
+          load_operand<Cfg::BMAJ, BN>(sB + st * Cfg::B_BYTES, &tmB, &full[st], nt * BN, tr.b_k0 + kb * BK);
+          if constexpr (Cfg::DUAL) {
+            load_operand<Cfg::AMAJ, BM>(sA2 + st * Cfg::A_BYTES, &tmA2, &full[st], tr.a2_row0 + mt * BM, tr.a_k0 + kb * BK);
+            load_operand<Cfg::BMAJ, BN>(sB2 + st * Cfg::B_BYTES, &tmB2, &full[st], nt * BN, tr.b_k0 + kb * BK);
+          }
+          if (++st == STAGES) { st = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------- MMA issuer
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, Cfg::AMAJ, Cfg::BMAJ);
+    int st = 0; uint32_t ph = 0; uint32_t it = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      int mt, ng; decode(u, mt, ng);
+      const int nt_end = min((ng + 1) * tpu, n_tiles);
+      for (int nt = ng * tpu; nt < nt_end; ++nt, ++it) {
+        const uint32_t as = it & 1, aph = (it >> 1) & 1;
+        mbar_wait(&tempty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + as * Cfg::ACC_COLS;
+        for (int kb = 0; kb < tr.k_blocks; ++kb) {
+          mbar_wait(&full[st], ph);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(sA + st * Cfg::A_BYTES), b0 = smem_u32(sB + st * Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_bf16<1>(acc, operand_desc<Cfg::AMAJ>(a0, k), operand_desc<Cfg::BMAJ>(b0, k), idesc, (kb | k) != 0);
+          if constexpr (Cfg::DUAL) {
+            const uint32_t a2 = smem_u32(sA2 + st * Cfg::A_BYTES), b2 = smem_u32(sB2 + st * Cfg::B_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_bf16<1>(acc + BN, operand_desc<Cfg::AMAJ>(a2, k), operand_desc<Cfg::BMAJ>(b2, k), idesc, (kb | k) != 0);
+          }
+          umma_commit<1>(&empty[st]);                 // smem slot reusable once these MMAs retire
+          if (kb == tr.k_blocks - 1) umma_commit<1>(&tfull[as]);
+          if (++st == STAGES) { st = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ------------------------------------------------------------- epilogue (thread == accumulator row)
+    const int q = warp & 3;                          // TMEM lane quadrant this warp may read
+    const int trow = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + (uint32_t(q * 32) << 16);
+    uint32_t it = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      int mt, ng; decode(u, mt, ng);
+      typename Epi::State s;
+      Epi::unit_begin(ep, s, tr.e_row0 + mt * BM + trow, mt * BM + trow);
+      const int nt_end = min((ng + 1) * tpu, n_tiles);
+      for (int nt = ng * tpu; nt < nt_end; ++nt, ++it) {
+        const uint32_t as = it & 1, aph = (it >> 1) & 1;
+        mbar_wait(&tfull[as], aph);
+        tc_fence_after();
+        Epi::tile(ep, s, lane_base + as * Cfg::ACC_COLS, nt * BN);
+        tc_fence_before();
+        mbar_arrive(&tempty[as]);
+      }
+      Epi::unit_end(ep, s, ng);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
+}
+
+// =====================================================================================================
+// Epilogues. `tile(ep, s, taddr, col0)`: taddr = TMEM address of this thread's lane, accumulator column 0.
+// =====================================================================================================
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+__device__ __forceinline__ void load_chunk(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  __syncwarp();                      // tcgen05.ld is warp-collective (.sync.aligned)
+  tmem_ld_32x32(taddr, r);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+template <bool ROUND>
+__device__ __forceinline__ void round_chunk(float (&v)[32]) {
+  if constexpr (ROUND) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = bf16_round_f32(v[i]);   // nn.Linear emits bf16 logits (modeling_llama.py:1028)
+  }
+}
+// online (max, sum-exp) update over one 32-column chunk; returns the rescale factor applied to the old sum
+__device__ __forceinline__ float online_update(const float (&v)[32], int nvalid, float& m, float& ssum, float (&e)[32]) {
+  float cmax = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) cmax = fmaxf(cmax, i < nvalid ? v[i] : -INFINITY);
+  const float m_new = fmaxf(m, cmax);
+  const float scale = fast_exp2((m - m_new) * kLog2e);            // m = -inf on first use -> 0
+  const float mb = m_new * kLog2e;
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    e[i] = i < nvalid ? fast_exp2(fmaf(v[i], kLog2e, -mb)) : 0.f;
+    acc += e[i];
+  }
+  ssum = fmaf(ssum, scale, acc);
+  m = m_new;
+  return scale;
+}
+
+// ---- forward statistics, pair rows: per (row, column group) partial {max, sum-exp, target logit}
+template <int BN, bool ROUND>
+struct EpiStatsPair {
+  struct Params {
+    const int* labels;     // packed row -> target id (global vocab id)
+    float4* part;          // [n_groups][row_cap]
+    int row_cap, v_local, v_offset;
+  };
+  struct State { float m, s, zy; int yloc; int row; };
+  __device__ static void unit_begin(const Params& p, State& s, int erow, int) {
+    s.m = -INFINITY; s.s = 0.f; s.zy = 0.f; s.row = erow;
+    s.yloc = p.labels[erow] - p.v_offset;
+  }
+  __device__ static void tile(const Params& p, State& s, uint32_t taddr, int col0) {
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int cbase = col0 + c * 32;
+      if (cbase >= p.v_local) break;
+      float v[32], e[32];
+      load_chunk(taddr + c * 32, v);
+      round_chunk<ROUND>(v);
+      online_update(v, p.v_local - cbase, s.m, s.s, e);
+      if ((unsigned)(s.yloc - cbase) < 32u) {
+        const int j = s.yloc - cbase;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) s.zy = (i == j) ? v[i] : s.zy;
+      }
+    }
+  }
+  __device__ static void unit_end(const Params& p, State& s, int ng) {
+    p.part[(size_t)ng * p.row_cap + s.row] = make_float4(s.m, s.s, s.zy, 0.f);
+  }
+};
+
+// ---- forward statistics, reference-sample rows (DUAL): policy logits in columns [0,BN), frozen in [BN,2BN)
+//      partial {m_p, s_p, m_r, s_r} and u = sum_v e^{z_r - m_r} (z_r - z_p)
+template <int BN, bool ROUND>
+struct EpiStatsRef {
+  struct Params {
+    float4* part;          // [n_groups][row_cap]
+    float* part_u;         // [n_groups][row_cap]
+    int row_cap, v_local;
+  };
+  struct State { float mp, sp, mr, sr, u; int row; };
+  __device__ static void unit_begin(const Params&, State& s, int erow, int) {
+    s.mp = -INFINITY; s.sp = 0.f; s.mr = -INFINITY; s.sr = 0.f; s.u = 0.f; s.row = erow;
+  }
+  __device__ static void tile(const Params& p, State& s, uint32_t taddr, int col0) {
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int cbase = col0 + c * 32;
+      if (cbase >= p.v_local) break;
+      const int nvalid = p.v_local - cbase;
+      float vp[32], vr[32], e[32];
+      load_chunk(taddr + c * 32, vp);
+      round_chunk<ROUND>(vp);
+      online_update(vp, nvalid, s.mp, s.sp, e);
+      load_chunk(taddr + BN + c * 32, vr);
+      round_chunk<ROUND>(vr);
+      const float scale = online_update(vr, nvalid, s.mr, s.sr, e);
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc = fmaf(e[i], vr[i] - vp[i], acc);   // e[i] == 0 beyond nvalid
+      s.u = fmaf(s.u, scale, acc);
+    }
+  }
+  __device__ static void unit_end(const Params& p, State& s, int ng) {
+    p.part[(size_t)ng * p.row_cap + s.row] = make_float4(s.mp, s.sp, s.mr, s.sr);
+    p.part_u[(size_t)ng * p.row_cap + s.row] = s.u;
+  }
+};
+
+__device__ __forceinline__ void store_bf16_chunk(__nv_bfloat16* dst, const float (&d)[32]) {
+  uint4* o = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    o[i] = make_uint4(pack_bf16x2(d[8 * i + 0], d[8 * i + 1]), pack_bf16x2(d[8 * i + 2], d[8 * i + 3]),
+                      pack_bf16x2(d[8 * i + 4], d[8 * i + 5]), pack_bf16x2(d[8 * i + 6], d[8 * i + 7]));
+}
+
+// ---- backward recompute, pair rows: dz = coef * (onehot(y) - softmax(z))  -> bf16 scratch [chunk_rows][ldz]
+template <int BN, bool ROUND>
+struct EpiDzPair {
+  struct Params {
+    const int* labels; const float* lse; const float* coef;   // indexed by packed row
+    __nv_bfloat16* dz; int ldz; int chunk_row0; int v_local, v_offset;
+  };
+  struct State { float nl, c; int yloc; __nv_bfloat16* out; };
+  __device__ static void unit_begin(const Params& p, State& s, int erow, int) {
+    s.nl = -p.lse[erow] * kLog2e; s.c = p.coef[erow];
+    s.yloc = p.labels[erow] - p.v_offset;
+    s.out = p.dz + (size_t)(erow - p.chunk_row0) * p.ldz;
+  }
+  __device__ static void tile(const Params& p, State& s, uint32_t taddr, int col0) {
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int cbase = col0 + c * 32;
+      if (cbase >= p.ldz) break;
+      float v[32], d[32];
+      load_chunk(taddr + c * 32, v);
+      round_chunk<ROUND>(v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) d[i] = -s.c * fast_exp2(fmaf(v[i], kLog2e, s.nl));
+      if ((unsigned)(s.yloc - cbase) < 32u) {
+        const int j = s.yloc - cbase;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) d[i] += (i == j) ? s.c : 0.f;
+      }
+      store_bf16_chunk(s.out + cbase, d);
+    }
+  }
+  __device__ static void unit_end(const Params&, State&, int) {}
+};
+
+// ---- backward recompute, reference-sample rows (DUAL): dz = coef * (softmax(z_pol) - softmax(z_frozen))
+template <int BN, bool ROUND>
+struct EpiDzRef {
+  struct Params {
+    const DpaMeta* meta;
+    const float* lse_p; const float* lse_r; const float* coef;   // indexed by reference row j
+    __nv_bfloat16* dz; int ldz; int chunk_row0; int v_local;
+  };
+  struct State { float nlp, nlr, c; __nv_bfloat16* out; };
+  __device__ static void unit_begin(const Params& p, State& s, int erow, int) {
+    // erow is the packed policy row; the reference-sample arrays are indexed from the segment start p0
+    const int j = erow - p.meta->p0;
+    s.out = p.dz + (size_t)(erow - p.chunk_row0) * p.ldz;
+    s.nlp = -p.lse_p[j] * kLog2e; s.nlr = -p.lse_r[j] * kLog2e; s.c = p.coef[j];
+  }
+  __device__ static void tile(const Params& p, State& s, uint32_t taddr, int col0) {
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int cbase = col0 + c * 32;
+      if (cbase >= p.ldz) break;
+      float vp[32], vr[32], d[32];
+      load_chunk(taddr + c * 32, vp);
+      round_chunk<ROUND>(vp);
+      load_chunk(taddr + BN + c * 32, vr);
+      round_chunk<ROUND>(vr);
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        d[i] = s.c * (fast_exp2(fmaf(vp[i], kLog2e, s.nlp)) - fast_exp2(fmaf(vr[i], kLog2e, s.nlr)));
+      store_bf16_chunk(s.out + cbase, d);
+    }
+  }
+  __device__ static void unit_end(const Params&, State&, int) {}
+};
+
+// ---- dH = dZ * W: fp32 accumulators -> bf16 rows scattered to their source positions
+template <int BN>
+struct EpiStoreRows {
+  struct Params {
+    const DpaMeta* meta;
+    const int* src_pair; const int* src_ref;       // packed row -> flat (sequence*T + t) row of the dense tensors
+    __nv_bfloat16* dH_pair; __nv_bfloat16* dH_ref; int H;
+  };
+  struct State { __nv_bfloat16* out; };
+  __device__ static void unit_begin(const Params& p, State& s, int erow, int) {
+    const int p0 = p.meta->p0;
+    s.out = nullptr;
+    if (erow < p0) { if (erow < p.meta->n_pair) s.out = p.dH_pair + (size_t)p.src_pair[erow] * p.H; }
+    else { const int j = erow - p0; if (j < p.meta->n_ref) s.out = p.dH_ref + (size_t)p.src_ref[j] * p.H; }
+  }
+  __device__ static void tile(const Params& p, State& s, uint32_t taddr, int col0) {
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int cbase = col0 + c * 32;
+      if (cbase >= p.H) break;
+      float v[32];
+      load_chunk(taddr + c * 32, v);                     // warp-collective: every lane loads
+      if (s.out) store_bf16_chunk(s.out + cbase, v);     // H % 32 == 0 is checked on the host
+    }
+  }
+  __device__ static void unit_end(const Params&, State&, int) {}
+};
+
+// ---- dW += dZ^T * H: fp32 accumulate into the [V][ld] fp32 buffer (thread == vocabulary row)
+template <int BN>
+struct EpiAccumF32 {
+  struct Params { float* out; int ld; int m_extent; int n_extent; int accumulate; };
+  struct State { float* out; };
+  __device__ static void unit_begin(const Params& p, State& s, int, int trow_global) {
+    s.out = trow_global < p.m_extent ? p.out + (size_t)trow_global * p.ld : nullptr;
+  }
+  __device__ static void tile(const Params& p, State& s, uint32_t taddr, int col0) {
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int cbase = col0 + c * 32;
+      if (cbase >= p.n_extent) break;
+      float v[32];
+      load_chunk(taddr + c * 32, v);
+      if (s.out) {
+        float4* o = reinterpret_cast<float4*>(s.out + cbase);
+        if (p.accumulate) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 t = o[i];
+            t.x += v[4 * i]; t.y += v[4 * i + 1]; t.z += v[4 * i + 2]; t.w += v[4 * i + 3];
+            o[i] = t;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+      }
+    }
+  }
+  __device__ static void unit_end(const Params&, State&, int) {}
+};
+
+}  // namespace dpa

@@ -1,0 +1,381 @@
+// Integer / bookkeeping / reduction kernels around the GEMMs of the DPA-loss path.
+// HBM-bound byte and index work: coalesced grid-stride loops, no tensor cores.
+#pragma once
+#include "dpa_gemm.cuh"
+#include "../../include/halva_dpa.h"
+
+namespace dpa {
+
+constexpr int IGNORE_INDEX = -100;          // /root/reference/llava/constants.py:7
+constexpr int kMaxSign = 255;               // phrase ids are small: mask_tag counts <MASK> spans (train_halva.py:275-332)
+constexpr int kScanBlock = 1024;            // positions per scan block
+constexpr int kNoCol = 0xFFFF;
+
+template <bool I64>
+__device__ __forceinline__ int load_index(const void* p, size_t i) {
+  if constexpr (I64) return (int)reinterpret_cast<const long long*>(p)[i];
+  else return reinterpret_cast<const int*>(p)[i];
+}
+
+struct MetaArgs {
+  const void* labels_pair; const void* signs_pair; const void* labels_ref;
+  int B, T, B_ref, T_ref, V, dense;
+  int n_pos_pair;          // 2B * (T-1)
+  int n_pos_ref;           // B_ref * (T_ref-1)
+  int nblk_pair, nblk_ref; // scan blocks
+  int cap_pair, cap_ref;
+  // state
+  DpaMeta* meta;
+  unsigned* bitmap;        // [2][8]  presence of phrase ids per half (pos / neg)
+  int* block_counts;       // [nblk_pair + nblk_ref]
+  int* src_pair; int* lab_pair; int* col_pair;   // col_pair: (sequence << 16) | column (kNoCol = none)
+  int* src_ref; int* act_ref;
+  int* status;             // user-visible [8]
+};
+
+// ---- pass 0: reset bookkeeping, then presence bitmap of phrase ids over signs[:, 1:] of each half
+//      (halva_trainer.py:560 maps -100 -> 0; :412 takes the sorted unique over the whole half batch)
+template <bool I64>
+__global__ void meta_bitmap_kernel(MetaArgs a) {
+  __shared__ unsigned bm[16];
+  __shared__ int bad;
+  if (threadIdx.x < 16) bm[threadIdx.x] = 0;
+  if (threadIdx.x == 0) bad = 0;
+  __syncthreads();
+  const int Tm = a.T - 1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_pos_pair; i += gridDim.x * blockDim.x) {
+    const int s = i / Tm, t = i - s * Tm;
+    int g = load_index<I64>(a.signs_pair, (size_t)s * a.T + t + 1);
+    if (g == IGNORE_INDEX) g = 0;
+    if (g < 0 || g > kMaxSign) { bad = 1; continue; }
+    const int half = s >= a.B;
+    atomicOr(&bm[half * 8 + (g >> 5)], 1u << (g & 31));
+  }
+  __syncthreads();
+  if (threadIdx.x < 16 && bm[threadIdx.x]) atomicOr(&a.bitmap[threadIdx.x], bm[threadIdx.x]);
+  if (threadIdx.x == 0 && bad) atomicOr(&a.meta->status, DPA_STATUS_BAD_SIGN);
+}
+
+// rank of phrase id g among the ids present in its half; rank 0 (the smallest id, normally 0) is dropped
+__device__ __forceinline__ int sign_rank(const unsigned* bm8, int g) {
+  int r = 0;
+  const int w = g >> 5;
+  for (int i = 0; i < w; ++i) r += __popc(bm8[i]);
+  r += __popc(bm8[w] & ((1u << (g & 31)) - 1u));
+  return r;
+}
+
+template <bool I64>
+__device__ __forceinline__ bool pair_position(const MetaArgs& a, const unsigned* bm, int i, int& src, int& lab, int& col) {
+  const int Tm = a.T - 1;
+  const int s = i / Tm, t = i - s * Tm;
+  src = s * a.T + t;                                   // hidden row (s, t) predicts label (s, t+1)
+  const int y = load_index<I64>(a.labels_pair, (size_t)s * a.T + t + 1);
+  int g = load_index<I64>(a.signs_pair, (size_t)s * a.T + t + 1);
+  if (g == IGNORE_INDEX) g = 0;
+  const int half = s >= a.B;
+  int rank = 0;
+  if (g >= 0 && g <= kMaxSign) rank = sign_rank(bm + half * 8, g);
+  const bool active = (y != IGNORE_INDEX) && rank >= 1;
+  lab = (y == IGNORE_INDEX) ? 0 : y;                   // -100 -> index 0 (halva_trainer.py:406)
+  col = (s << 16) | (active ? (rank - 1) : kNoCol);
+  return active;
+}
+
+// ---- pass 1: per-block counts of active rows
+template <bool I64>
+__global__ void meta_count_kernel(MetaArgs a) {
+  __shared__ unsigned bm[16];
+  __shared__ int cnt;
+  if (threadIdx.x < 16) bm[threadIdx.x] = a.bitmap[threadIdx.x];
+  if (threadIdx.x == 0) cnt = 0;
+  __syncthreads();
+  const int blk = blockIdx.x;
+  int local = 0;
+  if (blk < a.nblk_pair) {
+    const int i = blk * kScanBlock + threadIdx.x;
+    if (i < a.n_pos_pair) {
+      int src, lab, col;
+      const bool act = pair_position<I64>(a, bm, i, src, lab, col);
+      local = (act || a.dense) ? 1 : 0;
+    }
+  } else {
+    const int i = (blk - a.nblk_pair) * kScanBlock + threadIdx.x;
+    if (i < a.n_pos_ref) {
+      const int Tm = a.T_ref - 1;
+      const int s = i / Tm, t = i - s * Tm;
+      const int y = load_index<I64>(a.labels_ref, (size_t)s * a.T_ref + t + 1);
+      local = (y != IGNORE_INDEX || a.dense) ? 1 : 0;
+    }
+  }
+  const unsigned ball = __ballot_sync(0xffffffffu, local);
+  if ((threadIdx.x & 31) == 0 && ball) atomicAdd(&cnt, __popc(ball));
+  __syncthreads();
+  if (threadIdx.x == 0) a.block_counts[blk] = cnt;
+}
+
+// ---- pass 2: stable compaction (block offset = sum of earlier counts, warp-scan inside the block) + DpaMeta
+template <bool I64>
+__global__ void meta_fill_kernel(MetaArgs a) {
+  __shared__ unsigned bm[16];
+  __shared__ int warp_sums[kScanBlock / 32];
+  __shared__ int base_s, total_pair_s, total_ref_s;
+  if (threadIdx.x < 16) bm[threadIdx.x] = a.bitmap[threadIdx.x];
+  const int blk = blockIdx.x;
+  const bool is_pair = blk < a.nblk_pair;
+  // block offset inside its segment and segment totals (block counts are few: <= ~100)
+  if (threadIdx.x < 32) {
+    int before = 0, tp = 0, trf = 0;
+    for (int j = threadIdx.x; j < a.nblk_pair + a.nblk_ref; j += 32) {
+      const int c = a.block_counts[j];
+      if (j < a.nblk_pair) { tp += c; if (is_pair && j < blk) before += c; }
+      else { trf += c; if (!is_pair && j < blk) before += c; }
+    }
+    for (int o = 16; o; o >>= 1) {
+      before += __shfl_xor_sync(0xffffffffu, before, o);
+      tp += __shfl_xor_sync(0xffffffffu, tp, o);
+      trf += __shfl_xor_sync(0xffffffffu, trf, o);
+    }
+    if (threadIdx.x == 0) { base_s = before; total_pair_s = tp; total_ref_s = trf; }
+  }
+  __syncthreads();
+  int src = 0, lab = 0, col = 0, flag = 0, act = 0;
+  if (is_pair) {
+    const int i = blk * kScanBlock + threadIdx.x;
+    if (i < a.n_pos_pair) {
+      act = pair_position<I64>(a, bm, i, src, lab, col);
+      flag = (act || a.dense) ? 1 : 0;
+    }
+  } else {
+    const int i = (blk - a.nblk_pair) * kScanBlock + threadIdx.x;
+    if (i < a.n_pos_ref) {
+      const int Tm = a.T_ref - 1;
+      const int s = i / Tm, t = i - s * Tm;
+      src = s * a.T_ref + t;
+      act = load_index<I64>(a.labels_ref, (size_t)s * a.T_ref + t + 1) != IGNORE_INDEX;
+      flag = (act || a.dense) ? 1 : 0;
+    }
+  }
+  const unsigned ball = __ballot_sync(0xffffffffu, flag);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int in_warp = __popc(ball & ((1u << lane) - 1u));
+  if (lane == 0) warp_sums[w] = __popc(ball);
+  __syncthreads();
+  if (w == 0) {
+    int v = warp_sums[lane];
+    for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += n; }
+    warp_sums[lane] = v - warp_sums[lane];   // exclusive
+  }
+  __syncthreads();
+  if (flag) {
+    const int dst = base_s + warp_sums[w] + in_warp;
+    if (is_pair) {
+      if (act && (lab < 0 || lab >= a.V)) { atomicOr(&a.meta->status, DPA_STATUS_BAD_LABEL); lab = 0; }
+      a.src_pair[dst] = src; a.lab_pair[dst] = lab; a.col_pair[dst] = col;
+    } else {
+      a.src_ref[dst] = src; a.act_ref[dst] = act;
+    }
+  }
+  if (blk == 0 && threadIdx.x == 0) {
+    DpaMeta* m = a.meta;
+    const int np = total_pair_s, nr = total_ref_s;
+    m->n_pair = np; m->n_ref = nr;
+    m->p0 = (np + 127) & ~127;
+    m->n_tot = m->p0 + ((nr + 127) & ~127);
+    int kp = -1, kn = -1;
+    for (int i = 0; i < 8; ++i) { kp += __popc(bm[i]); kn += __popc(bm[8 + i]); }
+    m->K_pos = kp; m->K_neg = kn; m->K = kp;
+    int st = atomicOr(&m->status, 0);
+    if (kp != kn) st |= DPA_STATUS_K_MISMATCH;
+    else if (kp <= 0) st |= DPA_STATUS_K_ZERO;
+    atomicOr(&m->status, st);
+  }
+}
+
+// pad rows of the packed lists up to the tile boundary (labels 0, no column): one small block
+__global__ void meta_pad_kernel(MetaArgs a) {
+  const DpaMeta* m = a.meta;
+  for (int i = m->n_pair + threadIdx.x; i < m->p0; i += blockDim.x) { a.src_pair[i] = -1; a.lab_pair[i] = 0; a.col_pair[i] = kNoCol; }
+  const int nr_pad = m->n_tot - m->p0;
+  for (int i = m->n_ref + threadIdx.x; i < nr_pad; i += blockDim.x) { a.src_ref[i] = -1; a.act_ref[i] = 0; }
+  if (threadIdx.x == 0) {
+    a.status[0] = m->status; a.status[1] = m->K; a.status[2] = m->n_pair; a.status[3] = m->n_ref;
+    a.status[4] = m->K_pos; a.status[5] = m->K_neg; a.status[6] = m->p0; a.status[7] = m->n_tot;
+  }
+}
+
+// ---- gather active hidden rows into the packed, tile-padded operand buffers (one warp per row, 16 B vectors)
+struct GatherArgs {
+  const DpaMeta* meta;
+  const int* src_pair; const int* src_ref;
+  const __nv_bfloat16* h_pair; const __nv_bfloat16* h_ref_pol; const __nv_bfloat16* h_ref_frz;
+  __nv_bfloat16* Hp;   // [cap_pair + cap_ref][H]  policy rows: pair segment [0,p0), reference segment [p0, n_tot)
+  __nv_bfloat16* Hf;   // [cap_ref][H]             frozen-model rows of the reference segment
+  int H;
+};
+__global__ void gather_rows_kernel(GatherArgs a) {
+  const int p0 = a.meta->p0, n_tot = a.meta->n_tot;
+  const int nr_pad = n_tot - p0;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int vec = a.H / 8;                                 // uint4 per row
+  for (int r = wid; r < n_tot + nr_pad; r += warps) {
+    const uint4* src = nullptr; uint4* dst;
+    if (r < p0) {
+      const int s = a.src_pair[r];
+      if (s >= 0) src = reinterpret_cast<const uint4*>(a.h_pair + (size_t)s * a.H);
+      dst = reinterpret_cast<uint4*>(a.Hp + (size_t)r * a.H);
+    } else if (r < n_tot) {
+      const int s = a.src_ref[r - p0];
+      if (s >= 0) src = reinterpret_cast<const uint4*>(a.h_ref_pol + (size_t)s * a.H);
+      dst = reinterpret_cast<uint4*>(a.Hp + (size_t)r * a.H);
+    } else {
+      const int j = r - n_tot;
+      const int s = a.src_ref[j];
+      if (s >= 0) src = reinterpret_cast<const uint4*>(a.h_ref_frz + (size_t)s * a.H);
+      dst = reinterpret_cast<uint4*>(a.Hf + (size_t)j * a.H);
+    }
+    for (int i = lane; i < vec; i += 32) dst[i] = src ? __ldg(src + i) : make_uint4(0, 0, 0, 0);
+  }
+}
+
+// ---- per-row results: log-prob of the target (pair), KL row (reference sample)
+struct FinishArgs {
+  const DpaMeta* meta;
+  const float4* stats_pair; const float4* stats_ref; const float* stats_u;
+  const int* act_ref;
+  float* lse_pair; float* logp_pair;
+  float* lse_ref_p; float* lse_ref_r; float* kl_row;
+};
+__global__ void finish_rows_kernel(FinishArgs a) {
+  const int p0 = a.meta->p0, nr_pad = a.meta->n_tot - p0;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < p0 + nr_pad; r += gridDim.x * blockDim.x) {
+    if (r < p0) {
+      const float4 s = a.stats_pair[r];
+      const float lse = s.x + logf(s.y);
+      a.lse_pair[r] = lse; a.logp_pair[r] = s.z - lse;          // z[y] - LSE (halva_trainer.py:407)
+    } else {
+      const int j = r - p0;
+      const float4 s = a.stats_ref[j];
+      const float lp = s.x + logf(s.y), lr = s.z + logf(s.w);
+      a.lse_ref_p[j] = lp; a.lse_ref_r[j] = lr;
+      // sum_v q (log q - log p) = sum_v q (z_r - z_p) - LSE_r + LSE_p   (halva_trainer.py:583-586)
+      a.kl_row[j] = a.act_ref[j] ? (a.stats_u[j] / s.w - lr + lp) : 0.f;
+    }
+  }
+}
+
+// ---- P[b,k], N[b,k]: one block per sequence, one warp per phrase column round-robin; fixed summation order
+struct PhraseArgs {
+  const DpaMeta* meta;
+  const int* src_pair; const int* col_pair; const float* logp_pair;
+  float* PN;        // [2B][kMaxSign+1]
+  int T;
+};
+__global__ void phrase_sums_kernel(PhraseArgs a) {
+  const int s = blockIdx.x;
+  const int n = a.meta->n_pair, K = a.meta->K;
+  // packed rows are sequence-major: binary-search this sequence's range by source row
+  const int lo_key = s * a.T, hi_key = (s + 1) * a.T;
+  int lo = 0, hi = n;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (a.src_pair[mid] < lo_key) lo = mid + 1; else hi = mid; }
+  const int r0 = lo;
+  hi = n;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (a.src_pair[mid] < hi_key) lo = mid + 1; else hi = mid; }
+  const int r1 = lo;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int k = warp; k < K && k <= kMaxSign; k += nw) {
+    float acc = 0.f;
+    for (int r = r0 + lane; r < r1; r += 32)
+      if ((a.col_pair[r] & 0xFFFF) == k) acc += a.logp_pair[r];
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) a.PN[(size_t)s * (kMaxSign + 1) + k] = acc;
+  }
+}
+
+// ---- loss assembly (one block): align = mean log(1+exp(N-P)), div = sum(kl)/B_ref, sigma for the backward
+struct LossArgs {
+  const DpaMeta* meta;
+  const float* PN; const float* kl_row;
+  float* sigma;     // [B][kMaxSign+1]  d align / d x
+  float* losses;    // [4]
+  int B, B_ref; float alpha;
+};
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  float t = 0.f;
+  if (w == 0) {
+    t = lane < (blockDim.x >> 5) ? sh[lane] : 0.f;
+    for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) sh[0] = t;
+  }
+  __syncthreads();
+  return sh[0];
+}
+__global__ void loss_kernel(LossArgs a) {
+  __shared__ float sh[32];
+  const int K = a.meta->K, status = a.meta->status;
+  const int BK_ = a.B * max(K, 0);
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < BK_; i += blockDim.x) {
+    const int b = i / K, k = i - b * K;
+    const float P = a.PN[(size_t)b * (kMaxSign + 1) + k];
+    const float N = a.PN[(size_t)(a.B + b) * (kMaxSign + 1) + k];
+    const float e = expf(N - P);                       // literal log(1 + exp(x)) (halva_trainer.py:567)
+    acc += logf(1.f + e);
+    a.sigma[(size_t)b * (kMaxSign + 1) + k] = (e / (1.f + e)) / (float)BK_;
+  }
+  const float align_sum = block_sum(acc, sh);
+  float kacc = 0.f;
+  const int nr = a.meta->n_ref;
+  for (int i = threadIdx.x; i < nr; i += blockDim.x) kacc += a.kl_row[i];
+  const float kl_sum = block_sum(kacc, sh);
+  if (threadIdx.x == 0) {
+    float align = BK_ > 0 ? align_sum / (float)BK_ : nanf("");     // mean of empty -> NaN, like the reference
+    float div = kl_sum / (float)a.B_ref;                            // / batch size (halva_trainer.py:587-588)
+    if (status & (DPA_STATUS_BAD_SIGN | DPA_STATUS_K_MISMATCH | DPA_STATUS_K_ZERO | DPA_STATUS_BAD_LABEL)) align = nanf("");
+    a.losses[0] = align + a.alpha * div; a.losses[1] = align; a.losses[2] = div; a.losses[3] = 0.f;
+  }
+}
+
+// ---- backward row coefficients (incl. the upstream gradient): dz = coef (onehot - p) / coef (p - q)
+struct CoefArgs {
+  const DpaMeta* meta;
+  const int* col_pair; const int* act_ref; const float* sigma; const float* d_loss;
+  float* coef_pair; float* coef_ref;
+  int B, B_ref; float alpha;
+};
+__global__ void coef_kernel(CoefArgs a) {
+  const int p0 = a.meta->p0, nr_pad = a.meta->n_tot - p0;
+  const float go = a.d_loss ? *a.d_loss : 1.f;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < p0 + nr_pad; r += gridDim.x * blockDim.x) {
+    if (r < p0) {
+      const int c = a.col_pair[r], k = c & 0xFFFF, s = c >> 16;
+      float v = 0.f;
+      if (k != kNoCol && r < a.meta->n_pair) {
+        const int b = s >= a.B ? s - a.B : s;
+        const float sg = a.sigma[(size_t)b * (kMaxSign + 1) + k] * go;
+        v = s >= a.B ? sg : -sg;                       // d loss / d logp: -sigma (pos), +sigma (neg)
+      }
+      a.coef_pair[r] = v;
+    } else {
+      const int j = r - p0;
+      a.coef_ref[j] = (j < a.meta->n_ref && a.act_ref[j]) ? go * a.alpha / (float)a.B_ref : 0.f;
+    }
+  }
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
+  for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    const float4 v = *reinterpret_cast<const float4*>(in + i);
+    uint2 o = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    *reinterpret_cast<uint2*>(out + i) = o;
+  }
+}
+
+}  // namespace dpa

@@ -1,0 +1,211 @@
+"""`dpa_loss`: the fused DPA-loss operator (torch.autograd.Function over the C ABI of libhalva_dpa.so).
+
+Mirrors what HalvaTrainer.compute_loss computes once the decoder has produced final hidden states
+(/root/reference/llava/train/halva_trainer.py:534-592): same tensor inputs (hidden states, lm_head
+weight, labels, phrase ids "signs", frozen-reference hidden states), same scalar loss and gradients.
+The hot path is hand-written sm_100a CUDA behind `include/halva_dpa.h`; there is no PyTorch or CPU
+fallback -- if the library is missing or the device is not a B200 the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import Args, DPAError, Shape, Workspace
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _check_inputs(h_pair, labels_pair, signs_pair, h_ref_pol, h_ref_frozen, labels_ref, W, W_ref):
+    if h_pair.dim() != 3 or h_pair.shape[0] % 2:
+        raise ValueError("h_pair must be [2B, T, H] (first B correct, last B hallucinated sequences)")
+    if tuple(h_pair.shape[:2]) != tuple(labels_pair.shape) or tuple(labels_pair.shape) != tuple(signs_pair.shape):
+        # same check and message as the reference raises at halva_trainer.py:398-399
+        raise ValueError("Logits (batch and sequence length dim) and labels must have the same shape.")
+    if h_ref_pol.shape != h_ref_frozen.shape or tuple(h_ref_pol.shape[:2]) != tuple(labels_ref.shape):
+        raise ValueError("Logits (batch and sequence length dim) and labels must have the same shape.")
+    if W.dim() != 2 or W.shape != W_ref.shape or W.shape[1] != h_pair.shape[2] or h_ref_pol.shape[2] != h_pair.shape[2]:
+        raise ValueError("W / W_ref must be [V, H] with H matching the hidden states")
+    for name, t in (("h_pair", h_pair), ("h_ref_pol", h_ref_pol), ("h_ref_frozen", h_ref_frozen), ("W", W), ("W_ref", W_ref)):
+        if not t.is_cuda:
+            raise DPAError(f"{name} is on {t.device}: the DPA-loss path is CUDA (sm_100a) only, there is no CPU fallback")
+        if t.dtype != torch.bfloat16:
+            raise TypeError(f"{name} has dtype {t.dtype}; the tensor-core path takes bf16 (the HALVA recipes train in bf16)")
+    for name, t in (("labels_pair", labels_pair), ("signs_pair", signs_pair), ("labels_ref", labels_ref)):
+        if t.dtype not in (torch.int64, torch.int32):
+            raise TypeError(f"{name} must be int64 or int32")
+    if not (labels_pair.dtype == signs_pair.dtype == labels_ref.dtype):
+        raise TypeError("labels_pair, signs_pair and labels_ref must share one integer dtype")
+
+
+class _Call:
+    """Owns the ctypes argument block and the tensors it points to for one forward/backward pair."""
+
+    def __init__(self, h_pair, labels_pair, signs_pair, h_ref_pol, h_ref_frozen, labels_ref, W, W_ref, alpha,
+                 round_logits, need_dW, dense, chunk_rows, v_offset, V_global):
+        lib = _lib.load()
+        self.lib = lib
+        dev = h_pair.device
+        self.keep = [t.contiguous() for t in (h_pair, labels_pair, signs_pair, h_ref_pol, h_ref_frozen, labels_ref, W, W_ref)]
+        hp, lp, sp, hr, hf, lr, w, wr = self.keep
+        B2, T, H = hp.shape
+        Br, Tr, _ = hr.shape
+        flags = (_lib.FLAG_ROUND_LOGITS if round_logits else 0) | (_lib.FLAG_NEED_DW if need_dW else 0) | \
+                (_lib.FLAG_DENSE if dense else 0)
+        self.shape = Shape(B=B2 // 2, T=T, B_ref=Br, T_ref=Tr, H=H, V=V_global, V_local=w.shape[0], v_offset=v_offset,
+                           dtype=_lib.DPA_BF16, index_dtype=_lib.DPA_I64 if lp.dtype == torch.int64 else _lib.DPA_I32,
+                           flags=flags, chunk_rows=chunk_rows)
+        ws = Workspace()
+        _lib.check(lib.dpa_query_workspace(C.byref(self.shape), C.byref(ws)), "dpa_query_workspace")
+        self.ws = ws
+        self.state = torch.empty(ws.state_bytes, dtype=torch.uint8, device=dev)
+        self.losses = torch.empty(4, dtype=torch.float32, device=dev)
+        self.status = torch.empty(8, dtype=torch.int32, device=dev)
+        self.need_dW = need_dW
+        self.args = Args(shape=self.shape, alpha=float(alpha),
+                         h_pair=_ptr(hp), labels_pair=_ptr(lp), signs_pair=_ptr(sp), h_ref_pol=_ptr(hr), h_ref_frz=_ptr(hf),
+                         labels_ref=_ptr(lr), W=_ptr(w), W_ref=_ptr(wr),
+                         state=_ptr(self.state), state_bytes=ws.state_bytes, scratch=None, scratch_bytes=0,
+                         losses=_ptr(self.losses), status=_ptr(self.status), d_loss=None, dH_pair=None, dH_ref=None, dW=None)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.state.device).cuda_stream)
+
+    def _with_scratch(self, nbytes):
+        scratch = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=self.state.device)
+        self.args.scratch = _ptr(scratch)
+        self.args.scratch_bytes = int(nbytes)
+        return scratch
+
+    def forward(self, vocab_group=None):
+        with torch.cuda.device(self.state.device):
+            scratch = self._with_scratch(self.ws.fwd_bytes)
+            if vocab_group is None:
+                _lib.check(self.lib.dpa_forward(C.byref(self.args), self._stream()), "dpa_forward")
+            else:
+                import torch.distributed as dist
+                _lib.check(self.lib.dpa_forward_stats(C.byref(self.args), self._stream()), "dpa_forward_stats")
+                p, n = C.c_void_p(), C.c_size_t()
+                _lib.check(self.lib.dpa_row_stats_view(C.byref(self.args), C.byref(p), C.byref(n)), "dpa_row_stats_view")
+                off = p.value - self.state.data_ptr()
+                rec = self.state[off:off + n.value]
+                G = dist.get_world_size(vocab_group)
+                gathered = torch.empty(G * n.value, dtype=torch.uint8, device=rec.device)
+                dist.all_gather_into_tensor(gathered, rec, group=vocab_group)     # the one exchange step of the forward
+                _lib.check(self.lib.dpa_forward_finish(C.byref(self.args), C.c_void_p(gathered.data_ptr()), G, self._stream()),
+                           "dpa_forward_finish")
+                del gathered
+            del scratch            # stream-ordered free: safe to recycle after the kernels queued above
+        self.args.scratch, self.args.scratch_bytes = None, 0
+
+    def backward(self, d_loss: torch.Tensor):
+        hp, _, _, hr, _, _, w, _ = self.keep
+        with torch.cuda.device(self.state.device):
+            d_loss = d_loss.detach().to(torch.float32).reshape(1).contiguous()
+            dH_pair = torch.empty_like(hp)
+            dH_ref = torch.empty_like(hr)
+            dW = torch.empty_like(w) if self.need_dW else None
+            scratch = self._with_scratch(self.ws.bwd_bytes)
+            self.args.d_loss, self.args.dH_pair, self.args.dH_ref, self.args.dW = _ptr(d_loss), _ptr(dH_pair), _ptr(dH_ref), _ptr(dW)
+            _lib.check(self.lib.dpa_backward(C.byref(self.args), self._stream()), "dpa_backward")
+            del scratch
+        self.args.scratch, self.args.scratch_bytes = None, 0
+        return dH_pair, dH_ref, dW
+
+
+class DPALossFn(torch.autograd.Function):
+    """(h_pair, h_ref_pol, W) -> (loss, align, div); integer inputs and the frozen branch get no gradient."""
+
+    @staticmethod
+    def forward(ctx, h_pair, h_ref_pol, W, labels_pair, signs_pair, labels_ref, h_ref_frozen, W_ref, alpha, round_logits,
+                need_dW, dense, chunk_rows, vocab_group, v_offset, V_global):
+        call = _Call(h_pair.detach(), labels_pair, signs_pair, h_ref_pol.detach(), h_ref_frozen.detach(), labels_ref,
+                     W.detach(), W_ref.detach(), alpha, round_logits, need_dW, dense, chunk_rows, v_offset, V_global)
+        call.forward(vocab_group)
+        ctx.call = call
+        ctx.vocab_group = vocab_group
+        loss, align, div = call.losses[0], call.losses[1], call.losses[2]
+        ctx.mark_non_differentiable(align, div)
+        return loss, align, div
+
+    @staticmethod
+    def backward(ctx, g_loss, g_align, g_div):
+        call = ctx.call
+        dH_pair, dH_ref, dW = call.backward(g_loss)
+        if ctx.vocab_group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(dH_pair, group=ctx.vocab_group)      # partial sums over vocab shards
+            dist.all_reduce(dH_ref, group=ctx.vocab_group)
+        ctx.call = None
+        return (dH_pair, dH_ref, dW) + (None,) * 13
+
+
+def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.Tensor,
+             h_ref_pol: torch.Tensor, labels_ref: torch.Tensor, W: torch.Tensor, *,
+             h_ref_frozen: torch.Tensor, W_ref: Optional[torch.Tensor] = None, alpha: float,
+             round_logits: bool = True, need_dW: Optional[bool] = None, dense: bool = False, chunk_rows: int = 0,
+             vocab_group=None, v_offset: Optional[int] = None, vocab_size: Optional[int] = None,
+             ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Fused DPA loss.  Returns (loss, alignment_loss, divergence) as 0-dim fp32 CUDA tensors; `loss` carries grad.
+
+    h_pair       [2B, T, H] bf16   final hidden states; first B sequences "pos" (correct), last B "neg"
+                                   (hallucinated) -- the stacking of halva_trainer.py:434-447,485-487
+    labels_pair  [2B, T]  int      post-splice labels, -100 = ignore      (unshifted: the op applies the shift)
+    signs_pair   [2B, T]  int      phrase ids: 0 / -100 = none, k >= 1 = k-th <MASK> span
+    h_ref_pol    [Br,Tr,H] bf16    policy hidden states on the reference sample
+    labels_ref   [Br,Tr]  int
+    W            [V, H]   bf16     lm_head weight (or this rank's vocab shard with `vocab_group`)
+    h_ref_frozen [Br,Tr,H] bf16    frozen reference model's hidden states on the reference sample
+    W_ref        [V, H]            frozen lm_head (default: W itself, the LoRA recipe)
+    alpha                          loss = align + alpha * div            (halva_trainer.py:590)
+    round_logits                   True: round logits to bf16 before the fp32 softmax, exactly as the reference's
+                                   bf16 nn.Linear does (modeling_llama.py:1028-1029); False: keep fp32 accumulators
+    need_dW                        default W.requires_grad (False under the shipped LoRA recipe: lm_head frozen)
+    dense                          process every fed position instead of compacting to rows with a non-zero
+                                   contribution (what the reference executes; benchmarking only)
+    Ill-formed phrase ids (K_pos != K_neg, K == 0, id > 255) make the losses NaN and set bits in
+    `dpa_last_status()`; the reference raises / returns NaN there.
+    """
+    W_ref = W if W_ref is None else W_ref
+    _check_inputs(h_pair, labels_pair, signs_pair, h_ref_pol, h_ref_frozen, labels_ref, W, W_ref)
+    if need_dW is None:
+        need_dW = bool(W.requires_grad)
+    if vocab_group is not None:
+        import torch.distributed as dist
+        G, r = dist.get_world_size(vocab_group), dist.get_rank(vocab_group)
+        v_offset = r * W.shape[0] if v_offset is None else v_offset
+        vocab_size = G * W.shape[0] if vocab_size is None else vocab_size
+    else:
+        v_offset, vocab_size = 0, W.shape[0]
+    out = DPALossFn.apply(h_pair, h_ref_pol, W, labels_pair, signs_pair, labels_ref, h_ref_frozen, W_ref, float(alpha),
+                          bool(round_logits), bool(need_dW), bool(dense), int(chunk_rows), vocab_group, int(v_offset),
+                          int(vocab_size))
+    return out
+
+
+def read_status(loss: torch.Tensor):
+    """Synchronising debug helper: status word / K / active-row counts of the call that produced `loss`."""
+    fn = loss.grad_fn
+    call = getattr(fn, "call", None)
+    if call is None:
+        raise ValueError("not a live dpa_loss output")
+    s = call.status.cpu().tolist()
+    return dict(status=s[0], K=s[1], n_pair_active=s[2], n_ref_active=s[3], K_pos=s[4], K_neg=s[5])
+
+
+def debug_gemm(A: torch.Tensor, B: torch.Tensor, a_major: int = 0, b_major: int = 0, bn: int = 256) -> torch.Tensor:
+    """Unit-test hook: D = A_logical @ B_logical^T (fp32) through the library's tcgen05 mainloop.
+    K-major operands are [M,K] / [N,K]; MN-major operands are stored transposed, [K,M] / [K,N]."""
+    lib = _lib.load()
+    M, K = (A.shape if a_major == 0 else (A.shape[1], A.shape[0]))
+    N = B.shape[0] if b_major == 0 else B.shape[1]
+    D = torch.empty(M, N, dtype=torch.float32, device=A.device)
+    with torch.cuda.device(A.device):
+        _lib.check(lib.dpa_debug_gemm(A.data_ptr(), B.data_ptr(), D.data_ptr(), M, N, K, a_major, b_major, bn,
+                                      C.c_void_p(torch.cuda.current_stream().cuda_stream)), "dpa_debug_gemm")
+    return D

@@ -1,0 +1,138 @@
+/* libhalva_dpa.so -- C ABI of the B200-native DPA-loss path.
+ *
+ * Replaces, behind one call pair, what HalvaTrainer.compute_loss does after the decoder has produced the
+ * final hidden states (citations into the reference, pritamqu/HALVA):
+ *   lm_head projection + fp32 upcast        vila/train/transformers_replace/models/llama/modeling_llama.py:1022-1029
+ *   cal_batch_logp                          llava/train/halva_trainer.py:392-409
+ *   accumulate_logps                        llava/train/halva_trainer.py:411-419
+ *   concatenated_forward (shift, split)     llava/train/halva_trainer.py:475-489
+ *   reference_forward (shift)               llava/train/halva_trainer.py:522-531
+ *   compute_loss (alignment + divergence)   llava/train/halva_trainer.py:550-592
+ *   and the autograd backward of all of the above (dHidden, optional dW).
+ * The reference has no FFI layer; its seam is the Python override compute_loss(model, inputs)
+ * (llava/train/halva_trainer.py:534).  INTEGRATION.md shows the ctypes binding and the trainer patch.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated otherwise
+ *   - the caller owns all memory (inputs, outputs, workspaces); the library allocates nothing persistent
+ *   - all calls are asynchronous on `stream` and never synchronise the device on the success path
+ *   - return value 0 = OK, negative = dpa_status_t; message via dpa_last_error() (thread local)
+ *   - data-dependent errors (bad phrase ids, K_pos != K_neg, K == 0) cannot be seen by the host without a
+ *     sync: they are reported in status[0] (device) and turn the losses into NaN, which is also what the
+ *     reference returns for K == 0 (it raises RuntimeError for K_pos != K_neg).
+ */
+#ifndef HALVA_DPA_H
+#define HALVA_DPA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPA_ABI_VERSION 1
+
+typedef enum {
+  DPA_OK = 0,
+  DPA_ERR_BAD_SHAPE = -1,   /* dims not supported (H % 64, alignment of V_local, ...) */
+  DPA_ERR_DTYPE = -2,
+  DPA_ERR_ALIGN = -3,       /* a pointer is not 16-byte aligned (TMA) */
+  DPA_ERR_WORKSPACE = -4,   /* workspace too small / NULL */
+  DPA_ERR_CUDA = -5,
+  DPA_ERR_NCCL = -6,
+  DPA_ERR_ARG = -7,
+  DPA_ERR_ARCH = -8         /* not an sm_100 device */
+} dpa_status_t;
+
+/* bits of status[0] (device int), written by dpa_forward */
+#define DPA_STATUS_BAD_SIGN   1   /* a phrase id outside [0, 255] (after -100 -> 0) */
+#define DPA_STATUS_K_MISMATCH 2   /* K_pos != K_neg: the reference raises RuntimeError (or silently broadcasts) */
+#define DPA_STATUS_K_ZERO     4   /* no phrase at all: the reference returns NaN */
+#define DPA_STATUS_BAD_LABEL  8   /* an active label outside [0, V) */
+
+typedef enum { DPA_BF16 = 0 } dpa_dtype_t;
+typedef enum { DPA_I64 = 0, DPA_I32 = 1 } dpa_index_t;
+
+#define DPA_FLAG_ROUND_LOGITS 1   /* round logits to bf16 before the fp32 softmax, as nn.Linear does in bf16 */
+#define DPA_FLAG_NEED_DW      2   /* lm_head is trainable: backward also produces dW */
+#define DPA_FLAG_DENSE        4   /* do not compact: run every fed position (what the reference executes) */
+
+typedef struct {
+  int32_t B;          /* sample pairs; h_pair holds 2B sequences, first B "pos"(correct), last B "neg"(hallucinated) */
+  int32_t T;          /* pair sequence length (post image splice) */
+  int32_t B_ref;      /* reference samples */
+  int32_t T_ref;
+  int32_t H;          /* hidden size, multiple of 64 */
+  int32_t V;          /* global vocabulary */
+  int32_t V_local;    /* rows of W held by this rank (== V without vocab parallelism), multiple of 8 */
+  int32_t v_offset;   /* first global vocabulary id of this rank's shard */
+  int32_t dtype;      /* dpa_dtype_t of h_*, W, W_ref, dH_*, dW */
+  int32_t index_dtype;/* dpa_index_t of labels / signs */
+  int32_t flags;      /* DPA_FLAG_* */
+  int32_t chunk_rows; /* backward row chunk (multiple of 128); 0 = default (16384) */
+} dpa_shape_t;
+
+typedef struct {
+  size_t state_bytes;   /* kept alive by the caller from dpa_forward until dpa_backward returns */
+  size_t fwd_bytes;     /* scratch, dpa_forward only */
+  size_t bwd_bytes;     /* scratch, dpa_backward only */
+} dpa_workspace_t;
+
+typedef struct {
+  dpa_shape_t shape;
+  float alpha;                 /* loss = align + alpha * div  (halva_trainer.py:590) */
+  /* inputs (unshifted, post-splice; the library applies the [:, :-1] / [:, 1:] shift) */
+  const void* h_pair;          /* [2B, T, H] */
+  const void* labels_pair;     /* [2B, T]   -100 = ignore */
+  const void* signs_pair;      /* [2B, T]   0 / -100 = no phrase, k>=1 = phrase id */
+  const void* h_ref_pol;       /* [B_ref, T_ref, H]  policy hidden states on the reference sample */
+  const void* h_ref_frz;       /* [B_ref, T_ref, H]  frozen reference model's hidden states */
+  const void* labels_ref;      /* [B_ref, T_ref] */
+  const void* W;               /* [V_local, H] policy lm_head */
+  const void* W_ref;           /* [V_local, H] frozen lm_head (may alias W) */
+  /* workspaces */
+  void* state;  size_t state_bytes;
+  void* scratch; size_t scratch_bytes;
+  /* forward outputs */
+  float* losses;               /* [4]: loss, align, div, reserved */
+  int32_t* status;             /* [8]: status bits, K, n_pair_active, n_ref_active, ... */
+  /* backward */
+  const float* d_loss;         /* device scalar: upstream gradient of `loss` */
+  void* dH_pair;               /* [2B, T, H]  (fully written, zeros for inactive rows) */
+  void* dH_ref;                /* [B_ref, T_ref, H] */
+  void* dW;                    /* [V_local, H] or NULL */
+} dpa_args_t;
+
+int dpa_version(void);
+const char* dpa_last_error(void);
+int dpa_query_workspace(const dpa_shape_t* shape, dpa_workspace_t* out);
+
+/* forward: metadata + compaction + fused lm_head/log-softmax/gather/KL row statistics + loss assembly */
+int dpa_forward(const dpa_args_t* args, void* cuda_stream);
+/* backward: recompute logits chunk-wise -> dLogits (bf16, row chunks) -> dH (+ dW) */
+int dpa_backward(const dpa_args_t* args, void* cuda_stream);
+
+/* Vocab-parallel lm_head: the forward is split around the one exchange step (all-gather of per-row partial
+ * statistics).  stats -> [caller or dpa_comm all-gathers `row_stats`] -> finish. */
+int dpa_forward_stats(const dpa_args_t* args, void* cuda_stream);
+int dpa_forward_finish(const dpa_args_t* args, const void* gathered_stats, int n_shards, void* cuda_stream);
+/* byte size and device address of this rank's merged per-row statistics inside `state` */
+int dpa_row_stats_view(const dpa_args_t* args, void** ptr, size_t* bytes);
+
+/* Optional live timing of the kernels this library launches (bench.py): when enabled every launch group is
+ * bracketed by CUDA events on the caller's stream; collect() synchronises on them and sums milliseconds and
+ * kernel-launch counts per kernel class k (name via dpa_profile_kind_name(k)); returns the number of classes. */
+int dpa_profile_enable(int on);
+int dpa_profile_collect(double* ms, int* launches, int n);
+const char* dpa_profile_kind_name(int k);
+
+/* Debug / unit-test hook: D[M,N] (fp32) = A * B^T through the same tcgen05 mainloop.
+ * a_major/b_major: 0 = K-major ([M,K] / [N,K] row-major), 1 = MN-major ([K,M] / [K,N] row-major). */
+int dpa_debug_gemm(const void* A, const void* B, float* D, int M, int N, int K, int a_major, int b_major, int bn,
+                   void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HALVA_DPA_H */

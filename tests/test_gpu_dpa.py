@@ -1,0 +1,164 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the reference's golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+from dpa_testutil import GOLDEN_CASES, load_golden, rel
+from oracle import dpa_oracle
+
+pytestmark = pytest.mark.gpu
+
+# stated tolerances (BASELINE.json north_star): bf16 rel err <= 1e-3 losses, <= 1e-2 gradients;
+# fp32 maths on the same bf16 values: <= 1e-5 losses (gradients still pass through a bf16 dLogits operand)
+TOL_LOSS_BF16, TOL_GRAD_BF16, TOL_LOSS_FP32 = 1e-3, 1e-2, 2e-5
+
+
+def _to_cuda(g):
+    bf = lambda k: torch.from_numpy(g[k]).to(torch.bfloat16).cuda()
+    ix = lambda k: torch.from_numpy(g[k]).cuda()
+    return dict(h_pair=bf("h_pair"), labels_pair=ix("labels_pair"), signs_pair=ix("signs_pair"), h_ref_pol=bf("h_ref_pol"),
+                h_ref_frz=bf("h_ref_frz"), labels_ref=ix("labels_ref"), W=bf("W"), W_ref=bf("W_ref"), alpha=float(g["alpha"]))
+
+
+def _run_cuda(t, round_logits=True, need_dW=True, grad_out=1.0, **kw):
+    from halva_b200 import dpa_loss
+    hp = t["h_pair"].clone().requires_grad_(True)
+    hr = t["h_ref_pol"].clone().requires_grad_(True)
+    W = t["W"].clone().requires_grad_(need_dW)
+    W_ref = W if t["W_ref"] is t["W"] else t["W_ref"]
+    loss, align, div = dpa_loss(hp, t["labels_pair"], t["signs_pair"], hr, t["labels_ref"], W, h_ref_frozen=t["h_ref_frz"],
+                                W_ref=W_ref.detach() if W_ref is not W else None, alpha=t["alpha"], round_logits=round_logits, **kw)
+    (loss * grad_out).backward()
+    torch.cuda.synchronize()
+    f = lambda x: None if x is None else x.float().cpu().numpy()
+    return dict(loss=loss.item(), align=align.item(), div=div.item(), dH_pair=f(hp.grad), dH_ref=f(hr.grad), dW=f(W.grad))
+
+
+def _oracle(t, mode):
+    f = lambda x: x.float().cpu().numpy()
+    return dpa_oracle.dpa_loss(f(t["h_pair"]), t["labels_pair"].cpu().numpy(), t["signs_pair"].cpu().numpy(), f(t["h_ref_pol"]),
+                               f(t["h_ref_frz"]), t["labels_ref"].cpu().numpy(), f(t["W"]), f(t["W_ref"]), t["alpha"], mode=mode)
+
+
+def _close(a, b, tol):
+    return abs(a - b) <= tol * max(abs(b), 1e-6)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_golden_inputs_vs_oracle(name):
+    """Every golden case (inputs cast to bf16): CUDA vs oracle, in reference-bf16 mode and in fp32-maths mode."""
+    g = load_golden(name)
+    t = _to_cuda(g)
+    for round_logits, mode, tol in ((True, "bf16", TOL_LOSS_BF16), (False, "fp64", TOL_LOSS_FP32)):
+        c = _run_cuda(t, round_logits=round_logits)
+        o = _oracle(t, mode)
+        assert _close(c["loss"], o["loss"], tol), (name, mode, c["loss"], o["loss"])
+        assert _close(c["align"], o["align"], tol), (name, mode, c["align"], o["align"])
+        assert abs(c["div"] - o["div"]) <= tol * abs(o["div"]) + 1e-7, (name, mode, c["div"], o["div"])
+        for k in ("dH_pair", "dH_ref", "dW"):
+            assert rel(c[k], o[k]) <= TOL_GRAD_BF16, (name, mode, k, rel(c[k], o[k]))
+        # structural zeros: last position and rows without contribution get exactly zero gradient
+        assert np.all(c["dH_pair"][:, -1] == 0) and np.all(c["dH_ref"][:, -1] == 0)
+        assert np.all(c["dH_pair"][:, :-1][~o["active_pair"]] == 0)
+        assert np.all(c["dH_ref"][:, :-1][~o["active_ref"]] == 0)
+
+
+@pytest.mark.parametrize("name", ["tiny_bf16", "small_bf16"])
+def test_golden_reference_outputs_bf16(name):
+    """bf16 golden cases: CUDA vs what the reference itself produced in bf16 (tests/golden, oracle/gen_golden.py)."""
+    g = load_golden(name)
+    c = _run_cuda(_to_cuda(g), round_logits=True)
+    assert _close(c["loss"], float(g["ref_loss"]), TOL_LOSS_BF16)
+    assert _close(c["align"], float(g["ref_align"]), TOL_LOSS_BF16)
+    for k in ("dH_pair", "dH_ref", "dW"):
+        assert rel(c[k], g["ref_" + k]) <= TOL_GRAD_BF16, (k, rel(c[k], g["ref_" + k]))
+    # and against the reference's fp32 execution on the same bf16 values
+    c32 = _run_cuda(_to_cuda(g), round_logits=False)
+    assert _close(c32["loss"], float(g["ref32_loss"]), TOL_LOSS_FP32)
+    for k in ("dH_pair", "dH_ref", "dW"):
+        assert rel(c32[k], g["ref32_" + k]) <= TOL_GRAD_BF16
+
+
+def _synth(name="small", seed=3, **over):
+    import dataclasses
+    from halva_b200.synth import CONFIGS, make_inputs
+    shape = dataclasses.replace(CONFIGS[name], **over)
+    t = make_inputs(shape, seed=seed, device="cuda")
+    t["h_ref_frz"] = t.pop("h_ref_frz")
+    return t, shape
+
+
+@pytest.mark.parametrize("over", [dict(), dict(T=129, T_ref=77), dict(V=1000 - 8, H=192), dict(B=1, B_ref=3, k_max=1),
+                                  dict(H=4096, V=2048, T=64, T_ref=64, B=1)])
+def test_synthetic_shapes_vs_oracle(over):
+    """Ragged T, V not a multiple of the tile, H not a multiple of 256, B_ref != B."""
+    t, shape = _synth(**over)
+    c = _run_cuda(t)
+    o = _oracle(t, "bf16")
+    assert _close(c["loss"], o["loss"], TOL_LOSS_BF16) and _close(c["align"], o["align"], TOL_LOSS_BF16)
+    for k in ("dH_pair", "dH_ref", "dW"):
+        assert rel(c[k], o[k]) <= TOL_GRAD_BF16, (k, rel(c[k], o[k]))
+
+
+def test_int32_labels_and_frozen_head():
+    t, _ = _synth()
+    a = _run_cuda(t, need_dW=False)
+    t32 = dict(t)
+    for k in ("labels_pair", "signs_pair", "labels_ref"):
+        t32[k] = t[k].to(torch.int32)
+    b = _run_cuda(t32, need_dW=False)
+    assert a["dW"] is None and b["dW"] is None
+    assert a["loss"] == b["loss"] and np.array_equal(a["dH_pair"], b["dH_pair"])
+
+
+def test_dense_equals_compact_and_chunking_invariant():
+    """Processing every position (what the reference executes) gives the same loss and gradients as the compacted
+    path; the backward row-chunk size does not change the result."""
+    t, _ = _synth()
+    a = _run_cuda(t)
+    d = _run_cuda(t, dense=True)
+    ch = _run_cuda(t, chunk_rows=128)
+    assert _close(d["loss"], a["loss"], 1e-6)
+    for k in ("dH_pair", "dH_ref"):
+        assert np.array_equal(a[k], d[k]) and np.array_equal(a[k], ch[k]), k
+    assert rel(d["dW"], a["dW"]) <= 1e-5 and rel(ch["dW"], a["dW"]) <= 2e-3   # fp32 partial sums regroup
+
+
+def test_grad_output_scaling_and_determinism():
+    t, _ = _synth()
+    a = _run_cuda(t)
+    b = _run_cuda(t)
+    assert a["loss"] == b["loss"] and np.array_equal(a["dW"], b["dW"]) and np.array_equal(a["dH_pair"], b["dH_pair"])
+    s = _run_cuda(t, grad_out=0.25)                     # Trainer divides by gradient_accumulation_steps
+    assert rel(s["dH_pair"], 0.25 * a["dH_pair"]) <= 5e-3 and rel(s["dW"], 0.25 * a["dW"]) <= 5e-3
+
+
+def test_quirks_match_reference():
+    """K == 0 -> NaN (as the reference); K_pos != K_neg -> NaN + status bit (the reference raises RuntimeError)."""
+    from halva_b200 import dpa_loss, read_status
+    t, _ = _synth()
+    z = torch.zeros_like(t["signs_pair"])
+    loss, _, _ = dpa_loss(t["h_pair"], t["labels_pair"], z, t["h_ref_pol"], t["labels_ref"], t["W"],
+                          h_ref_frozen=t["h_ref_frz"], alpha=0.4)
+    assert torch.isnan(loss).item()
+    s = t["signs_pair"].clone()
+    B = s.shape[0] // 2
+    s[B:][s[B:] > 0] = 1
+    s[:B][s[:B] > 2] = 2
+    tt = dict(t); tt["signs_pair"] = s
+    hp = t["h_pair"].clone().requires_grad_(True)
+    loss, _, _ = dpa_loss(hp, t["labels_pair"], s, t["h_ref_pol"], t["labels_ref"], t["W"], h_ref_frozen=t["h_ref_frz"], alpha=0.4)
+    st = read_status(loss)
+    if st["K_pos"] != st["K_neg"]:
+        assert torch.isnan(loss).item() and (st["status"] & 2)
+
+
+def test_rejects_cpu_and_fp32_inputs():
+    from halva_b200 import DPAError, dpa_loss
+    t, _ = _synth()
+    with pytest.raises(DPAError):
+        dpa_loss(t["h_pair"].cpu(), t["labels_pair"], t["signs_pair"], t["h_ref_pol"], t["labels_ref"], t["W"],
+                 h_ref_frozen=t["h_ref_frz"], alpha=0.4)
+    with pytest.raises(TypeError):
+        dpa_loss(t["h_pair"].float(), t["labels_pair"], t["signs_pair"], t["h_ref_pol"], t["labels_ref"], t["W"],
+                 h_ref_frozen=t["h_ref_frz"], alpha=0.4)

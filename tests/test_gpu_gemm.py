@@ -1,0 +1,29 @@
+"""tcgen05 mainloop unit tests: D = A B^T through libhalva_dpa's debug hook vs torch fp32 matmul."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(M, N, K, a_major, b_major, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    A = torch.randn(M, K, generator=g, device="cuda").to(torch.bfloat16)
+    B = torch.randn(N, K, generator=g, device="cuda").to(torch.bfloat16)
+    ref = A.float() @ B.float().t()
+    As = A if a_major == 0 else A.t().contiguous()
+    Bs = B if b_major == 0 else B.t().contiguous()
+    return As, Bs, ref
+
+
+@pytest.mark.parametrize("a_major,b_major,bn", [(0, 0, 256), (0, 0, 128), (0, 1, 256), (1, 1, 256), (1, 0, 256)])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 256), (384, 320, 200), (1000, 1024, 4096)])
+def test_debug_gemm(a_major, b_major, bn, M, N, K):
+    from halva_b200 import debug_gemm
+    if (a_major == 1 and M % 8) or (b_major == 1 and N % 8):
+        pytest.skip("alignment")
+    As, Bs, ref = _mk(M, N, K, a_major, b_major)
+    D = debug_gemm(As, Bs, a_major, b_major, bn)
+    torch.cuda.synchronize()
+    err = (D - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 2e-3 * scale + 1e-3, f"max abs err {err} (scale {scale})"
