@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- DPA loss forward+backward throughput on synthetic LLaVA-1.5-7B lm_head shapes.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU)
+    python bench.py --impl reference --steps K --warmup W    # the reference op chain on the host CPU (oracle port)
+
+One "step" = one dpa_loss forward + backward over one batch of BASELINE.json configs[1]
+(16 sample pairs + 16 reference samples, T 2048, H 4096, V 32000, bf16; per GPU under data parallelism).
+Prints ONE JSON line (rank 0). See DESIGN.md "Measurement" for the definitions used here.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "DPA loss fwd+bwd tokens/s (7B lm_head shape)"
+UNIT = "tokens/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(bf16_tflops=d["bf16_tflops"], bf16_tflops_sustained=d.get("bf16_tflops_sustained"), hbm_gbs=d["hbm_gbs"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz, self.power = [], set(), None, []
+        self._halt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(self.period)
+
+    def finish(self):
+        self._halt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        if not self.samples:
+            return dict(sm_mhz=None, sm_max_mhz=self.max_mhz, reasons=[], note="no NVML samples")
+        s = sorted(self.samples)
+        return dict(sm_mhz=s[len(s) // 2], sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons),
+                    power_w_max=round(max(self.power), 1) if self.power else None, samples=len(s))
+
+
+# ------------------------------------------------------------------------------------------------ CPU arms
+def cpu_sample_inputs():
+    """Bounded sample of the workload for the host-CPU arms: 1 pair + 1 reference sample, T 1024, fp32 (the
+    reference's CPU-runnable configuration, BASELINE.json configs[0])."""
+    import torch
+    from halva_b200.synth import CONFIGS, make_inputs
+    shape = CONFIGS["cfg1"]
+    return shape, make_inputs(shape, seed=1234, dtype=torch.float32, device="cpu")
+
+
+def time_cpu_port(steps, warmup):
+    import torch
+    from oracle import dpa_port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    shape, inp = cpu_sample_inputs()
+    for _ in range(warmup):
+        dpa_port.step_cpu(inp)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        dpa_port.step_cpu(inp)
+        ts.append(time.perf_counter() - t0)
+    total = sum(ts)
+    return dict(value=shape.tokens * steps / total, ms_per_step=1e3 * total / steps, cores=cores, tokens_per_step=shape.tokens,
+                sample="1 pair + 1 reference sample, T=1024, H=4096, V=32000, fp32, lm_head trainable (cfg-1 shaped sample of the cfg-2 batch)")
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = time_cpu_port(args.steps, max(args.warmup, 1))
+    line = dict(metric=METRIC, value=r["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=r["ms_per_step"], higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", impl="reference",
+                config=config_dict(args, None),
+                cpu_baseline=dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="port", sample=r["sample"]),
+                e2e=dict(value=r["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(args, shape):
+    from halva_b200.synth import CONFIGS
+    shape = shape or CONFIGS[args.config]
+    return dict(workload=f"HALVA-7B DPA loss at training shape ({args.config}): {shape.B} pairs + {shape.B_ref} reference samples per GPU, "
+                         f"T={shape.T} incl. {shape.n_img} image tokens, H={shape.H}, V={shape.V}, bf16, phrase density {shape.density:.2f}",
+                parallelism=f"dp{args.gpus}", need_dW=not args.no_dw, dense=bool(args.dense),
+                l2="inputs (1.3 GB hidden states + 262 MB lm_head) exceed the 126 MB L2; no explicit flush")
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import dataclasses
+    import torch
+    import torch.distributed as dist
+    from halva_b200 import _lib, dpa_loss, read_status
+    from halva_b200.synth import CONFIGS, algorithmic_flops, make_inputs
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    need_dw = not args.no_dw
+    shape = CONFIGS[args.config]
+    if args.density is not None:
+        shape = dataclasses.replace(shape, density=args.density)
+    if args.pairs is not None:
+        shape = dataclasses.replace(shape, B=args.pairs, B_ref=args.pairs)
+    t = make_inputs(shape, seed=1234 + rank, device=dev)
+    hp, hr = t["h_pair"].requires_grad_(True), t["h_ref_pol"].requires_grad_(True)
+    W = t["W"].requires_grad_(need_dw)
+    tensors = dict(h_pair=hp, h_ref_pol=hr, h_ref_frz=t["h_ref_frz"], labels_pair=t["labels_pair"], signs_pair=t["signs_pair"],
+                   labels_ref=t["labels_ref"])
+
+    def step(src=tensors):
+        src["h_pair"].grad = None
+        src["h_ref_pol"].grad = None
+        W.grad = None
+        loss, align, div = dpa_loss(src["h_pair"], src["labels_pair"], src["signs_pair"], src["h_ref_pol"], src["labels_ref"], W,
+                                    h_ref_frozen=src["h_ref_frz"], alpha=shape.alpha, dense=args.dense, chunk_rows=args.chunk_rows)
+        loss.backward()
+        if world > 1 and need_dw:          # data parallel: average the lm_head gradient over ranks (NCCL over NVLink)
+            dist.all_reduce(W.grad, op=dist.ReduceOp.AVG)
+        return loss, align, div
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    loss, _, _ = step()
+    st = read_status(loss)
+    assert st["status"] == 0, st
+    rows_pair, rows_ref = st["n_pair_active"], st["n_ref_active"]
+    for _ in range(max(args.warmup, 3) - 1):
+        step()
+    barrier()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    _lib.profile_enable(True)
+    _lib.profile_collect()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss, _, _ = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    prof = _lib.profile_collect()
+    _lib.profile_enable(False)
+    if world > 1:
+        tt = torch.tensor([ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = tt.item()
+    loss_val = loss.item()
+
+    # ---- end to end: host (pinned) buffers in, losses out, H2D double-buffered against the previous step's compute
+    host = {k: v.detach().cpu().pin_memory() for k, v in tensors.items()}
+    sets = []
+    for _ in range(2):
+        s = {k: torch.empty_like(v.detach()) for k, v in tensors.items()}
+        s["h_pair"].requires_grad_(True)
+        s["h_ref_pol"].requires_grad_(True)
+        sets.append(s)
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+    out_host = torch.empty(4, dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream(device=dev)
+    ev_copied = [torch.cuda.Event() for _ in range(2)]
+    ev_done = [torch.cuda.Event() for _ in range(2)]
+
+    def e2e_loop(n):
+        cur = torch.cuda.current_stream()
+        for i in range(n + 1):
+            if i < n:
+                b = i % 2
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(ev_done[b])           # buffer set b free again (step i-2 finished)
+                    for k, v in host.items():
+                        sets[b][k].detach().copy_(v, non_blocking=True)
+                    ev_copied[b].record(copy_stream)
+            if i > 0:
+                b = (i - 1) % 2
+                cur.wait_event(ev_copied[b])
+                l, al, dv = step(sets[b])
+                ev_done[b].record(cur)
+                out_host[:3].copy_(torch.stack([l.detach(), al, dv]), non_blocking=True)
+                cur.synchronize()                                 # the step's result is read on the host every step
+
+    for b in range(2):
+        ev_done[b].record(torch.cuda.current_stream())
+    e2e_loop(2)
+    barrier()
+    e0.record()
+    e2e_loop(args.steps)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        tt = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_e2e = tt.item()
+    clocks = sampler.finish() if sampler else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    K = args.steps
+    tokens_step = shape.tokens * world
+    ms_step = ms / K
+    value = tokens_step / (ms_step * 1e-3)
+    unit_flops = 2.0 * shape.H * shape.V
+    # executed tensor-core FLOPs of each GEMM class per step (rows actually processed, tile padding not counted)
+    exec_flops = dict(fwd_pair=rows_pair * unit_flops, fwd_ref=2 * rows_ref * unit_flops, dz_pair=rows_pair * unit_flops,
+                      dz_ref=2 * rows_ref * unit_flops, dH=(rows_pair + rows_ref) * unit_flops,
+                      dW=(rows_pair + rows_ref) * unit_flops if need_dw else 0.0)
+    if args.dense:
+        n_p, n_r = 2 * shape.B * (shape.T - 1), shape.B_ref * (shape.T_ref - 1)
+        exec_flops = dict(fwd_pair=n_p * unit_flops, fwd_ref=2 * n_r * unit_flops, dz_pair=n_p * unit_flops, dz_ref=2 * n_r * unit_flops,
+                          dH=(n_p + n_r) * unit_flops, dW=(n_p + n_r) * unit_flops if need_dw else 0.0)
+    kernels = {}
+    for k, (t_ms, launches) in prof.items():
+        per_step = t_ms / K
+        kernels[k] = dict(ms_per_step=round(per_step, 4), launches_per_step=launches / K,
+                          tflops=round(exec_flops[k] / (per_step * 1e-3) / 1e12, 1) if k in exec_flops and per_step > 0 else None)
+    gemm_kinds = [k for k in exec_flops if kernels.get(k, {}).get("ms_per_step", 0) > 0]
+    dom = max(gemm_kinds, key=lambda k: kernels[k]["ms_per_step"])
+    n_launch_dom = max(1.0, kernels[dom]["launches_per_step"])
+    dom_ms_launch = kernels[dom]["ms_per_step"] / n_launch_dom
+    achieved = exec_flops[dom] / n_launch_dom / (dom_ms_launch * 1e-3) / 1e12
+    f_alg_dense = algorithmic_flops(shape, need_dw)
+    f_alg_active = algorithmic_flops(shape, need_dw, rows_pair, rows_ref)
+    gemm_ms = sum(kernels[k]["ms_per_step"] for k in gemm_kinds)
+    roofline = dict(bound="tensor", kernel=dom, achieved=round(achieved, 1), peak=peaks["bf16_tflops"], unit="TFLOP/s",
+                    frac=round(achieved / peaks["bf16_tflops"], 4), traffic=None, peak_source=peaks["source"],
+                    flops_per_launch=exec_flops[dom] / n_launch_dom, ms_per_launch=round(dom_ms_launch, 4),
+                    share_of_step=round(kernels[dom]["ms_per_step"] / ms_step, 3),
+                    note="FLOPs executed by this kernel for the rows it processed (row compaction: only rows with a non-zero "
+                         "contribution are run). Whole-step figures: step_tc_frac_*")
+    e2e_ms_step = ms_e2e / K
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=max(args.warmup, 3), ms_per_step=ms_step,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+                config=config_dict(args, shape),
+                e2e=dict(value=tokens_step / (e2e_ms_step * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=12,
+                         ms_per_step=e2e_ms_step, note="pinned host hidden states/labels -> device every step (double-buffered), losses read back every step"),
+                gpu_launches=int(round(sum(v["launches_per_step"] for v in kernels.values()) * K)),
+                roofline=roofline, kernels=kernels, clocks=clocks,
+                rows=dict(pair_active=rows_pair, ref_active=rows_ref, pair_fed=2 * shape.B * shape.T, ref_fed=shape.B_ref * shape.T_ref),
+                step_tc_frac_dense_alg=round(f_alg_dense / (ms_step * 1e-3) / 1e12 / peaks["bf16_tflops"], 4),
+                step_tc_frac_active_alg=round(f_alg_active / (ms_step * 1e-3) / 1e12 / peaks["bf16_tflops"], 4),
+                step_tc_frac_executed=round(sum(exec_flops.values()) / (ms_step * 1e-3) / 1e12 / peaks["bf16_tflops"], 4),
+                gemm_share_of_step=round(gemm_ms / ms_step, 3), loss=loss_val)
+    if world == 1 and not args.no_cpu_baseline:
+        r = time_cpu_port(2, 1)
+        line["cpu_baseline"] = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="port", sample=r["sample"],
+                                    ms_per_step=r["ms_per_step"])
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2")
+    ap.add_argument("--density", type=float, default=None)
+    ap.add_argument("--pairs", type=int, default=None)
+    ap.add_argument("--chunk-rows", type=int, default=0)
+    ap.add_argument("--no-dw", action="store_true", help="lm_head frozen (the shipped LoRA recipe): no dW")
+    ap.add_argument("--dense", action="store_true", help="process every fed position (no row compaction)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

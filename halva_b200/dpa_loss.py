@@ -128,6 +128,7 @@ class DPALossFn(torch.autograd.Function):
                      W.detach(), W_ref.detach(), alpha, round_logits, need_dW, dense, chunk_rows, v_offset, V_global)
         call.forward(vocab_group)
         ctx.call = call
+        ctx.status_t = call.status
         ctx.vocab_group = vocab_group
         loss, align, div = call.losses[0], call.losses[1], call.losses[2]
         ctx.mark_non_differentiable(align, div)
@@ -191,10 +192,10 @@ def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.
 def read_status(loss: torch.Tensor):
     """Synchronising debug helper: status word / K / active-row counts of the call that produced `loss`."""
     fn = loss.grad_fn
-    call = getattr(fn, "call", None)
-    if call is None:
-        raise ValueError("not a live dpa_loss output")
-    s = call.status.cpu().tolist()
+    st = getattr(fn, "status_t", None)
+    if st is None:
+        raise ValueError("not a dpa_loss output that carries grad")
+    s = st.cpu().tolist()
     return dict(status=s[0], K=s[1], n_pair_active=s[2], n_ref_active=s[3], K_pos=s[4], K_neg=s[5])
 
 
