@@ -133,6 +133,59 @@ def config_dict(args, shape):
                 l2="inputs (1.3 GB hidden states + 262 MB lm_head) exceed the 126 MB L2; no explicit flush")
 
 
+def run_e2e(args, tensors, step, barrier, dev, world):
+    """Same step driven from HOST buffers: pinned hidden states / labels copied to the device every step
+    (double-buffered against the previous step's compute), the three losses read back every step."""
+    import torch
+    import torch.distributed as dist
+    host = {k: v.detach().cpu().pin_memory() for k, v in tensors.items()}
+    sets = []
+    for _ in range(2):
+        s = {k: torch.empty_like(v.detach()) for k, v in tensors.items()}
+        s["h_pair"].requires_grad_(True)
+        s["h_ref_pol"].requires_grad_(True)
+        sets.append(s)
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+    out_host = torch.empty(4, dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream(device=dev)
+    ev_copied = [torch.cuda.Event() for _ in range(2)]
+    ev_done = [torch.cuda.Event() for _ in range(2)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def e2e_loop(n):
+        cur = torch.cuda.current_stream()
+        for i in range(n + 1):
+            if i < n:
+                b = i % 2
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(ev_done[b])           # buffer set b free again (step i-2 finished)
+                    for k, v in host.items():
+                        sets[b][k].detach().copy_(v, non_blocking=True)
+                    ev_copied[b].record(copy_stream)
+            if i > 0:
+                b = (i - 1) % 2
+                cur.wait_event(ev_copied[b])
+                l, al, dv = step(sets[b])
+                ev_done[b].record(cur)
+                out_host[:3].copy_(torch.stack([l.detach(), al, dv]), non_blocking=True)
+                cur.synchronize()                                 # the step's result is read on the host every step
+
+    for b in range(2):
+        ev_done[b].record(torch.cuda.current_stream())
+    e2e_loop(2)
+    barrier()
+    e0.record()
+    e2e_loop(args.steps)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        tt = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_e2e = tt.item()
+    return ms_e2e, h2d_bytes
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def run_ours(args):
     import dataclasses
@@ -206,51 +259,11 @@ def run_ours(args):
     loss_val = loss.item()
 
     # ---- end to end: host (pinned) buffers in, losses out, H2D double-buffered against the previous step's compute
-    host = {k: v.detach().cpu().pin_memory() for k, v in tensors.items()}
-    sets = []
-    for _ in range(2):
-        s = {k: torch.empty_like(v.detach()) for k, v in tensors.items()}
-        s["h_pair"].requires_grad_(True)
-        s["h_ref_pol"].requires_grad_(True)
-        sets.append(s)
-    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
-    out_host = torch.empty(4, dtype=torch.float32).pin_memory()
-    copy_stream = torch.cuda.Stream(device=dev)
-    ev_copied = [torch.cuda.Event() for _ in range(2)]
-    ev_done = [torch.cuda.Event() for _ in range(2)]
-
-    def e2e_loop(n):
-        cur = torch.cuda.current_stream()
-        for i in range(n + 1):
-            if i < n:
-                b = i % 2
-                with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(ev_done[b])           # buffer set b free again (step i-2 finished)
-                    for k, v in host.items():
-                        sets[b][k].detach().copy_(v, non_blocking=True)
-                    ev_copied[b].record(copy_stream)
-            if i > 0:
-                b = (i - 1) % 2
-                cur.wait_event(ev_copied[b])
-                l, al, dv = step(sets[b])
-                ev_done[b].record(cur)
-                out_host[:3].copy_(torch.stack([l.detach(), al, dv]), non_blocking=True)
-                cur.synchronize()                                 # the step's result is read on the host every step
-
-    for b in range(2):
-        ev_done[b].record(torch.cuda.current_stream())
-    e2e_loop(2)
-    barrier()
-    e0.record()
-    e2e_loop(args.steps)
-    e1.record()
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
-    if world > 1:
-        tt = torch.tensor([ms_e2e], device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_e2e = tt.item()
+    ms_e2e, h2d_bytes = None, 0
+    if not args.no_e2e:
+        ms_e2e, h2d_bytes = run_e2e(args, tensors, step, barrier, dev, world)
     clocks = sampler.finish() if sampler else None
+
 
     if rank != 0:
         if world > 1:
@@ -290,12 +303,13 @@ def run_ours(args):
                     share_of_step=round(kernels[dom]["ms_per_step"] / ms_step, 3),
                     note="FLOPs executed by this kernel for the rows it processed (row compaction: only rows with a non-zero "
                          "contribution are run). Whole-step figures: step_tc_frac_*")
-    e2e_ms_step = ms_e2e / K
+    e2e_ms_step = ms_e2e / K if ms_e2e else None
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=max(args.warmup, 3), ms_per_step=ms_step,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
                 config=config_dict(args, shape),
                 e2e=dict(value=tokens_step / (e2e_ms_step * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=12,
-                         ms_per_step=e2e_ms_step, note="pinned host hidden states/labels -> device every step (double-buffered), losses read back every step"),
+                         ms_per_step=e2e_ms_step, note="pinned host hidden states/labels -> device every step (double-buffered), "
+                         "losses read back every step") if e2e_ms_step else None,
                 gpu_launches=int(round(sum(v["launches_per_step"] for v in kernels.values()) * K)),
                 roofline=roofline, kernels=kernels, clocks=clocks,
                 rows=dict(pair_active=rows_pair, ref_active=rows_ref, pair_fed=2 * shape.B * shape.T, ref_fed=shape.B_ref * shape.T_ref),
@@ -325,6 +339,7 @@ def main():
     ap.add_argument("--no-dw", action="store_true", help="lm_head frozen (the shipped LoRA recipe): no dW")
     ap.add_argument("--dense", action="store_true", help="process every fed position (no row compaction)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end loop (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -259,8 +259,10 @@ __global__ void finish_rows_kernel(FinishArgs a) {
       const float4 s = a.stats_ref[j];
       const float lp = s.x + logf(s.y), lr = s.z + logf(s.w);
       a.lse_ref_p[j] = lp; a.lse_ref_r[j] = lr;
-      // sum_v q (log q - log p) = sum_v q (z_r - z_p) - LSE_r + LSE_p   (halva_trainer.py:583-586)
-      a.kl_row[j] = a.act_ref[j] ? (a.stats_u[j] / s.w - lr + lp) : 0.f;
+      // sum_v q (log q - log p) = sum_v q (z_r - z_p) - (LSE_r - LSE_p)   (halva_trainer.py:583-586).
+      // LSE_r - LSE_p is formed as (m_r - m_p) + log(s_r / s_p): the two maxima are close (exact difference) and
+      // the ratio is near 1, so the ~1e-6 absolute rounding of each LSE does not swamp a KL row of ~1e-3.
+      a.kl_row[j] = a.act_ref[j] ? (a.stats_u[j] / s.w - ((s.z - s.x) + logf(s.w / s.y))) : 0.f;
     }
   }
 }
