@@ -130,6 +130,7 @@ def config_dict(args, shape):
     return dict(workload=f"HALVA-7B DPA loss at training shape ({args.config}): {shape.B} pairs + {shape.B_ref} reference samples per GPU, "
                          f"T={shape.T} incl. {shape.n_img} image tokens, H={shape.H}, V={shape.V}, bf16, phrase density {shape.density:.2f}",
                 parallelism=f"dp{args.gpus}", need_dW=not args.no_dw, dense=bool(args.dense),
+                backward="recompute" if args.backward == "recompute" else "fused (gradients formed in the forward pass)",
                 l2="inputs (1.3 GB hidden states + 262 MB lm_head) exceed the 126 MB L2; no explicit flush")
 
 
@@ -218,7 +219,8 @@ def run_ours(args):
         src["h_ref_pol"].grad = None
         W.grad = None
         loss, align, div = dpa_loss(src["h_pair"], src["labels_pair"], src["signs_pair"], src["h_ref_pol"], src["labels_ref"], W,
-                                    h_ref_frozen=src["h_ref_frz"], alpha=shape.alpha, dense=args.dense, chunk_rows=args.chunk_rows)
+                                    h_ref_frozen=src["h_ref_frz"], alpha=shape.alpha, dense=args.dense, chunk_rows=args.chunk_rows,
+                                    backward=args.backward)
         loss.backward()
         if world > 1 and need_dw:          # data parallel: average the lm_head gradient over ranks (NCCL over NVLink)
             dist.all_reduce(W.grad, op=dist.ReduceOp.AVG)
@@ -277,13 +279,16 @@ def run_ours(args):
     value = tokens_step / (ms_step * 1e-3)
     unit_flops = 2.0 * shape.H * shape.V
     # executed tensor-core FLOPs of each GEMM class per step (rows actually processed, tile padding not counted)
-    exec_flops = dict(fwd_pair=rows_pair * unit_flops, fwd_ref=2 * rows_ref * unit_flops, dz_pair=rows_pair * unit_flops,
-                      dz_ref=2 * rows_ref * unit_flops, dH=(rows_pair + rows_ref) * unit_flops,
-                      dW=(rows_pair + rows_ref) * unit_flops if need_dw else 0.0)
-    if args.dense:
-        n_p, n_r = 2 * shape.B * (shape.T - 1), shape.B_ref * (shape.T_ref - 1)
-        exec_flops = dict(fwd_pair=n_p * unit_flops, fwd_ref=2 * n_r * unit_flops, dz_pair=n_p * unit_flops, dz_ref=2 * n_r * unit_flops,
-                          dH=(n_p + n_r) * unit_flops, dW=(n_p + n_r) * unit_flops if need_dw else 0.0)
+    n_p, n_r = (2 * shape.B * (shape.T - 1), shape.B_ref * (shape.T_ref - 1)) if args.dense else (rows_pair, rows_ref)
+    fused = args.backward != "recompute"
+    # GEMM classes: fwd_pair/dz_pair = one [rows x H].[V x H]^T each; fwd_ref/dz_ref/stash_ref = policy + frozen logits of the
+    # reference-sample rows (two GEMMs' worth per launch); dH = dz.W; dW = dz^T.H
+    exec_flops = dict(fwd_pair=n_p * unit_flops, dz_pair=n_p * unit_flops, dH=(n_p + n_r) * unit_flops,
+                      dW=(n_p + n_r) * unit_flops if need_dw else 0.0)
+    if fused:
+        exec_flops.update(stash_ref=2 * n_r * unit_flops)
+    else:
+        exec_flops.update(fwd_ref=2 * n_r * unit_flops, dz_ref=2 * n_r * unit_flops)
     kernels = {}
     for k, (t_ms, launches) in prof.items():
         per_step = t_ms / K
@@ -338,6 +343,8 @@ def main():
     ap.add_argument("--chunk-rows", type=int, default=0)
     ap.add_argument("--no-dw", action="store_true", help="lm_head frozen (the shipped LoRA recipe): no dW")
     ap.add_argument("--dense", action="store_true", help="process every fed position (no row compaction)")
+    ap.add_argument("--backward", default="auto", choices=["auto", "fused", "recompute"],
+                    help="gradient strategy of dpa_loss (auto = fused)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end loop (profiling runs)")
     args = ap.parse_args()

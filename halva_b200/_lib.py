@@ -9,11 +9,12 @@ LIB_PATH = os.path.join(HERE, "libhalva_dpa.so")
 
 DPA_BF16 = 0
 DPA_I64, DPA_I32 = 0, 1
-FLAG_ROUND_LOGITS, FLAG_NEED_DW, FLAG_DENSE = 1, 2, 4
+FLAG_ROUND_LOGITS, FLAG_NEED_DW, FLAG_DENSE, FLAG_FUSED_GRAD = 1, 2, 4, 8
+ABI_VERSION = 2
 STATUS_BAD_SIGN, STATUS_K_MISMATCH, STATUS_K_ZERO, STATUS_BAD_LABEL = 1, 2, 4, 8
 EXPORTS = ["dpa_version", "dpa_last_error", "dpa_query_workspace", "dpa_forward", "dpa_backward",
            "dpa_forward_stats", "dpa_forward_finish", "dpa_row_stats_view", "dpa_debug_gemm",
-           "dpa_profile_enable", "dpa_profile_collect", "dpa_profile_kind_name"]
+           "dpa_profile_enable", "dpa_profile_collect", "dpa_profile_kind_name", "dpa_set_cta_group"]
 
 
 class Shape(C.Structure):
@@ -22,7 +23,7 @@ class Shape(C.Structure):
 
 
 class Workspace(C.Structure):
-    _fields_ = [("state_bytes", C.c_size_t), ("fwd_bytes", C.c_size_t), ("bwd_bytes", C.c_size_t)]
+    _fields_ = [("state_bytes", C.c_size_t), ("fwd_bytes", C.c_size_t), ("bwd_bytes", C.c_size_t), ("fused_bytes", C.c_size_t)]
 
 
 class Args(C.Structure):
@@ -53,6 +54,9 @@ def load():
                        "(nvcc, sm_100a). There is no CPU or PyTorch fallback for the DPA-loss path.")
     lib = C.CDLL(LIB_PATH)
     lib.dpa_version.restype = C.c_int
+    if lib.dpa_version() != ABI_VERSION:
+        raise DPAError(f"{LIB_PATH} has ABI version {lib.dpa_version()}, this package needs {ABI_VERSION}: rebuild it "
+                       "(`python -m halva_b200.build --force`)")
     lib.dpa_last_error.restype = C.c_char_p
     lib.dpa_query_workspace.argtypes = [C.POINTER(Shape), C.POINTER(Workspace)]
     for name in ("dpa_forward", "dpa_backward", "dpa_forward_stats"):
@@ -62,6 +66,7 @@ def load():
     lib.dpa_debug_gemm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_void_p]
     lib.dpa_profile_enable.argtypes = [C.c_int]
+    lib.dpa_set_cta_group.argtypes = [C.c_int]
     lib.dpa_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]
     lib.dpa_profile_kind_name.argtypes = [C.c_int]
     lib.dpa_profile_kind_name.restype = C.c_char_p
@@ -73,6 +78,11 @@ def check(rc: int, what: str):
     if rc != 0:
         msg = load().dpa_last_error().decode(errors="replace")
         raise DPAError(f"{what} failed ({rc}): {msg}")
+
+
+def set_cta_group(cg: int):
+    """1 = one CTA per 128 x 256 tile, 2 = CTA pairs on 256 x 256 tiles (tcgen05 cta_group::2; the default)."""
+    check(load().dpa_set_cta_group(int(cg)), "dpa_set_cta_group")
 
 
 def profile_enable(on: bool):

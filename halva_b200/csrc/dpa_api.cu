@@ -1,5 +1,6 @@
 // C ABI of libhalva_dpa.so (include/halva_dpa.h): workspace layout, TMA descriptors, launch sequences.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cstdarg>
 #include <mutex>
@@ -23,7 +24,8 @@ int fail(int code, const char* fmt, ...) {
 // ---------------------------------------------------------------------------------- optional per-kernel timing
 // bench.py asks for live CUDA-event timings of the individual kernels (they are launched inside this library,
 // so the caller cannot bracket them). Off by default; when on, every launch group is bracketed by two events.
-enum ProfKind { PK_META = 0, PK_GATHER, PK_FWD_PAIR, PK_FWD_REF, PK_REDUCE, PK_COEF, PK_DZ_PAIR, PK_DZ_REF, PK_DH, PK_DW, PK_MISC, PK_COUNT };
+enum ProfKind { PK_META = 0, PK_GATHER, PK_FWD_PAIR, PK_FWD_REF, PK_REDUCE, PK_COEF, PK_DZ_PAIR, PK_DZ_REF, PK_DH, PK_DW, PK_MISC,
+                PK_STASH_REF, PK_DZ_ELEM, PK_SCALE, PK_COUNT };
 struct ProfSpan { int kind; int launches; cudaEvent_t a, b; };
 std::vector<ProfSpan> g_spans;
 std::mutex g_prof_mu;
@@ -99,7 +101,7 @@ int make_operand_tmap(const DeviceInfo* d, CUtensorMap* tm, const void* ptr, int
 }
 
 template <class Cfg, class Epi>
-int launch_gemm(cudaStream_t st, int grid, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA2,
+int launch_gemm(cudaStream_t st, int sms, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA2,
                 const CUtensorMap& tmB2, const GemmWork& work, const typename Epi::Params& ep, const char* what) {
   auto kern = dpa_gemm_kernel<Cfg, Epi>;
   static std::once_flag once[16];
@@ -107,15 +109,57 @@ int launch_gemm(cudaStream_t st, int grid, const CUtensorMap& tmA, const CUtenso
   cudaError_t attr_err = cudaSuccess;
   std::call_once(once[dev & 15], [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES); });
   if (attr_err != cudaSuccess) return fail(DPA_ERR_CUDA, "cudaFuncSetAttribute(%s): %s", what, cudaGetErrorString(attr_err));
-  kern<<<grid, kNumThreads, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmA2, tmB2, work, ep);
-  LAUNCH_CHECK(what);
+  // persistent: one CTA per SM; cta_group::2 kernels run as clusters of two CTAs on an SM pair.  The units are
+  // statically strided over the grid, so every cluster must be co-resident: size the grid by the occupancy query.
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(sms / Cfg::CG * Cfg::CG));
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = Cfg::CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = Cfg::CG > 1 ? 1 : 0;
+  if constexpr (Cfg::CG > 1) {
+    static int max_clusters[16] = {0};
+    if (max_clusters[dev & 15] == 0) {
+      int n = 0;
+      cudaError_t oe = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+      if (oe != cudaSuccess || n < 1) return fail(DPA_ERR_CUDA, "cudaOccupancyMaxActiveClusters(%s): %s (n=%d)", what, cudaGetErrorString(oe), n);
+      max_clusters[dev & 15] = n;
+      if (getenv("DPA_VERBOSE")) fprintf(stderr, "dpa: %s: %d co-resident clusters of %d (SMs %d)\n", what, n, Cfg::CG, sms);
+    }
+    cfg.gridDim = dim3((unsigned)(std::min(sms / Cfg::CG, max_clusters[dev & 15]) * Cfg::CG));
+  }
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmA2, tmB2, work, ep);
+  if (e != cudaSuccess) return fail(DPA_ERR_CUDA, "launch %s: %s", what, cudaGetErrorString(e));
   return DPA_OK;
+}
+
+// cta_group of the single-accumulator GEMMs: 2 = CTA pairs on 256 x 256 tiles (default), 1 = one CTA per 128 x 256 tile.
+// Both are compiled; dpa_set_cta_group() / DPA_CTA_GROUP pick one (A/B measurements, bring-up).
+int g_cta_group = 0;
+int cta_group() {
+  if (g_cta_group == 0) {
+    const char* e = getenv("DPA_CTA_GROUP");
+    g_cta_group = (e && e[0] == '1') ? 1 : 2;
+  }
+  return g_cta_group;
+}
+// tmB1 / tmB2: the B-operand maps whose box holds BN (cta_group 1) or BN / 2 (cta_group 2) rows; equal for MN-major B
+template <class Epi, int AMAJ, int BMAJ>
+int launch_single(cudaStream_t st, const DeviceInfo* d, const CUtensorMap& tmA, const CUtensorMap& tmB1, const CUtensorMap& tmB2,
+                  const GemmWork& work, const typename Epi::Params& ep, const char* what) {
+  if (cta_group() == 2)
+    return launch_gemm<GemmCfg<256, false, AMAJ, BMAJ, 2>, Epi>(st, d->sms, tmA, tmB2, tmA, tmB2, work, ep, what);
+  return launch_gemm<GemmCfg<256, false, AMAJ, BMAJ, 1>, Epi>(st, d->sms, tmA, tmB1, tmA, tmB1, work, ep, what);
 }
 
 // ---------------------------------------------------------------------------------- workspace layout
 constexpr int kTpuPair = 5;     // 256-wide column tiles per unit  (V=32000: 125 tiles -> 25 groups)
 constexpr int kTpuRef = 10;     // 128-wide column tiles per unit  (V=32000: 250 tiles -> 25 groups)
 constexpr int kBnPair = 256, kBnRef = 128;
+static_assert(kBnPair * kTpuPair == kBnRef * kTpuRef, "both tilings must produce the same column groups (shared partials)");
 
 struct Layout {
   int n_pos_pair, n_pos_ref, cap_pair, cap_ref, nblk_pair, nblk_ref, ng_pair, ng_ref, ldz, chunk_rows, n_chunks;
@@ -127,27 +171,29 @@ struct Layout {
   size_t f_Hp, f_Hf, f_part_pair, f_part_ref, f_part_u, fwd_total;
   // backward scratch offsets
   size_t b_Hp, b_Hf, b_dz, b_dW32, bwd_total;
+  // fused-gradient forward scratch offsets (DPA_FLAG_FUSED_GRAD)
+  size_t u_Hp, u_Hf, u_part_pair, u_part_ref, u_part_u, u_dz, u_zr, u_dW32, fused_total;
 };
 
 int make_layout(const dpa_shape_t& s, Layout& L) {
   if (s.B < 1 || s.T < 2 || s.B_ref < 1 || s.T_ref < 2) return fail(DPA_ERR_BAD_SHAPE, "need B>=1, T>=2, B_ref>=1, T_ref>=2");
   if (s.H < 64 || s.H % 64) return fail(DPA_ERR_BAD_SHAPE, "H=%d must be a positive multiple of 64", s.H);
-  if (s.V_local < 8 || s.V_local % 8) return fail(DPA_ERR_BAD_SHAPE, "V_local=%d must be a positive multiple of 8 (16-byte TMA rows)", s.V_local);
+  if (s.V_local < 1) return fail(DPA_ERR_BAD_SHAPE, "V_local=%d must be positive", s.V_local);
   if (s.v_offset < 0 || s.v_offset + s.V_local > s.V) return fail(DPA_ERR_BAD_SHAPE, "vocab shard [%d,%d) outside V=%d", s.v_offset, s.v_offset + s.V_local, s.V);
   if (s.dtype != DPA_BF16) return fail(DPA_ERR_DTYPE, "only bf16 hidden states / weights are supported by the tensor-core path");
   if (s.index_dtype != DPA_I64 && s.index_dtype != DPA_I32) return fail(DPA_ERR_DTYPE, "labels/signs must be int64 or int32");
   if ((long long)2 * s.B * s.T >= (1ll << 31) / 2 || 2 * s.B >= 32768) return fail(DPA_ERR_BAD_SHAPE, "batch too large for 32-bit row ids");
   L.n_pos_pair = 2 * s.B * (s.T - 1);
   L.n_pos_ref = s.B_ref * (s.T_ref - 1);
-  L.cap_pair = round_up_i(L.n_pos_pair, BM);
-  L.cap_ref = round_up_i(L.n_pos_ref, BM);
+  L.cap_pair = round_up_i(L.n_pos_pair, kRowPad);
+  L.cap_ref = round_up_i(L.n_pos_ref, kRowPad);
   L.nblk_pair = (L.n_pos_pair + kScanBlock - 1) / kScanBlock;
   L.nblk_ref = (L.n_pos_ref + kScanBlock - 1) / kScanBlock;
   L.ng_pair = ((s.V_local + kBnPair - 1) / kBnPair + kTpuPair - 1) / kTpuPair;
   L.ng_ref = ((s.V_local + kBnRef - 1) / kBnRef + kTpuRef - 1) / kTpuRef;
   L.ldz = round_up_i(s.V_local, 64);
   L.chunk_rows = s.chunk_rows > 0 ? s.chunk_rows : 16384;
-  if (L.chunk_rows % BM) return fail(DPA_ERR_BAD_SHAPE, "chunk_rows=%d must be a multiple of 128", L.chunk_rows);
+  if (L.chunk_rows % kRowPad) return fail(DPA_ERR_BAD_SHAPE, "chunk_rows=%d must be a multiple of %d", L.chunk_rows, kRowPad);
   const int cap_tot = L.cap_pair + L.cap_ref;
   L.chunk_rows = std::min(L.chunk_rows, cap_tot);
   L.n_chunks = (cap_tot + L.chunk_rows - 1) / L.chunk_rows;
@@ -186,6 +232,17 @@ int make_layout(const dpa_shape_t& s, Layout& L) {
   L.b_dz = take((size_t)L.chunk_rows * L.ldz * 2);
   L.b_dW32 = (s.flags & DPA_FLAG_NEED_DW) ? take((size_t)s.V_local * s.H * 4) : o;
   L.bwd_total = o;
+
+  o = 0;
+  L.u_Hp = take((size_t)cap_tot * s.H * 2);
+  L.u_Hf = take((size_t)L.cap_ref * s.H * 2);
+  L.u_part_pair = take((size_t)L.ng_pair * L.cap_pair * 16);
+  L.u_part_ref = take((size_t)L.ng_ref * L.cap_ref * 16);
+  L.u_part_u = take((size_t)L.ng_ref * L.cap_ref * 4);
+  L.u_dz = take((size_t)L.chunk_rows * L.ldz * 2);
+  L.u_zr = take((size_t)L.chunk_rows * L.ldz * 2);
+  L.u_dW32 = (s.flags & DPA_FLAG_NEED_DW) ? take((size_t)s.V_local * s.H * 4) : o;
+  L.fused_total = o;
   return DPA_OK;
 }
 
@@ -252,12 +309,11 @@ int run_forward_gemms(const dpa_args_t* a, const Layout& L, const DeviceInfo* d,
   tmHpD = tmHp;
   const DpaMeta* meta = at<DpaMeta>(a->state, L.meta);
   {
-    using Cfg = GemmCfg<kBnPair, false, KMAJOR, KMAJOR>;
     using Epi = EpiStatsPair<kBnPair, ROUND>;
     GemmWork w{meta, KIND_FWD_PAIR, 0, 0, 0, s.V_local, s.H, kTpuPair};
     typename Epi::Params ep{at<int>(a->state, L.lab_pair), at<float4>(a->scratch, L.f_part_pair), L.cap_pair, s.V_local, s.v_offset};
     ProfScope ps(PK_FWD_PAIR, 1, st);
-    if ((rc = launch_gemm<Cfg, Epi>(st, d->sms, tmHp, tmW256, tmHp, tmW256, w, ep, "fwd_pair"))) return rc;
+    if ((rc = launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHp, tmW256, tmW128, w, ep, "fwd_pair"))) return rc;
   }
   {
     using Cfg = GemmCfg<kBnRef, true, KMAJOR, KMAJOR>;
@@ -271,7 +327,8 @@ int run_forward_gemms(const dpa_args_t* a, const Layout& L, const DeviceInfo* d,
 }
 
 int run_merge(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, const float4* part_pair, const float4* part_ref,
-              const float* part_u, int n_pair, int n_ref, size_t stride_pair, size_t stride_ref, size_t stride_u, cudaStream_t st);
+              const float* part_u, int n_pair, int n_ref, size_t stride_pair, size_t stride_ref, size_t stride_u, cudaStream_t st,
+              RowRange rr = RowRange{SEG_ALL, 0, 0});
 
 }  // namespace
 
@@ -279,14 +336,16 @@ int run_merge(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, const f
 namespace dpa {
 struct MergeStrided {
   const DpaMeta* meta;
+  RowRange rr;
   const float4* part_pair; const float4* part_ref; const float* part_u;
   int n_parts_pair, n_parts_ref;
   size_t stride_pair, stride_ref, stride_u;     // element strides between partial records
   float4* stats_pair; float4* stats_ref; float* stats_u;
 };
 __global__ void merge_strided_kernel(MergeStrided a) {
-  const int p0 = a.meta->p0, nr_pad = a.meta->n_tot - p0;
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < p0 + nr_pad; r += gridDim.x * blockDim.x) {
+  const int p0 = a.meta->p0;
+  int lo, hi; row_range(a.meta, a.rr, lo, hi);
+  for (int r = lo + blockIdx.x * blockDim.x + threadIdx.x; r < hi; r += gridDim.x * blockDim.x) {
     if (r < p0) {
       float m = -INFINITY;
       for (int g = 0; g < a.n_parts_pair; ++g) m = fmaxf(m, a.part_pair[g * a.stride_pair + r].x);
@@ -307,10 +366,11 @@ __global__ void merge_strided_kernel(MergeStrided a) {
       for (int g = 0; g < a.n_parts_ref; ++g) {
         const float4 p = a.part_ref[g * a.stride_ref + j];
         const float wr = expf(p.z - mr);
-        sp += p.y * expf(p.x - mp); sr += p.w * wr; u += a.part_u[g * a.stride_u + j] * wr;
+        sp += p.y * expf(p.x - mp); sr += p.w * wr;
+        if (a.part_u) u += a.part_u[g * a.stride_u + j] * wr;
       }
       a.stats_ref[j] = make_float4(mp, sp, mr, sr);
-      a.stats_u[j] = u;
+      if (a.part_u) a.stats_u[j] = u;
     }
   }
 }
@@ -319,8 +379,9 @@ __global__ void merge_strided_kernel(MergeStrided a) {
 namespace {
 
 int run_merge(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, const float4* part_pair, const float4* part_ref,
-              const float* part_u, int n_pair, int n_ref, size_t stride_pair, size_t stride_ref, size_t stride_u, cudaStream_t st) {
-  MergeStrided m{at<DpaMeta>(a->state, L.meta), part_pair, part_ref, part_u, n_pair, n_ref, stride_pair, stride_ref, stride_u,
+              const float* part_u, int n_pair, int n_ref, size_t stride_pair, size_t stride_ref, size_t stride_u, cudaStream_t st,
+              RowRange rr) {
+  MergeStrided m{at<DpaMeta>(a->state, L.meta), rr, part_pair, part_ref, part_u, n_pair, n_ref, stride_pair, stride_ref, stride_u,
                  at<float4>(a->state, L.stats_pair), at<float4>(a->state, L.stats_ref), at<float>(a->state, L.stats_u)};
   ProfScope ps(PK_REDUCE, 1, st);
   merge_strided_kernel<<<d->sms * 2, 256, 0, st>>>(m);
@@ -328,37 +389,46 @@ int run_merge(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, const f
   return DPA_OK;
 }
 
-int run_finish(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, cudaStream_t st) {
-  const DpaMeta* meta = at<DpaMeta>(a->state, L.meta);
-  FinishArgs f{meta, at<float4>(a->state, L.stats_pair), at<float4>(a->state, L.stats_ref), at<float>(a->state, L.stats_u),
-               at<int>(a->state, L.act_ref), at<float>(a->state, L.lse_pair), at<float>(a->state, L.logp_pair),
-               at<float>(a->state, L.lse_ref_p), at<float>(a->state, L.lse_ref_r), at<float>(a->state, L.kl_row)};
-  ProfScope ps(PK_REDUCE, 3, st);
+int run_finish_rows(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, cudaStream_t st, RowRange rr, bool kl_from_stats = true) {
+  FinishArgs f{at<DpaMeta>(a->state, L.meta), rr, at<float4>(a->state, L.stats_pair), at<float4>(a->state, L.stats_ref),
+               kl_from_stats ? at<float>(a->state, L.stats_u) : nullptr, at<int>(a->state, L.act_ref), at<float>(a->state, L.lse_pair),
+               at<float>(a->state, L.logp_pair), at<float>(a->state, L.lse_ref_p), at<float>(a->state, L.lse_ref_r),
+               at<float>(a->state, L.kl_row)};
+  ProfScope ps(PK_REDUCE, 1, st);
   finish_rows_kernel<<<d->sms * 2, 256, 0, st>>>(f);
   LAUNCH_CHECK("finish_rows");
-  PhraseArgs p{meta, at<int>(a->state, L.src_pair), at<int>(a->state, L.col_pair), at<float>(a->state, L.logp_pair),
-               at<float>(a->state, L.PN), a->shape.T};
-  phrase_sums_kernel<<<2 * a->shape.B, 256, 0, st>>>(p);
-  LAUNCH_CHECK("phrase_sums");
+  return DPA_OK;
+}
+
+// P[b,k] / N[b,k] sums, then the loss phases asked for (LOSS_ALIGN needs the pair rows, LOSS_TOTAL every kl_row)
+int run_losses(const dpa_args_t* a, const Layout& L, cudaStream_t st, int phases) {
+  const DpaMeta* meta = at<DpaMeta>(a->state, L.meta);
+  ProfScope ps(PK_REDUCE, (phases & LOSS_ALIGN) ? 2 : 1, st);
+  if (phases & LOSS_ALIGN) {
+    PhraseArgs p{meta, at<int>(a->state, L.src_pair), at<int>(a->state, L.col_pair), at<float>(a->state, L.logp_pair),
+                 at<float>(a->state, L.PN), a->shape.T};
+    phrase_sums_kernel<<<2 * a->shape.B, 256, 0, st>>>(p);
+    LAUNCH_CHECK("phrase_sums");
+  }
   LossArgs l{meta, at<float>(a->state, L.PN), at<float>(a->state, L.kl_row), at<float>(a->state, L.sigma), a->losses,
-             a->shape.B, a->shape.B_ref, a->alpha};
+             a->shape.B, a->shape.B_ref, a->alpha, phases};
   loss_kernel<<<1, 1024, 0, st>>>(l);
   LAUNCH_CHECK("loss");
   return DPA_OK;
 }
 
-int forward_stats_impl(const dpa_args_t* a, cudaStream_t st, Layout& L, DeviceInfo** dev) {
-  int rc = check_common(a, L, dev);
+int run_finish(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, cudaStream_t st) {
+  int rc = run_finish_rows(a, L, d, st, RowRange{SEG_ALL, 0, 0});
   if (rc) return rc;
-  DeviceInfo* d = *dev;
-  if (!a->scratch || a->scratch_bytes < L.fwd_total) return fail(DPA_ERR_WORKSPACE, "forward scratch: need %zu bytes, got %zu", L.fwd_total, a->scratch_bytes);
-  if (!a->losses || !a->status) return fail(DPA_ERR_ARG, "losses/status is NULL");
+  return run_losses(a, L, st, LOSS_ALIGN | LOSS_TOTAL);
+}
+
+int run_meta(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, cudaStream_t st) {
   CUDA_TRY(cudaMemsetAsync(at<char>(a->state, L.meta), 0, L.block_counts - L.meta, st));   // DpaMeta + bitmap
   MetaArgs m = meta_args(a, L);
   const bool i64 = a->shape.index_dtype == DPA_I64;
   const int nblk = L.nblk_pair + L.nblk_ref;
   const int bm_grid = std::min((L.n_pos_pair + 255) / 256, d->sms * 4);
-  {
   ProfScope ps(PK_META, 4, st);
   if (i64) {
     meta_bitmap_kernel<true><<<bm_grid, 256, 0, st>>>(m);
@@ -371,12 +441,168 @@ int forward_stats_impl(const dpa_args_t* a, cudaStream_t st, Layout& L, DeviceIn
   }
   meta_pad_kernel<<<1, 256, 0, st>>>(m);
   LAUNCH_CHECK("meta");
-  }
+  return DPA_OK;
+}
+
+int forward_stats_impl(const dpa_args_t* a, cudaStream_t st, Layout& L, DeviceInfo** dev) {
+  int rc = check_common(a, L, dev);
+  if (rc) return rc;
+  DeviceInfo* d = *dev;
+  if (!a->scratch || a->scratch_bytes < L.fwd_total) return fail(DPA_ERR_WORKSPACE, "forward scratch: need %zu bytes, got %zu", L.fwd_total, a->scratch_bytes);
+  if (!a->losses || !a->status) return fail(DPA_ERR_ARG, "losses/status is NULL");
+  if ((rc = run_meta(a, L, d, st))) return rc;
   if ((rc = run_gather(a, L, d, a->scratch, L.f_Hp, L.f_Hf, st))) return rc;
   rc = (a->shape.flags & DPA_FLAG_ROUND_LOGITS) ? run_forward_gemms<true>(a, L, d, st) : run_forward_gemms<false>(a, L, d, st);
   if (rc) return rc;
   return run_merge(a, L, d, at<float4>(a->scratch, L.f_part_pair), at<float4>(a->scratch, L.f_part_ref),
                    at<float>(a->scratch, L.f_part_u), L.ng_pair, L.ng_ref, L.cap_pair, L.cap_ref, L.cap_ref, st);
+}
+
+int check_grad_outputs(const dpa_args_t* a) {
+  if (!a->dH_pair || !a->dH_ref) return fail(DPA_ERR_ARG, "dH_pair/dH_ref is NULL");
+  if ((a->shape.flags & DPA_FLAG_NEED_DW) && !a->dW) return fail(DPA_ERR_ARG, "DPA_FLAG_NEED_DW set but dW is NULL");
+  if (!aligned16(a->dH_pair) || !aligned16(a->dH_ref) || (a->dW && !aligned16(a->dW))) return fail(DPA_ERR_ALIGN, "gradient buffers must be 16-byte aligned");
+  return DPA_OK;
+}
+
+// ---------------------------------------------------------------------------------- fused-gradient forward
+// Loss AND gradients (for d_loss = 1) in one pass; dpa_backward then only scales.  Pair rows: statistics GEMM, then
+// the recompute GEMM writes dz once sigma is known (they are few).  Reference-sample rows, chunk by chunk: ONE dual
+// GEMM produces the statistics and keeps the chunk's bf16 logits, an elementwise pass turns them into dz in place.
+// Every chunk ends with dH = dz W and dW += dz^T H.  Per row that is 3 (pair: 4) GEMM units instead of 6 (4).
+int forward_fused_impl(const dpa_args_t* a, cudaStream_t st) {
+  Layout L; DeviceInfo* d;
+  int rc = check_common(a, L, &d);
+  if (rc) return rc;
+  const dpa_shape_t& s = a->shape;
+  if (!(s.flags & DPA_FLAG_ROUND_LOGITS)) return fail(DPA_ERR_ARG, "DPA_FLAG_FUSED_GRAD needs DPA_FLAG_ROUND_LOGITS (the kept logits are bf16)");
+  if (!a->scratch || a->scratch_bytes < L.fused_total) return fail(DPA_ERR_WORKSPACE, "fused scratch: need %zu bytes, got %zu", L.fused_total, a->scratch_bytes);
+  if (!a->losses || !a->status) return fail(DPA_ERR_ARG, "losses/status is NULL");
+  if ((rc = check_grad_outputs(a))) return rc;
+  const bool need_dw = (s.flags & DPA_FLAG_NEED_DW) != 0;
+  const int cap_tot = L.cap_pair + L.cap_ref;
+  const DpaMeta* meta = at<DpaMeta>(a->state, L.meta);
+  __nv_bfloat16* dz = at<__nv_bfloat16>(a->scratch, L.u_dz);
+  __nv_bfloat16* zr = at<__nv_bfloat16>(a->scratch, L.u_zr);
+  float* dW32 = need_dw ? at<float>(a->scratch, L.u_dW32) : nullptr;
+
+  if ((rc = run_meta(a, L, d, st))) return rc;
+  if ((rc = run_gather(a, L, d, a->scratch, L.u_Hp, L.u_Hf, st))) return rc;
+  {
+    ProfScope ps(PK_MISC, 0, st);
+    CUDA_TRY(cudaMemsetAsync(a->dH_pair, 0, (size_t)2 * s.B * s.T * s.H * 2, st));
+    CUDA_TRY(cudaMemsetAsync(a->dH_ref, 0, (size_t)s.B_ref * s.T_ref * s.H * 2, st));
+    if (need_dw) CUDA_TRY(cudaMemsetAsync(dW32, 0, (size_t)s.V_local * s.H * 4, st));
+  }
+
+  CUtensorMap tmHp, tmHf, tmW256, tmW128, tmWr128, tmWr256, tmDzK, tmWmn, tmDzMN, tmHpMN;
+  if ((rc = make_operand_tmap(d, &tmHp, at<char>(a->scratch, L.u_Hp), KMAJOR, cap_tot, s.H, s.H, BM))) return rc;
+  if ((rc = make_operand_tmap(d, &tmHf, at<char>(a->scratch, L.u_Hf), KMAJOR, L.cap_ref, s.H, s.H, BM))) return rc;
+  if ((rc = make_operand_tmap(d, &tmW256, a->W, KMAJOR, s.V_local, s.H, s.H, kBnPair))) return rc;
+  if ((rc = make_operand_tmap(d, &tmW128, a->W, KMAJOR, s.V_local, s.H, s.H, kBnRef))) return rc;
+  if ((rc = make_operand_tmap(d, &tmWr128, a->W_ref, KMAJOR, s.V_local, s.H, s.H, kBnRef))) return rc;
+  if ((rc = make_operand_tmap(d, &tmWr256, a->W_ref, KMAJOR, s.V_local, s.H, s.H, kBnPair))) return rc;
+  if ((rc = make_operand_tmap(d, &tmDzK, dz, KMAJOR, L.chunk_rows, s.V_local, L.ldz, BM))) return rc;
+  if ((rc = make_operand_tmap(d, &tmWmn, a->W, MNMAJOR, s.H, s.V_local, s.H, 0))) return rc;
+  if ((rc = make_operand_tmap(d, &tmDzMN, dz, MNMAJOR, s.V_local, L.chunk_rows, L.ldz, 0))) return rc;
+  if ((rc = make_operand_tmap(d, &tmHpMN, at<char>(a->scratch, L.u_Hp), MNMAJOR, s.H, cap_tot, s.H, 0))) return rc;
+
+  // ---- alignment half: statistics of every pair row -> P, N -> sigma, alignment loss -> row coefficients
+  {
+    using Epi = EpiStatsPair<kBnPair, true>;
+    GemmWork w{meta, KIND_FWD_PAIR, 0, 0, 0, s.V_local, s.H, kTpuPair};
+    typename Epi::Params ep{at<int>(a->state, L.lab_pair), at<float4>(a->scratch, L.u_part_pair), L.cap_pair, s.V_local, s.v_offset};
+    ProfScope ps(PK_FWD_PAIR, 1, st);
+    if ((rc = launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHp, tmW256, tmW128, w, ep, "fwd_pair"))) return rc;
+  }
+  const float4* part_pair = at<float4>(a->scratch, L.u_part_pair);
+  const float4* part_ref = at<float4>(a->scratch, L.u_part_ref);
+  const float* part_u = at<float>(a->scratch, L.u_part_u);
+  if ((rc = run_merge(a, L, d, part_pair, part_ref, part_u, L.ng_pair, L.ng_ref, L.cap_pair, L.cap_ref, L.cap_ref, st,
+                      RowRange{SEG_PAIR, 0, 0}))) return rc;
+  if ((rc = run_finish_rows(a, L, d, st, RowRange{SEG_PAIR, 0, 0}))) return rc;
+  if ((rc = run_losses(a, L, st, LOSS_ALIGN))) return rc;
+  {
+    CoefArgs c{meta, at<int>(a->state, L.col_pair), at<int>(a->state, L.act_ref), at<float>(a->state, L.sigma), nullptr /* d_loss = 1 */,
+               at<float>(a->state, L.coef_pair), at<float>(a->state, L.coef_ref), s.B, s.B_ref, a->alpha};
+    ProfScope ps(PK_COEF, 1, st);
+    coef_kernel<<<d->sms * 2, 256, 0, st>>>(c);
+    LAUNCH_CHECK("coef");
+  }
+
+  // ---- row chunks of the packed space [pair rows | reference-sample rows]
+  for (int ch = 0; ch < L.n_chunks; ++ch) {
+    {
+      using Epi = EpiDzPair<kBnPair, true>;
+      GemmWork w{meta, KIND_DZ_PAIR, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair};
+      typename Epi::Params ep{at<int>(a->state, L.lab_pair), at<float>(a->state, L.lse_pair), at<float>(a->state, L.coef_pair),
+                              dz, L.ldz, ch * L.chunk_rows, s.V_local, s.v_offset};
+      ProfScope ps(PK_DZ_PAIR, 1, st);
+      if ((rc = launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHp, tmW256, tmW128, w, ep, "dz_pair"))) return rc;
+    }
+    {
+      // policy and frozen-model logits of the chunk's reference-sample rows: statistics + the bf16 logits themselves
+      using Epi = EpiStatsStore<256>;
+      float2* part2 = reinterpret_cast<float2*>(at<float4>(a->scratch, L.u_part_ref));
+      ProfScope ps(PK_STASH_REF, 2, st);
+      GemmWork wp{meta, KIND_STASH_POL, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair};
+      typename Epi::Params epp{meta, part2, dz, L.cap_ref, s.V_local, L.ldz, ch * L.chunk_rows, 0};
+      if ((rc = launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHp, tmW256, tmW128, wp, epp, "stash_pol"))) return rc;
+      GemmWork wf{meta, KIND_STASH_FRZ, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair};
+      typename Epi::Params epf{meta, part2, zr, L.cap_ref, s.V_local, L.ldz, ch * L.chunk_rows, 1};
+      if ((rc = launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHf, tmWr256, tmWr128, wf, epf, "stash_frz"))) return rc;
+    }
+    const RowRange rr{SEG_REF_CHUNK, ch, L.chunk_rows};
+    if ((rc = run_merge(a, L, d, part_pair, part_ref, nullptr, L.ng_pair, L.ng_ref, L.cap_pair, L.cap_ref, L.cap_ref, st, rr))) return rc;
+    if ((rc = run_finish_rows(a, L, d, st, rr, /*kl_from_stats=*/false))) return rc;
+    {
+      DzElemArgs e{meta, ch, L.chunk_rows, dz, zr, L.ldz, s.V_local, at<float>(a->state, L.lse_ref_p), at<float>(a->state, L.lse_ref_r),
+                   at<float>(a->state, L.coef_ref), at<int>(a->state, L.act_ref), at<float>(a->state, L.kl_row)};
+      ProfScope ps(PK_DZ_ELEM, 1, st);
+      dz_kl_elem_kernel<<<d->sms * 8, 256, 0, st>>>(e);
+      LAUNCH_CHECK("dz_kl_elem");
+    }
+    {
+      using Epi = EpiStoreRows<256>;
+      GemmWork w{meta, KIND_DH, ch, L.chunk_rows, 0, s.H, s.V_local, 1};
+      typename Epi::Params ep{meta, at<int>(a->state, L.src_pair), at<int>(a->state, L.src_ref),
+                              static_cast<__nv_bfloat16*>(a->dH_pair), static_cast<__nv_bfloat16*>(a->dH_ref), s.H};
+      ProfScope ps(PK_DH, 1, st);
+      if ((rc = launch_single<Epi, KMAJOR, MNMAJOR>(st, d, tmDzK, tmWmn, tmWmn, w, ep, "dH"))) return rc;
+    }
+    if (need_dw) {
+      using Epi = EpiAccumF32<256>;
+      GemmWork w{meta, KIND_DW, ch, L.chunk_rows, s.V_local, s.H, 0, 1};
+      typename Epi::Params ep{dW32, s.H, s.V_local, s.H, 1};
+      ProfScope ps(PK_DW, 1, st);
+      if ((rc = launch_single<Epi, MNMAJOR, MNMAJOR>(st, d, tmDzMN, tmHpMN, tmHpMN, w, ep, "dW"))) return rc;
+    }
+  }
+  if ((rc = run_losses(a, L, st, LOSS_TOTAL))) return rc;
+  if (need_dw) {
+    const size_t n = (size_t)s.V_local * s.H;
+    ProfScope ps(PK_MISC, 1, st);
+    f32_to_bf16_kernel<<<d->sms * 8, 256, 0, st>>>(dW32, static_cast<__nv_bfloat16*>(a->dW), n);
+    LAUNCH_CHECK("dW convert");
+  }
+  return DPA_OK;
+}
+
+// fused-gradient backward: scale what the forward left in dH_pair / dH_ref / dW by the upstream gradient
+int backward_scale_impl(const dpa_args_t* a, cudaStream_t st) {
+  Layout L; DeviceInfo* d;
+  int rc = check_common(a, L, &d);
+  if (rc) return rc;
+  if ((rc = check_grad_outputs(a))) return rc;
+  if (!a->d_loss) return DPA_OK;                                 // NULL = 1
+  const dpa_shape_t& s = a->shape;
+  ProfScope ps(PK_SCALE, 3, st);
+  scale_bf16_kernel<<<d->sms * 8, 256, 0, st>>>(static_cast<__nv_bfloat16*>(a->dH_pair), (size_t)2 * s.B * s.T * s.H, a->d_loss);
+  scale_bf16_kernel<<<d->sms * 8, 256, 0, st>>>(static_cast<__nv_bfloat16*>(a->dH_ref), (size_t)s.B_ref * s.T_ref * s.H, a->d_loss);
+  if (s.flags & DPA_FLAG_NEED_DW)
+    scale_bf16_kernel<<<d->sms * 8, 256, 0, st>>>(static_cast<__nv_bfloat16*>(a->dW), (size_t)s.V_local * s.H, a->d_loss);
+  LAUNCH_CHECK("scale_grads");
+  return DPA_OK;
 }
 
 template <bool ROUND>
@@ -418,13 +644,12 @@ int run_backward(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, cuda
 
   for (int ch = 0; ch < L.n_chunks; ++ch) {
     {
-      using Cfg = GemmCfg<kBnPair, false, KMAJOR, KMAJOR>;
       using Epi = EpiDzPair<kBnPair, ROUND>;
       GemmWork w{meta, KIND_DZ_PAIR, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair};
       typename Epi::Params ep{at<int>(a->state, L.lab_pair), at<float>(a->state, L.lse_pair), at<float>(a->state, L.coef_pair),
                               dz, L.ldz, ch * L.chunk_rows, s.V_local, s.v_offset};
       ProfScope ps(PK_DZ_PAIR, 1, st);
-      if ((rc = launch_gemm<Cfg, Epi>(st, d->sms, tmHp, tmW256, tmHp, tmW256, w, ep, "dz_pair"))) return rc;
+      if ((rc = launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHp, tmW256, tmW128, w, ep, "dz_pair"))) return rc;
     }
     {
       using Cfg = GemmCfg<kBnRef, true, KMAJOR, KMAJOR>;
@@ -436,21 +661,19 @@ int run_backward(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, cuda
       if ((rc = launch_gemm<Cfg, Epi>(st, d->sms, tmHp, tmW128, tmHf, tmWr128, w, ep, "dz_ref"))) return rc;
     }
     {
-      using Cfg = GemmCfg<256, false, KMAJOR, MNMAJOR>;
       using Epi = EpiStoreRows<256>;
       GemmWork w{meta, KIND_DH, ch, L.chunk_rows, 0, s.H, s.V_local, 1};
       typename Epi::Params ep{meta, at<int>(a->state, L.src_pair), at<int>(a->state, L.src_ref),
                               static_cast<__nv_bfloat16*>(a->dH_pair), static_cast<__nv_bfloat16*>(a->dH_ref), s.H};
       ProfScope ps(PK_DH, 1, st);
-      if ((rc = launch_gemm<Cfg, Epi>(st, d->sms, tmDzK, tmWmn, tmDzK, tmWmn, w, ep, "dH"))) return rc;
+      if ((rc = launch_single<Epi, KMAJOR, MNMAJOR>(st, d, tmDzK, tmWmn, tmWmn, w, ep, "dH"))) return rc;
     }
     if (need_dw) {
-      using Cfg = GemmCfg<256, false, MNMAJOR, MNMAJOR>;
       using Epi = EpiAccumF32<256>;
       GemmWork w{meta, KIND_DW, ch, L.chunk_rows, s.V_local, s.H, 0, 1};
       typename Epi::Params ep{dW32, s.H, s.V_local, s.H, 1};
       ProfScope ps(PK_DW, 1, st);
-      if ((rc = launch_gemm<Cfg, Epi>(st, d->sms, tmDzMN, tmHpMN, tmDzMN, tmHpMN, w, ep, "dW"))) return rc;
+      if ((rc = launch_single<Epi, MNMAJOR, MNMAJOR>(st, d, tmDzMN, tmHpMN, tmHpMN, w, ep, "dW"))) return rc;
     }
   }
   if (need_dw) {
@@ -474,7 +697,7 @@ int dpa_query_workspace(const dpa_shape_t* shape, dpa_workspace_t* out) {
   Layout L;
   int rc = make_layout(*shape, L);
   if (rc) return rc;
-  out->state_bytes = L.state_total; out->fwd_bytes = L.fwd_total; out->bwd_bytes = L.bwd_total;
+  out->state_bytes = L.state_total; out->fwd_bytes = L.fwd_total; out->bwd_bytes = L.bwd_total; out->fused_bytes = L.fused_total;
   return DPA_OK;
 }
 
@@ -512,6 +735,7 @@ int dpa_forward_finish(const dpa_args_t* a, const void* gathered, int n_shards, 
 int dpa_forward(const dpa_args_t* a, void* stream) {
   Layout L; DeviceInfo* d;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (a && (a->shape.flags & DPA_FLAG_FUSED_GRAD)) return forward_fused_impl(a, st);
   int rc = forward_stats_impl(a, st, L, &d);
   if (rc) return rc;
   return run_finish(a, L, d, st);
@@ -519,14 +743,19 @@ int dpa_forward(const dpa_args_t* a, void* stream) {
 
 int dpa_backward(const dpa_args_t* a, void* stream) {
   Layout L; DeviceInfo* d;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (a && (a->shape.flags & DPA_FLAG_FUSED_GRAD)) return backward_scale_impl(a, st);
   int rc = check_common(a, L, &d);
   if (rc) return rc;
   if (!a->scratch || a->scratch_bytes < L.bwd_total) return fail(DPA_ERR_WORKSPACE, "backward scratch: need %zu bytes, got %zu", L.bwd_total, a->scratch_bytes);
-  if (!a->dH_pair || !a->dH_ref) return fail(DPA_ERR_ARG, "dH_pair/dH_ref is NULL");
-  if ((a->shape.flags & DPA_FLAG_NEED_DW) && !a->dW) return fail(DPA_ERR_ARG, "DPA_FLAG_NEED_DW set but dW is NULL");
-  if (!aligned16(a->dH_pair) || !aligned16(a->dH_ref) || (a->dW && !aligned16(a->dW))) return fail(DPA_ERR_ALIGN, "gradient buffers must be 16-byte aligned");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if ((rc = check_grad_outputs(a))) return rc;
   return (a->shape.flags & DPA_FLAG_ROUND_LOGITS) ? run_backward<true>(a, L, d, st) : run_backward<false>(a, L, d, st);
+}
+
+int dpa_set_cta_group(int cg) {
+  if (cg != 1 && cg != 2) return fail(DPA_ERR_ARG, "cta_group must be 1 or 2");
+  g_cta_group = cg;
+  return DPA_OK;
 }
 
 int dpa_profile_enable(int on) {
@@ -551,7 +780,8 @@ int dpa_profile_collect(double* ms, int* launches, int n) {
 }
 
 const char* dpa_profile_kind_name(int k) {
-  static const char* names[PK_COUNT] = {"meta", "gather", "fwd_pair", "fwd_ref", "reduce", "coef", "dz_pair", "dz_ref", "dH", "dW", "misc"};
+  static const char* names[PK_COUNT] = {"meta", "gather", "fwd_pair", "fwd_ref", "reduce", "coef", "dz_pair", "dz_ref", "dH", "dW", "misc",
+                                        "stash_ref", "dz_elem", "scale"};
   return (k >= 0 && k < PK_COUNT) ? names[k] : "";
 }
 
@@ -565,18 +795,23 @@ int dpa_debug_gemm(const void* A, const void* B, float* D, int M, int N, int K, 
   if ((rc = make_operand_tmap(d, &tmA, A, a_major, M, K, a_major == KMAJOR ? K : M, BM))) return rc;
   if ((rc = make_operand_tmap(d, &tmB, B, b_major, N, K, b_major == KMAJOR ? K : N, bn))) return rc;
   GemmWork w{nullptr, KIND_STATIC, 0, 0, M, N, K, 1};
-#define DBG_CASE(BN_, AM, BMJ)                                                                        \
-  if (bn == BN_ && a_major == AM && b_major == BMJ) {                                                 \
-    using Cfg = GemmCfg<BN_, false, AM, BMJ>;                                                         \
-    using Epi = EpiAccumF32<BN_>;                                                                     \
-    typename Epi::Params ep{D, N, M, N, 0};                                                           \
-    return launch_gemm<Cfg, Epi>(st, d->sms, tmA, tmB, tmA, tmB, w, ep, "debug_gemm");                \
+  if (bn == 128 && a_major == KMAJOR && b_major == KMAJOR) {     // the tile shape of the dual-accumulator kernels
+    using Epi = EpiAccumF32<128>;
+    typename Epi::Params ep{D, N, M, N, 0};
+    return launch_gemm<GemmCfg<128, false, KMAJOR, KMAJOR, 1>, Epi>(st, d->sms, tmA, tmB, tmA, tmB, w, ep, "debug_gemm");
   }
-  DBG_CASE(256, KMAJOR, KMAJOR)
-  DBG_CASE(128, KMAJOR, KMAJOR)
-  DBG_CASE(256, KMAJOR, MNMAJOR)
-  DBG_CASE(256, MNMAJOR, MNMAJOR)
-  DBG_CASE(256, MNMAJOR, KMAJOR)
+  CUtensorMap tmBh;                                                // B box of BN / 2 rows for cta_group 2
+  if ((rc = make_operand_tmap(d, &tmBh, B, b_major, N, K, b_major == KMAJOR ? K : N, bn / 2))) return rc;
+#define DBG_CASE(AM, BMJ)                                                                             \
+  if (bn == 256 && a_major == AM && b_major == BMJ) {                                                 \
+    using Epi = EpiAccumF32<256>;                                                                     \
+    typename Epi::Params ep{D, N, M, N, 0};                                                           \
+    return launch_single<Epi, AM, BMJ>(st, d, tmA, tmB, tmBh, w, ep, "debug_gemm");                   \
+  }
+  DBG_CASE(KMAJOR, KMAJOR)
+  DBG_CASE(KMAJOR, MNMAJOR)
+  DBG_CASE(MNMAJOR, MNMAJOR)
+  DBG_CASE(MNMAJOR, KMAJOR)
 #undef DBG_CASE
   return fail(DPA_ERR_ARG, "debug gemm: unsupported (bn=%d, a_major=%d, b_major=%d)", bn, a_major, b_major);
 }

@@ -17,7 +17,8 @@
 
 namespace dpa {
 
-constexpr int BM = 128;      // rows per tile == TMEM lanes == epilogue threads
+constexpr int BM = 128;      // rows per CTA tile == TMEM lanes == epilogue threads
+constexpr int kRowPad = 256; // packed row segments and row chunks are padded to this (one cta_group::2 tile pair)
 constexpr int BK = 64;       // K per smem stage: 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;   // K per tcgen05.mma (bf16)
 constexpr int kNumThreads = 256;
@@ -30,8 +31,8 @@ enum : int { KMAJOR = 0, MNMAJOR = 1 };
 struct DpaMeta {
   int n_pair;    // active pair rows (packed order: sequence-major, pos sequences first)
   int n_ref;     // active reference-sample rows
-  int p0;        // round_up(n_pair, 128): first packed row of the reference-sample segment
-  int n_tot;     // p0 + round_up(n_ref, 128): padded rows of the packed policy space
+  int p0;        // round_up(n_pair, kRowPad): first packed row of the reference-sample segment
+  int n_tot;     // p0 + round_up(n_ref, kRowPad): padded rows of the packed policy space
   int K;         // phrase columns (K_pos == K_neg)
   int K_pos, K_neg;
   int status;    // 0 = ok, else DPA_STATUS_* bits
@@ -46,6 +47,8 @@ enum : int {
   KIND_DZ_REF,       // chunk ∩ [p0, n_tot)
   KIND_DH,           // chunk rows x H, K = V
   KIND_DW,           // V x H, K = chunk rows
+  KIND_STASH_POL,    // chunk ∩ [p0, n_tot), policy rows: statistics + bf16 logits kept for the chunk
+  KIND_STASH_FRZ,    // same rows of the frozen-model buffer
 };
 
 struct GemmWork {
@@ -83,7 +86,9 @@ __device__ __forceinline__ TileRange compute_range(const GemmWork& w) {
     case KIND_FWD_PAIR: lo = 0; hi = p0; r.a_row0 = 0; r.e_row0 = 0; break;
     case KIND_FWD_REF: lo = p0; hi = n_tot; r.a_row0 = p0; r.a2_row0 = 0; r.e_row0 = 0; break;
     case KIND_DZ_PAIR: lo = c_lo; hi = min(c_hi, p0); r.a_row0 = lo; r.e_row0 = lo; break;
-    case KIND_DZ_REF: lo = max(c_lo, p0); hi = min(c_hi, n_tot); r.a_row0 = lo; r.a2_row0 = lo - p0; r.e_row0 = lo; break;
+    case KIND_DZ_REF:
+    case KIND_STASH_POL: lo = max(c_lo, p0); hi = min(c_hi, n_tot); r.a_row0 = lo; r.a2_row0 = lo - p0; r.e_row0 = lo; break;
+    case KIND_STASH_FRZ: lo = max(c_lo, p0); hi = min(c_hi, n_tot); r.a_row0 = lo - p0; r.e_row0 = lo; break;
     case KIND_DH: lo = c_lo; hi = min(c_hi, n_tot); r.a_row0 = 0; r.e_row0 = lo; break;
     case KIND_DW: {
       lo = c_lo; hi = min(c_hi, n_tot);
@@ -97,30 +102,36 @@ __device__ __forceinline__ TileRange compute_range(const GemmWork& w) {
   return r;
 }
 
-template <int BN_, bool DUAL_, int AMAJ_, int BMAJ_>
+template <int BN_, bool DUAL_, int AMAJ_, int BMAJ_, int CG_ = 1>
 struct GemmCfg {
-  static constexpr int BN = BN_;
+  static constexpr int BN = BN_;                 // N of one tcgen05.mma / columns of one accumulator
   static constexpr bool DUAL = DUAL_;
   static constexpr int AMAJ = AMAJ_, BMAJ = BMAJ_;
+  static constexpr int CG = CG_;                 // cta_group: 2 = a CTA pair shares one M=256 MMA, each staging half of B
+  static constexpr int BN_CTA = BN / CG;         // B rows staged by this CTA
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = BN_CTA * BK * 2;
   static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (DUAL ? 2 : 1);
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;   // 4 x 48 KiB or 3 x 64 KiB
-  static constexpr int ACC_COLS = DUAL ? 2 * BN : BN;          // TMEM columns per accumulator stage
+  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;   // 6 x 32 KiB (pair), 4 x 48 KiB, 3 x 64 KiB (dual)
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int ACC_COLS = DUAL ? 2 * BN : BN;             // TMEM columns per accumulator stage
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static_assert(2 * ACC_COLS <= 512, "two accumulator stages must fit TMEM");
-  static_assert(BN % 64 == 0 && BN <= 256, "BN");
+  static_assert(BN % 64 == 0 && BN <= 256 && BN_CTA % 64 == 0, "BN");
+  static_assert(CG == 1 || (CG == 2 && !DUAL), "cta_group");
 };
 
 // issue the TMA loads of one operand tile for one K block
-template <int MAJ, int ROWS>
+template <int MAJ, int ROWS, int CG>
 __device__ __forceinline__ void load_operand(uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int row, int k) {
-  if constexpr (MAJ == KMAJOR) {
-    tma_load_2d(dst, tm, bar, k, row);                       // box {64 k, ROWS}
+  if constexpr (MAJ == KMAJOR) {                               // box {64 k, ROWS}
+    if constexpr (CG == 1) tma_load_2d(dst, tm, bar, k, row); else tma_load_2d_pair(dst, tm, bar, k, row);
   } else {
 #pragma unroll
-    for (int j = 0; j < ROWS / 64; ++j)                        // box {64 mn, 64 k}: [atom][k][64 mn]
-      tma_load_2d(dst + j * (BK * 128), tm, bar, row + j * 64, k);
+    for (int j = 0; j < ROWS / 64; ++j) {                      // box {64 mn, 64 k}: [atom][k][64 mn]
+      if constexpr (CG == 1) tma_load_2d(dst + j * (BK * 128), tm, bar, row + j * 64, k);
+      else tma_load_2d_pair(dst + j * (BK * 128), tm, bar, row + j * 64, k);
+    }
   }
 }
 template <int MAJ>
@@ -136,7 +147,7 @@ __global__ void __launch_bounds__(kNumThreads, 1)
 dpa_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                 const GemmWork work, const typename Epi::Params ep) {
-  constexpr int BN = Cfg::BN, STAGES = Cfg::STAGES;
+  constexpr int BN = Cfg::BN, STAGES = Cfg::STAGES, CG = Cfg::CG;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -144,69 +155,87 @@ dpa_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint8_t* sA2 = sB + STAGES * Cfg::B_BYTES;
   uint8_t* sB2 = sA2 + (Cfg::DUAL ? STAGES * Cfg::A_BYTES : 0);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
-  uint64_t* full = bars;
+  uint64_t* full = bars;                      // CG == 2: only the leader CTA's are used
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
-  uint64_t* tempty = bars + 2 * STAGES + 2;
+  uint64_t* tempty = bars + 2 * STAGES + 2;   // CG == 2: only the leader CTA's are used
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // CG == 2: the two CTAs of a cluster work on one 256-row tile pair; rank 0 ("leader") issues the MMAs for both
+  const int cta_rank = CG == 2 ? (int)cluster_ctarank() : 0;
+  const bool leader = cta_rank == 0;
+  const int group_id = blockIdx.x / CG, n_cta_groups = gridDim.x / CG;
 
   const TileRange tr = compute_range(work);
   const int n_tiles = (work.n_cols + BN - 1) / BN;
   const int tpu = work.tiles_per_unit;
   const int n_groups = (n_tiles + tpu - 1) / tpu;
-  const int n_units = tr.k_blocks > 0 ? tr.m_tiles * n_groups : 0;
+  const int m_units = (tr.m_tiles + CG - 1) / CG;             // row tiles of BM * CG rows
+  const int n_units = tr.k_blocks > 0 ? m_units * n_groups : 0;
 
+  if constexpr (CG == 2) cluster_sync_all();                   // both CTAs resident before the paired TMEM allocation
   if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], BM); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], CG); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], CG * BM); }
     fence_barrier_init();
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
     if (Cfg::DUAL) { tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); }
   }
-  if (warp == 2) { tmem_alloc<1>(tmem_slot, 512); tmem_relinquish<1>(); }
+  if (warp == 2) { tmem_alloc<CG>(tmem_slot, 512); tmem_relinquish<CG>(); }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // unit -> (row tile, column group): super-blocks of kSuperM row tiles walk the column groups together
-  auto decode = [&](int u, int& mt, int& ng) {
+  // unit -> (row-tile unit, column group): super-blocks of kSuperM row units walk the column groups together
+  auto decode = [&](int u, int& mu, int& ng) {
     const int per_sb = kSuperM * n_groups;
     const int sb = u / per_sb, r = u - sb * per_sb;
-    const int sb_m = min(kSuperM, tr.m_tiles - sb * kSuperM);
+    const int sb_m = min(kSuperM, m_units - sb * kSuperM);
     ng = r / sb_m;
-    mt = sb * kSuperM + (r - ng * sb_m);
+    mu = sb * kSuperM + (r - ng * sb_m);
   };
 
-  if (warp == 0 && lane == 0) {
-    // ------------------------------------------------------------- TMA producer
+  // The producer and MMA warps run their loops with all 32 lanes converged (lane 0 issues): lanes parked at the
+  // final cluster barrier while lane 0 loops starve it (measured: 3x slower mainloop with cta_group::2).
+  if (warp == 0) {
+    // ------------------------------------------------------------- TMA producer (one per CTA)
     int st = 0; uint32_t ph = 0;
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-      int mt, ng; decode(u, mt, ng);
+    for (int u = group_id; u < n_units; u += n_cta_groups) {
+      int mu, ng; decode(u, mu, ng);
+      const int mt = mu * CG + cta_rank;
       const int nt_end = min((ng + 1) * tpu, n_tiles);
       for (int nt = ng * tpu; nt < nt_end; ++nt) {
         for (int kb = 0; kb < tr.k_blocks; ++kb) {
           mbar_wait(&empty[st], ph ^ 1);
-          mbar_arrive_expect_tx(&full[st], Cfg::STAGE_BYTES);
-          load_operand<Cfg::AMAJ, BM>(sA + st * Cfg::A_BYTES, &tmA, &full[st], tr.a_row0 + mt * BM, tr.a_k0 + kb * BK);
-          load_operand<Cfg::BMAJ, BN>(sB + st * Cfg::B_BYTES, &tmB, &full[st], nt * BN, tr.b_k0 + kb * BK);
-          if constexpr (Cfg::DUAL) {
-            load_operand<Cfg::AMAJ, BM>(sA2 + st * Cfg::A_BYTES, &tmA2, &full[st], tr.a2_row0 + mt * BM, tr.a_k0 + kb * BK);
-            load_operand<Cfg::BMAJ, BN>(sB2 + st * Cfg::B_BYTES, &tmB2, &full[st], nt * BN, tr.b_k0 + kb * BK);
+          if (lane == 0) {
+            if constexpr (CG == 1) mbar_arrive_expect_tx(&full[st], Cfg::STAGE_BYTES);
+            load_operand<Cfg::AMAJ, BM, CG>(sA + st * Cfg::A_BYTES, &tmA, &full[st], tr.a_row0 + mt * BM, tr.a_k0 + kb * BK);
+            load_operand<Cfg::BMAJ, Cfg::BN_CTA, CG>(sB + st * Cfg::B_BYTES, &tmB, &full[st], nt * BN + cta_rank * Cfg::BN_CTA,
+                                                     tr.b_k0 + kb * BK);
+            if constexpr (Cfg::DUAL) {
+              load_operand<Cfg::AMAJ, BM, CG>(sA2 + st * Cfg::A_BYTES, &tmA2, &full[st], tr.a2_row0 + mt * BM, tr.a_k0 + kb * BK);
+              load_operand<Cfg::BMAJ, Cfg::BN_CTA, CG>(sB2 + st * Cfg::B_BYTES, &tmB2, &full[st], nt * BN, tr.b_k0 + kb * BK);
+            }
+            if constexpr (CG == 2) {
+              // both CTAs' bytes are accounted on the leader's barrier (the .cta_group::2 loads signal it)
+              if (leader) mbar_arrive_expect_tx(&full[st], CG * Cfg::STAGE_BYTES);
+              else mbar_arrive_cluster(&full[st], 0);
+            }
           }
+          __syncwarp();
           if (++st == STAGES) { st = 0; ph ^= 1; }
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------- MMA issuer
-    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, Cfg::AMAJ, Cfg::BMAJ);
+  } else if (warp == 1 && leader) {
+    // ------------------------------------------------------------- MMA issuer (leader CTA only)
+    constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN, Cfg::AMAJ, Cfg::BMAJ);
     int st = 0; uint32_t ph = 0; uint32_t it = 0;
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-      int mt, ng; decode(u, mt, ng);
+    for (int u = group_id; u < n_units; u += n_cta_groups) {
+      int mu, ng; decode(u, mu, ng);
       const int nt_end = min((ng + 1) * tpu, n_tiles);
       for (int nt = ng * tpu; nt < nt_end; ++nt, ++it) {
         const uint32_t as = it & 1, aph = (it >> 1) & 1;
@@ -216,18 +245,21 @@ dpa_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int kb = 0; kb < tr.k_blocks; ++kb) {
           mbar_wait(&full[st], ph);
           tc_fence_after();
-          const uint32_t a0 = smem_u32(sA + st * Cfg::A_BYTES), b0 = smem_u32(sB + st * Cfg::B_BYTES);
-#pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_bf16<1>(acc, operand_desc<Cfg::AMAJ>(a0, k), operand_desc<Cfg::BMAJ>(b0, k), idesc, (kb | k) != 0);
-          if constexpr (Cfg::DUAL) {
-            const uint32_t a2 = smem_u32(sA2 + st * Cfg::A_BYTES), b2 = smem_u32(sB2 + st * Cfg::B_BYTES);
+          if (lane == 0) {
+            const uint32_t a0 = smem_u32(sA + st * Cfg::A_BYTES), b0 = smem_u32(sB + st * Cfg::B_BYTES);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k)
-              umma_bf16<1>(acc + BN, operand_desc<Cfg::AMAJ>(a2, k), operand_desc<Cfg::BMAJ>(b2, k), idesc, (kb | k) != 0);
+              umma_bf16<CG>(acc, operand_desc<Cfg::AMAJ>(a0, k), operand_desc<Cfg::BMAJ>(b0, k), idesc, (kb | k) != 0);
+            if constexpr (Cfg::DUAL) {
+              const uint32_t a2 = smem_u32(sA2 + st * Cfg::A_BYTES), b2 = smem_u32(sB2 + st * Cfg::B_BYTES);
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k)
+                umma_bf16<CG>(acc + BN, operand_desc<Cfg::AMAJ>(a2, k), operand_desc<Cfg::BMAJ>(b2, k), idesc, (kb | k) != 0);
+            }
+            umma_commit<CG>(&empty[st]);              // smem slot reusable (in both CTAs) once these MMAs retire
+            if (kb == tr.k_blocks - 1) umma_commit<CG>(&tfull[as]);
           }
-          umma_commit<1>(&empty[st]);                 // smem slot reusable once these MMAs retire
-          if (kb == tr.k_blocks - 1) umma_commit<1>(&tfull[as]);
+          __syncwarp();
           if (++st == STAGES) { st = 0; ph ^= 1; }
         }
       }
@@ -238,8 +270,9 @@ dpa_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int trow = q * 32 + lane;
     const uint32_t lane_base = tmem_base + (uint32_t(q * 32) << 16);
     uint32_t it = 0;
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-      int mt, ng; decode(u, mt, ng);
+    for (int u = group_id; u < n_units; u += n_cta_groups) {
+      int mu, ng; decode(u, mu, ng);
+      const int mt = mu * CG + cta_rank;
       typename Epi::State s;
       Epi::unit_begin(ep, s, tr.e_row0 + mt * BM + trow, mt * BM + trow);
       const int nt_end = min((ng + 1) * tpu, n_tiles);
@@ -249,15 +282,15 @@ dpa_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tc_fence_after();
         Epi::tile(ep, s, lane_base + as * Cfg::ACC_COLS, nt * BN);
         tc_fence_before();
-        mbar_arrive(&tempty[as]);
+        if (leader) mbar_arrive(&tempty[as]); else mbar_arrive_cluster(&tempty[as], 0);
       }
       Epi::unit_end(ep, s, ng);
     }
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();   // remote arrives have landed before either CTA exits
+  if (warp == 2) tmem_dealloc<CG>(tmem_base, 512);
 }
 
 // =====================================================================================================
@@ -379,6 +412,42 @@ __device__ __forceinline__ void store_bf16_chunk(__nv_bfloat16* dst, const float
     o[i] = make_uint4(pack_bf16x2(d[8 * i + 0], d[8 * i + 1]), pack_bf16x2(d[8 * i + 2], d[8 * i + 3]),
                       pack_bf16x2(d[8 * i + 4], d[8 * i + 5]), pack_bf16x2(d[8 * i + 6], d[8 * i + 7]));
 }
+
+// ---- fused-gradient forward, reference-sample rows: per (row, column group) partial {max, sum-exp} of one model's
+//      logits, and the bf16-rounded logits of the row chunk are kept (policy -> the chunk's dz buffer, frozen -> zr) so
+//      that dz = c (p - q) and the KL row are one elementwise pass once the chunk's log-sum-exps are known, instead of a
+//      second pair of GEMMs.  Only valid in reference-bf16 numerics (the logits ARE bf16 there,
+//      modeling_llama.py:1028), hence always rounded.
+template <int BN>
+struct EpiStatsStore {
+  struct Params {
+    const DpaMeta* meta;
+    float2* part;            // [n_groups][row_cap][2]: {m, s} of the policy (which = 0) / frozen (which = 1) logits
+    __nv_bfloat16* z;        // [chunk_rows][ldz]
+    int row_cap, v_local, ldz, chunk_row0, which;
+  };
+  struct State { float m, s; int row; __nv_bfloat16* out; };
+  __device__ static void unit_begin(const Params& p, State& s, int erow, int) {
+    s.m = -INFINITY; s.s = 0.f;
+    s.row = erow - p.meta->p0;                                   // reference-sample row id
+    s.out = p.z + (size_t)(erow - p.chunk_row0) * p.ldz;
+  }
+  __device__ static void tile(const Params& p, State& s, uint32_t taddr, int col0) {
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int cbase = col0 + c * 32;
+      if (cbase >= p.v_local) break;
+      float v[32], e[32];
+      load_chunk(taddr + c * 32, v);
+      round_chunk<true>(v);
+      store_bf16_chunk(s.out + cbase, v);                        // a partial last chunk still stores 32 columns (ldz % 64 == 0)
+      online_update(v, p.v_local - cbase, s.m, s.s, e);
+    }
+  }
+  __device__ static void unit_end(const Params& p, State& s, int ng) {
+    p.part[((size_t)ng * p.row_cap + s.row) * 2 + p.which] = make_float2(s.m, s.s);
+  }
+};
 
 // ---- backward recompute, pair rows: dz = coef * (onehot(y) - softmax(z))  -> bf16 scratch [chunk_rows][ldz]
 template <int BN, bool ROUND>

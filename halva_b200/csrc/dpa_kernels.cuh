@@ -180,8 +180,8 @@ __global__ void meta_fill_kernel(MetaArgs a) {
     DpaMeta* m = a.meta;
     const int np = total_pair_s, nr = total_ref_s;
     m->n_pair = np; m->n_ref = nr;
-    m->p0 = (np + 127) & ~127;
-    m->n_tot = m->p0 + ((nr + 127) & ~127);
+    m->p0 = (np + kRowPad - 1) / kRowPad * kRowPad;
+    m->n_tot = m->p0 + (nr + kRowPad - 1) / kRowPad * kRowPad;
     int kp = -1, kn = -1;
     for (int i = 0; i < 8; ++i) { kp += __popc(bm[i]); kn += __popc(bm[8 + i]); }
     m->K_pos = kp; m->K_neg = kn; m->K = kp;
@@ -239,17 +239,30 @@ __global__ void gather_rows_kernel(GatherArgs a) {
   }
 }
 
+// ---- packed-row ranges the row-wise kernels can be restricted to (the fused-gradient forward finishes the pair
+//      segment first and the reference-sample segment chunk by chunk)
+enum : int { SEG_ALL = 0, SEG_PAIR = 1, SEG_REF_CHUNK = 2 };
+struct RowRange { int seg, chunk, chunk_rows; };
+__device__ __forceinline__ void row_range(const DpaMeta* m, const RowRange& rr, int& lo, int& hi) {
+  const int p0 = m->p0, n_tot = m->n_tot;
+  if (rr.seg == SEG_PAIR) { lo = 0; hi = p0; }
+  else if (rr.seg == SEG_REF_CHUNK) { lo = max(rr.chunk * rr.chunk_rows, p0); hi = min((rr.chunk + 1) * rr.chunk_rows, n_tot); }
+  else { lo = 0; hi = n_tot; }
+}
+
 // ---- per-row results: log-prob of the target (pair), KL row (reference sample)
 struct FinishArgs {
   const DpaMeta* meta;
+  RowRange rr;
   const float4* stats_pair; const float4* stats_ref; const float* stats_u;
   const int* act_ref;
   float* lse_pair; float* logp_pair;
   float* lse_ref_p; float* lse_ref_r; float* kl_row;
 };
 __global__ void finish_rows_kernel(FinishArgs a) {
-  const int p0 = a.meta->p0, nr_pad = a.meta->n_tot - p0;
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < p0 + nr_pad; r += gridDim.x * blockDim.x) {
+  const int p0 = a.meta->p0;
+  int lo, hi; row_range(a.meta, a.rr, lo, hi);
+  for (int r = lo + blockIdx.x * blockDim.x + threadIdx.x; r < hi; r += gridDim.x * blockDim.x) {
     if (r < p0) {
       const float4 s = a.stats_pair[r];
       const float lse = s.x + logf(s.y);
@@ -262,7 +275,9 @@ __global__ void finish_rows_kernel(FinishArgs a) {
       // sum_v q (log q - log p) = sum_v q (z_r - z_p) - (LSE_r - LSE_p)   (halva_trainer.py:583-586).
       // LSE_r - LSE_p is formed as (m_r - m_p) + log(s_r / s_p): the two maxima are close (exact difference) and
       // the ratio is near 1, so the ~1e-6 absolute rounding of each LSE does not swamp a KL row of ~1e-3.
-      a.kl_row[j] = a.act_ref[j] ? (a.stats_u[j] / s.w - ((s.z - s.x) + logf(s.w / s.y))) : 0.f;
+      const float dlse = (s.z - s.x) + logf(s.w / s.y);
+      if (a.stats_u) a.kl_row[j] = a.act_ref[j] ? (a.stats_u[j] / s.w - dlse) : 0.f;
+      else a.kl_row[j] = dlse;       // fused-gradient forward: dz_kl_elem_kernel finishes the row from the kept logits
     }
   }
 }
@@ -302,7 +317,9 @@ struct LossArgs {
   float* sigma;     // [B][kMaxSign+1]  d align / d x
   float* losses;    // [4]
   int B, B_ref; float alpha;
+  int phases;       // bit 0: alignment loss + sigma (needs P, N);  bit 1: divergence + total (needs every kl_row)
 };
+enum : int { LOSS_ALIGN = 1, LOSS_TOTAL = 2 };
 __device__ __forceinline__ float block_sum(float v, float* sh) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -322,25 +339,33 @@ __global__ void loss_kernel(LossArgs a) {
   __shared__ float sh[32];
   const int K = a.meta->K, status = a.meta->status;
   const int BK_ = a.B * max(K, 0);
-  float acc = 0.f;
-  for (int i = threadIdx.x; i < BK_; i += blockDim.x) {
-    const int b = i / K, k = i - b * K;
-    const float P = a.PN[(size_t)b * (kMaxSign + 1) + k];
-    const float N = a.PN[(size_t)(a.B + b) * (kMaxSign + 1) + k];
-    const float e = expf(N - P);                       // literal log(1 + exp(x)) (halva_trainer.py:567)
-    acc += logf(1.f + e);
-    a.sigma[(size_t)b * (kMaxSign + 1) + k] = (e / (1.f + e)) / (float)BK_;
+  if (a.phases & LOSS_ALIGN) {
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < BK_; i += blockDim.x) {
+      const int b = i / K, k = i - b * K;
+      const float P = a.PN[(size_t)b * (kMaxSign + 1) + k];
+      const float N = a.PN[(size_t)(a.B + b) * (kMaxSign + 1) + k];
+      const float e = expf(N - P);                       // literal log(1 + exp(x)) (halva_trainer.py:567)
+      acc += logf(1.f + e);
+      a.sigma[(size_t)b * (kMaxSign + 1) + k] = (e / (1.f + e)) / (float)BK_;
+    }
+    const float align_sum = block_sum(acc, sh);
+    if (threadIdx.x == 0) {
+      float align = BK_ > 0 ? align_sum / (float)BK_ : nanf("");   // mean of empty -> NaN, like the reference
+      if (status & (DPA_STATUS_BAD_SIGN | DPA_STATUS_K_MISMATCH | DPA_STATUS_K_ZERO | DPA_STATUS_BAD_LABEL)) align = nanf("");
+      a.losses[1] = align;
+    }
   }
-  const float align_sum = block_sum(acc, sh);
-  float kacc = 0.f;
-  const int nr = a.meta->n_ref;
-  for (int i = threadIdx.x; i < nr; i += blockDim.x) kacc += a.kl_row[i];
-  const float kl_sum = block_sum(kacc, sh);
-  if (threadIdx.x == 0) {
-    float align = BK_ > 0 ? align_sum / (float)BK_ : nanf("");     // mean of empty -> NaN, like the reference
-    float div = kl_sum / (float)a.B_ref;                            // / batch size (halva_trainer.py:587-588)
-    if (status & (DPA_STATUS_BAD_SIGN | DPA_STATUS_K_MISMATCH | DPA_STATUS_K_ZERO | DPA_STATUS_BAD_LABEL)) align = nanf("");
-    a.losses[0] = align + a.alpha * div; a.losses[1] = align; a.losses[2] = div; a.losses[3] = 0.f;
+  if (a.phases & LOSS_TOTAL) {
+    float kacc = 0.f;
+    const int nr = a.meta->n_ref;
+    for (int i = threadIdx.x; i < nr; i += blockDim.x) kacc += a.kl_row[i];
+    const float kl_sum = block_sum(kacc, sh);
+    if (threadIdx.x == 0) {
+      const float align = a.losses[1];                            // written by this thread or by the LOSS_ALIGN launch
+      const float div = kl_sum / (float)a.B_ref;                  // / batch size (halva_trainer.py:587-588)
+      a.losses[0] = align + a.alpha * div; a.losses[2] = div; a.losses[3] = 0.f;
+    }
   }
 }
 
@@ -368,6 +393,81 @@ __global__ void coef_kernel(CoefArgs a) {
       const int j = r - p0;
       a.coef_ref[j] = (j < a.meta->n_ref && a.act_ref[j]) ? go * a.alpha / (float)a.B_ref : 0.f;
     }
+  }
+}
+
+// ---- fused-gradient forward: from the chunk's kept bf16 logits, dz = coef (softmax(z_pol) - softmax(z_frozen)) in place
+//      over the policy logits, and the KL row sum_v q_v (z_r - z_p) - (LSE_r - LSE_p)  (halva_trainer.py:583-586).
+//      HBM-bound elementwise pass: 4 B read + 2 B written per logit; one block per row at a time.
+struct DzElemArgs {
+  const DpaMeta* meta; int chunk, chunk_rows;
+  __nv_bfloat16* dz; const __nv_bfloat16* zr; int ldz, v_local;
+  const float* lse_p; const float* lse_r; const float* coef; const int* act;   // indexed by reference row j
+  float* kl_row;                                                               // in: LSE_r - LSE_p, out: KL of the row
+};
+__device__ __forceinline__ uint32_t dz_pack2(uint32_t zp, uint32_t zr, float c, float nlp, float nlr, float& t) {
+  const float2 p = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&zp));
+  const float2 r = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&zr));
+  const float qx = fast_exp2(fmaf(r.x, kLog2e, nlr)), qy = fast_exp2(fmaf(r.y, kLog2e, nlr));
+  t = fmaf(qx, r.x - p.x, t);
+  t = fmaf(qy, r.y - p.y, t);
+  return pack_bf16x2(c * (fast_exp2(fmaf(p.x, kLog2e, nlp)) - qx), c * (fast_exp2(fmaf(p.y, kLog2e, nlp)) - qy));
+}
+__global__ void __launch_bounds__(256) dz_kl_elem_kernel(DzElemArgs a) {
+  __shared__ float sh[32];
+  const int p0 = a.meta->p0, n_tot = a.meta->n_tot;
+  const int c_lo = a.chunk * a.chunk_rows;
+  const int lo = max(c_lo, p0), hi = min(c_lo + a.chunk_rows, n_tot);
+  const int nvec = (a.v_local + 7) >> 3;             // columns past v_local hold logits of zero-filled weight rows (0 - 0)
+  constexpr int U = 4;
+  for (int r = lo + blockIdx.x; r < hi; r += gridDim.x) {
+    const int j = r - p0;
+    uint4* pz = reinterpret_cast<uint4*>(a.dz + (size_t)(r - c_lo) * a.ldz);
+    const uint4* pr = reinterpret_cast<const uint4*>(a.zr + (size_t)(r - c_lo) * a.ldz);
+    if (!a.act[j]) {                                  // padding / ignored rows: no loads at all
+      for (int v = threadIdx.x; v < nvec; v += blockDim.x) pz[v] = make_uint4(0, 0, 0, 0);
+      if (threadIdx.x == 0) a.kl_row[j] = 0.f;
+      continue;
+    }
+    const float c = a.coef[j];
+    const float nlp = -a.lse_p[j] * kLog2e, nlr = -a.lse_r[j] * kLog2e;
+    float t = 0.f;
+    for (int v0 = threadIdx.x; v0 < nvec; v0 += U * blockDim.x) {
+      uint4 zp[U], zr[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int v = v0 + u * blockDim.x;
+        if (v < nvec) { zp[u] = pz[v]; zr[u] = __ldg(pr + v); }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int v = v0 + u * blockDim.x;
+        if (v < nvec)
+          pz[v] = make_uint4(dz_pack2(zp[u].x, zr[u].x, c, nlp, nlr, t), dz_pack2(zp[u].y, zr[u].y, c, nlp, nlr, t),
+                             dz_pack2(zp[u].z, zr[u].z, c, nlp, nlr, t), dz_pack2(zp[u].w, zr[u].w, c, nlp, nlr, t));
+      }
+    }
+    const float tot = block_sum(t, sh);
+    if (threadIdx.x == 0) a.kl_row[j] = tot - a.kl_row[j];                 // sum_v q (z_r - z_p) - (LSE_r - LSE_p)
+  }
+}
+
+// ---- fused-gradient backward: the gradients were formed for d_loss = 1 during the forward; scale them by the
+//      upstream gradient (a device scalar) unless it is exactly 1
+__global__ void scale_bf16_kernel(__nv_bfloat16* x, size_t n, const float* __restrict__ d_loss) {
+  const float go = *d_loss;
+  if (go == 1.f) return;
+  uint4* p = reinterpret_cast<uint4*>(x);
+  const size_t nv = n >> 3, stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+    uint4 v = p[i];
+    uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
+      w[k] = pack_bf16x2(f.x * go, f.y * go);
+    }
+    p[i] = v;
   }
 }
 

@@ -33,12 +33,16 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// arrive on the barrier at the same smem offset in CTA `cta` of the cluster
+// arrive on the barrier at the same smem offset in CTA `cta` of the cluster.  Deliberately WITHOUT .release.cluster:
+// that form compiles to MEMBAR.ALL.CTA + ERRBAR, which makes the issuing thread wait for its outstanding TMA loads /
+// global stores every time (measured: the peer producer then keeps only one stage in flight, 3x slower mainloop).
+// The barriers this is used on order asynchronous-proxy traffic (TMA bytes via complete_tx, TMEM reads via
+// tcgen05.wait::ld + fence), not generic-proxy memory.
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
       "r"(cta)
       : "memory");
 }

@@ -47,7 +47,7 @@ class _Call:
     """Owns the ctypes argument block and the tensors it points to for one forward/backward pair."""
 
     def __init__(self, h_pair, labels_pair, signs_pair, h_ref_pol, h_ref_frozen, labels_ref, W, W_ref, alpha,
-                 round_logits, need_dW, dense, chunk_rows, v_offset, V_global):
+                 round_logits, need_dW, dense, chunk_rows, v_offset, V_global, fused):
         lib = _lib.load()
         self.lib = lib
         dev = h_pair.device
@@ -56,7 +56,9 @@ class _Call:
         B2, T, H = hp.shape
         Br, Tr, _ = hr.shape
         flags = (_lib.FLAG_ROUND_LOGITS if round_logits else 0) | (_lib.FLAG_NEED_DW if need_dW else 0) | \
-                (_lib.FLAG_DENSE if dense else 0)
+                (_lib.FLAG_DENSE if dense else 0) | (_lib.FLAG_FUSED_GRAD if fused else 0)
+        self.fused = fused
+        self.grads = None
         self.shape = Shape(B=B2 // 2, T=T, B_ref=Br, T_ref=Tr, H=H, V=V_global, V_local=w.shape[0], v_offset=v_offset,
                            dtype=_lib.DPA_BF16, index_dtype=_lib.DPA_I64 if lp.dtype == torch.int64 else _lib.DPA_I32,
                            flags=flags, chunk_rows=chunk_rows)
@@ -82,8 +84,23 @@ class _Call:
         self.args.scratch_bytes = int(nbytes)
         return scratch
 
+    def _alloc_grads(self):
+        hp, _, _, hr, _, _, w, _ = self.keep
+        dH_pair, dH_ref = torch.empty_like(hp), torch.empty_like(hr)
+        dW = torch.empty_like(w) if self.need_dW else None
+        self.args.dH_pair, self.args.dH_ref, self.args.dW = _ptr(dH_pair), _ptr(dH_ref), _ptr(dW)
+        return dH_pair, dH_ref, dW
+
     def forward(self, vocab_group=None):
         with torch.cuda.device(self.state.device):
+            if self.fused:
+                # loss and (d_loss = 1) gradients in one pass; backward() only scales
+                self.grads = self._alloc_grads()
+                scratch = self._with_scratch(self.ws.fused_bytes)
+                _lib.check(self.lib.dpa_forward(C.byref(self.args), self._stream()), "dpa_forward[fused]")
+                del scratch
+                self.args.scratch, self.args.scratch_bytes = None, 0
+                return
             scratch = self._with_scratch(self.ws.fwd_bytes)
             if vocab_group is None:
                 _lib.check(self.lib.dpa_forward(C.byref(self.args), self._stream()), "dpa_forward")
@@ -104,14 +121,15 @@ class _Call:
         self.args.scratch, self.args.scratch_bytes = None, 0
 
     def backward(self, d_loss: torch.Tensor):
-        hp, _, _, hr, _, _, w, _ = self.keep
         with torch.cuda.device(self.state.device):
             d_loss = d_loss.detach().to(torch.float32).reshape(1).contiguous()
-            dH_pair = torch.empty_like(hp)
-            dH_ref = torch.empty_like(hr)
-            dW = torch.empty_like(w) if self.need_dW else None
+            self.args.d_loss = _ptr(d_loss)
+            if self.fused:
+                _lib.check(self.lib.dpa_backward(C.byref(self.args), self._stream()), "dpa_backward[fused]")
+                grads, self.grads = self.grads, None
+                return grads
+            dH_pair, dH_ref, dW = self._alloc_grads()
             scratch = self._with_scratch(self.ws.bwd_bytes)
-            self.args.d_loss, self.args.dH_pair, self.args.dH_ref, self.args.dW = _ptr(d_loss), _ptr(dH_pair), _ptr(dH_ref), _ptr(dW)
             _lib.check(self.lib.dpa_backward(C.byref(self.args), self._stream()), "dpa_backward")
             del scratch
         self.args.scratch, self.args.scratch_bytes = None, 0
@@ -123,9 +141,10 @@ class DPALossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, h_pair, h_ref_pol, W, labels_pair, signs_pair, labels_ref, h_ref_frozen, W_ref, alpha, round_logits,
-                need_dW, dense, chunk_rows, vocab_group, v_offset, V_global):
+                need_dW, dense, chunk_rows, vocab_group, v_offset, V_global, fused):
+        fused = bool(fused and any(ctx.needs_input_grad[:3]))      # no gradient wanted (eval): statistics only
         call = _Call(h_pair.detach(), labels_pair, signs_pair, h_ref_pol.detach(), h_ref_frozen.detach(), labels_ref,
-                     W.detach(), W_ref.detach(), alpha, round_logits, need_dW, dense, chunk_rows, v_offset, V_global)
+                     W.detach(), W_ref.detach(), alpha, round_logits, need_dW, dense, chunk_rows, v_offset, V_global, fused)
         call.forward(vocab_group)
         ctx.call = call
         ctx.status_t = call.status
@@ -143,7 +162,7 @@ class DPALossFn(torch.autograd.Function):
             dist.all_reduce(dH_pair, group=ctx.vocab_group)      # partial sums over vocab shards
             dist.all_reduce(dH_ref, group=ctx.vocab_group)
         ctx.call = None
-        return (dH_pair, dH_ref, dW) + (None,) * 13
+        return (dH_pair, dH_ref, dW) + (None,) * 14
 
 
 def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.Tensor,
@@ -151,7 +170,7 @@ def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.
              h_ref_frozen: torch.Tensor, W_ref: Optional[torch.Tensor] = None, alpha: float,
              round_logits: bool = True, need_dW: Optional[bool] = None, dense: bool = False, chunk_rows: int = 0,
              vocab_group=None, v_offset: Optional[int] = None, vocab_size: Optional[int] = None,
-             ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+             backward: str = "auto") -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """Fused DPA loss.  Returns (loss, alignment_loss, divergence) as 0-dim fp32 CUDA tensors; `loss` carries grad.
 
     h_pair       [2B, T, H] bf16   final hidden states; first B sequences "pos" (correct), last B "neg"
@@ -169,6 +188,12 @@ def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.
     need_dW                        default W.requires_grad (False under the shipped LoRA recipe: lm_head frozen)
     dense                          process every fed position instead of compacting to rows with a non-zero
                                    contribution (what the reference executes; benchmarking only)
+    backward                       "recompute": forward keeps only per-row statistics, backward recomputes the logits
+                                   chunk-wise (BASELINE north star);  "fused": the forward pass also forms the gradients
+                                   (for d_loss = 1) -- reference-sample logits of one row chunk are kept in bf16 and
+                                   turned into dLogits in place, which saves two of the six GEMMs per such row -- and
+                                   backward only scales by d_loss;  "auto" = "fused" when round_logits is on, a gradient
+                                   is needed and there is no vocab_group, else "recompute".
     Ill-formed phrase ids (K_pos != K_neg, K == 0, id > 255) make the losses NaN and set bits in
     `dpa_last_status()`; the reference raises / returns NaN there.
     """
@@ -183,9 +208,14 @@ def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.
         vocab_size = G * W.shape[0] if vocab_size is None else vocab_size
     else:
         v_offset, vocab_size = 0, W.shape[0]
+    if backward not in ("auto", "recompute", "fused"):
+        raise ValueError("backward must be 'auto', 'recompute' or 'fused'")
+    if backward == "fused" and (not round_logits or vocab_group is not None):
+        raise ValueError("backward='fused' needs round_logits=True and no vocab_group")
+    fused = backward == "fused" or (backward == "auto" and round_logits and vocab_group is None)
     out = DPALossFn.apply(h_pair, h_ref_pol, W, labels_pair, signs_pair, labels_ref, h_ref_frozen, W_ref, float(alpha),
                           bool(round_logits), bool(need_dW), bool(dense), int(chunk_rows), vocab_group, int(v_offset),
-                          int(vocab_size))
+                          int(vocab_size), fused)
     return out
 
 

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DPA_ABI_VERSION 1
+#define DPA_ABI_VERSION 2
 
 typedef enum {
   DPA_OK = 0,
@@ -57,6 +57,10 @@ typedef enum { DPA_I64 = 0, DPA_I32 = 1 } dpa_index_t;
 #define DPA_FLAG_ROUND_LOGITS 1   /* round logits to bf16 before the fp32 softmax, as nn.Linear does in bf16 */
 #define DPA_FLAG_NEED_DW      2   /* lm_head is trainable: backward also produces dW */
 #define DPA_FLAG_DENSE        4   /* do not compact: run every fed position (what the reference executes) */
+#define DPA_FLAG_FUSED_GRAD   8   /* dpa_forward also forms dH (+dW) for d_loss = 1 (reference-sample logits are kept in
+                                     bf16 per row chunk instead of being recomputed); dpa_backward then only scales by
+                                     *d_loss.  Needs DPA_FLAG_ROUND_LOGITS, the gradient pointers at forward time and
+                                     `fused_bytes` of scratch. */
 
 typedef struct {
   int32_t B;          /* sample pairs; h_pair holds 2B sequences, first B "pos"(correct), last B "neg"(hallucinated) */
@@ -77,6 +81,7 @@ typedef struct {
   size_t state_bytes;   /* kept alive by the caller from dpa_forward until dpa_backward returns */
   size_t fwd_bytes;     /* scratch, dpa_forward only */
   size_t bwd_bytes;     /* scratch, dpa_backward only */
+  size_t fused_bytes;   /* scratch of dpa_forward under DPA_FLAG_FUSED_GRAD (dpa_backward then needs none) */
 } dpa_workspace_t;
 
 typedef struct {
@@ -126,6 +131,10 @@ int dpa_row_stats_view(const dpa_args_t* args, void** ptr, size_t* bytes);
 int dpa_profile_enable(int on);
 int dpa_profile_collect(double* ms, int* launches, int n);
 const char* dpa_profile_kind_name(int k);
+
+/* cta_group of the single-accumulator GEMMs: 2 (default; CTA pairs on 256 x 256 tiles, tcgen05 cta_group::2) or 1
+ * (one CTA per 128 x 256 tile).  Also settable with the environment variable DPA_CTA_GROUP before the first call. */
+int dpa_set_cta_group(int cg);
 
 /* Debug / unit-test hook: D[M,N] (fp32) = A * B^T through the same tcgen05 mainloop.
  * a_major/b_major: 0 = K-major ([M,K] / [N,K] row-major), 1 = MN-major ([K,M] / [K,N] row-major). */

@@ -24,7 +24,7 @@ def test_exports_match_header():
     assert declared == set(EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.dpa_version() == 1
+    assert lib.dpa_version() == 2
 
 
 def test_workspace_query_and_shape_validation():

@@ -49,29 +49,32 @@ def _close(a, b, tol):
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_golden_inputs_vs_oracle(name):
-    """Every golden case (inputs cast to bf16): CUDA vs oracle, in reference-bf16 mode and in fp32-maths mode."""
+    """Every golden case (inputs cast to bf16): CUDA vs oracle, in reference-bf16 mode (fused-gradient forward and
+    recompute backward) and in fp32-maths mode."""
     g = load_golden(name)
     t = _to_cuda(g)
-    for round_logits, mode, tol in ((True, "bf16", TOL_LOSS_BF16), (False, "fp64", TOL_LOSS_FP32)):
-        c = _run_cuda(t, round_logits=round_logits)
+    for round_logits, mode, tol, bwd in ((True, "bf16", TOL_LOSS_BF16, "fused"), (True, "bf16", TOL_LOSS_BF16, "recompute"),
+                                          (False, "fp64", TOL_LOSS_FP32, "recompute")):
+        c = _run_cuda(t, round_logits=round_logits, backward=bwd)
         o = _oracle(t, mode)
-        assert _close(c["loss"], o["loss"], tol), (name, mode, c["loss"], o["loss"])
-        assert _close(c["align"], o["align"], tol), (name, mode, c["align"], o["align"])
+        assert _close(c["loss"], o["loss"], tol), (name, mode, bwd, c["loss"], o["loss"])
+        assert _close(c["align"], o["align"], tol), (name, mode, bwd, c["align"], o["align"])
         tol_div = TOL_DIV_FP32 if mode == "fp64" else tol
-        assert abs(c["div"] - o["div"]) <= tol_div * abs(o["div"]) + 1e-7, (name, mode, c["div"], o["div"])
+        assert abs(c["div"] - o["div"]) <= tol_div * abs(o["div"]) + 1e-7, (name, mode, bwd, c["div"], o["div"])
         for k in ("dH_pair", "dH_ref", "dW"):
-            assert rel(c[k], o[k]) <= TOL_GRAD_BF16, (name, mode, k, rel(c[k], o[k]))
+            assert rel(c[k], o[k]) <= TOL_GRAD_BF16, (name, mode, bwd, k, rel(c[k], o[k]))
         # structural zeros: last position and rows without contribution get exactly zero gradient
         assert np.all(c["dH_pair"][:, -1] == 0) and np.all(c["dH_ref"][:, -1] == 0)
         assert np.all(c["dH_pair"][:, :-1][~o["active_pair"]] == 0)
         assert np.all(c["dH_ref"][:, :-1][~o["active_ref"]] == 0)
 
 
+@pytest.mark.parametrize("bwd", ["fused", "recompute"])
 @pytest.mark.parametrize("name", ["tiny_bf16", "small_bf16"])
-def test_golden_reference_outputs_bf16(name):
+def test_golden_reference_outputs_bf16(name, bwd):
     """bf16 golden cases: CUDA vs what the reference itself produced in bf16 (tests/golden, oracle/gen_golden.py)."""
     g = load_golden(name)
-    c = _run_cuda(_to_cuda(g), round_logits=True)
+    c = _run_cuda(_to_cuda(g), round_logits=True, backward=bwd)
     assert _close(c["loss"], float(g["ref_loss"]), TOL_LOSS_BF16)
     assert _close(c["align"], float(g["ref_align"]), TOL_LOSS_BF16)
     for k in ("dH_pair", "dH_ref", "dW"):
@@ -97,11 +100,13 @@ def _synth(name="small", seed=3, **over):
 def test_synthetic_shapes_vs_oracle(over):
     """Ragged T, V not a multiple of the tile, H not a multiple of 256, B_ref != B."""
     t, shape = _synth(**over)
-    c = _run_cuda(t)
     o = _oracle(t, "bf16")
-    assert _close(c["loss"], o["loss"], TOL_LOSS_BF16) and _close(c["align"], o["align"], TOL_LOSS_BF16)
-    for k in ("dH_pair", "dH_ref", "dW"):
-        assert rel(c[k], o[k]) <= TOL_GRAD_BF16, (k, rel(c[k], o[k]))
+    for bwd in ("fused", "recompute"):
+        c = _run_cuda(t, backward=bwd)
+        assert _close(c["loss"], o["loss"], TOL_LOSS_BF16) and _close(c["align"], o["align"], TOL_LOSS_BF16), bwd
+        assert _close(c["div"], o["div"], TOL_LOSS_BF16), bwd
+        for k in ("dH_pair", "dH_ref", "dW"):
+            assert rel(c[k], o[k]) <= TOL_GRAD_BF16, (bwd, k, rel(c[k], o[k]))
 
 
 def test_int32_labels_and_frozen_head():
@@ -115,25 +120,42 @@ def test_int32_labels_and_frozen_head():
     assert a["loss"] == b["loss"] and np.array_equal(a["dH_pair"], b["dH_pair"])
 
 
-def test_dense_equals_compact_and_chunking_invariant():
+@pytest.mark.parametrize("bwd", ["fused", "recompute"])
+def test_dense_equals_compact_and_chunking_invariant(bwd):
     """Processing every position (what the reference executes) gives the same loss and gradients as the compacted
-    path; the backward row-chunk size does not change the result."""
+    path; the row-chunk size does not change the result."""
     t, _ = _synth()
-    a = _run_cuda(t)
-    d = _run_cuda(t, dense=True)
-    ch = _run_cuda(t, chunk_rows=128)
-    assert _close(d["loss"], a["loss"], 1e-6)
+    a = _run_cuda(t, backward=bwd)
+    d = _run_cuda(t, dense=True, backward=bwd)
+    ch = _run_cuda(t, chunk_rows=256, backward=bwd)
+    assert _close(d["loss"], a["loss"], 1e-6) and _close(ch["loss"], a["loss"], 1e-6)
     for k in ("dH_pair", "dH_ref"):
         assert np.array_equal(a[k], d[k]) and np.array_equal(a[k], ch[k]), k
     assert rel(d["dW"], a["dW"]) <= 1e-5 and rel(ch["dW"], a["dW"]) <= 2e-3   # fp32 partial sums regroup
 
 
-def test_grad_output_scaling_and_determinism():
+def test_fused_matches_recompute():
+    """The two gradient strategies see the same bf16 logits: losses identical, gradients equal to rounding."""
+    t, _ = _synth(seed=11)
+    a = _run_cuda(t, backward="fused")
+    b = _run_cuda(t, backward="recompute")
+    assert a["loss"] == b["loss"] and a["align"] == b["align"] and a["div"] == b["div"]
+    for k in ("dH_pair", "dH_ref", "dW"):
+        assert rel(a[k], b[k]) <= 1e-3, (k, rel(a[k], b[k]))
+    with torch.no_grad():                                  # evaluation: statistics only, no gradient work, same loss
+        from halva_b200 import dpa_loss
+        l, _, _ = dpa_loss(t["h_pair"], t["labels_pair"], t["signs_pair"], t["h_ref_pol"], t["labels_ref"], t["W"],
+                           h_ref_frozen=t["h_ref_frz"], alpha=t["alpha"])
+    assert l.item() == a["loss"]
+
+
+@pytest.mark.parametrize("bwd", ["fused", "recompute"])
+def test_grad_output_scaling_and_determinism(bwd):
     t, _ = _synth()
-    a = _run_cuda(t)
-    b = _run_cuda(t)
+    a = _run_cuda(t, backward=bwd)
+    b = _run_cuda(t, backward=bwd)
     assert a["loss"] == b["loss"] and np.array_equal(a["dW"], b["dW"]) and np.array_equal(a["dH_pair"], b["dH_pair"])
-    s = _run_cuda(t, grad_out=0.25)                     # Trainer divides by gradient_accumulation_steps
+    s = _run_cuda(t, grad_out=0.25, backward=bwd)       # Trainer divides by gradient_accumulation_steps
     assert rel(s["dH_pair"], 0.25 * a["dH_pair"]) <= 5e-3 and rel(s["dW"], 0.25 * a["dW"]) <= 5e-3
 
 

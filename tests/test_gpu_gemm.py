@@ -15,14 +15,22 @@ def _mk(M, N, K, a_major, b_major, seed=0):
     return As, Bs, ref
 
 
+@pytest.mark.parametrize("cg", [2, 1])
 @pytest.mark.parametrize("a_major,b_major,bn", [(0, 0, 256), (0, 0, 128), (0, 1, 256), (1, 1, 256), (1, 0, 256)])
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 256), (384, 320, 200), (1000, 1024, 4096)])
-def test_debug_gemm(a_major, b_major, bn, M, N, K):
-    from halva_b200 import debug_gemm
+def test_debug_gemm(a_major, b_major, bn, M, N, K, cg):
+    """cg = tcgen05 cta_group of the 256-wide tiles: 2 = CTA pairs sharing one M=256 MMA (default), 1 = single CTA."""
+    from halva_b200 import _lib, debug_gemm
     if (a_major == 1 and M % 8) or (b_major == 1 and N % 8):
         pytest.skip("alignment")
+    if bn == 128 and cg == 1:
+        pytest.skip("the 128-wide (dual-accumulator) tile shape is cta_group 1 only: covered by cg=2's run")
     As, Bs, ref = _mk(M, N, K, a_major, b_major)
-    D = debug_gemm(As, Bs, a_major, b_major, bn)
+    _lib.set_cta_group(cg)
+    try:
+        D = debug_gemm(As, Bs, a_major, b_major, bn)
+    finally:
+        _lib.set_cta_group(2)
     torch.cuda.synchronize()
     err = (D - ref).abs().max().item()
     scale = ref.abs().max().item()
