@@ -131,22 +131,23 @@ def test_dense_equals_compact_and_chunking_invariant(bwd):
     assert _close(d["loss"], a["loss"], 1e-6) and _close(ch["loss"], a["loss"], 1e-6)
     for k in ("dH_pair", "dH_ref"):
         assert np.array_equal(a[k], d[k]) and np.array_equal(a[k], ch[k]), k
-    assert rel(d["dW"], a["dW"]) <= 1e-5 and rel(ch["dW"], a["dW"]) <= 2e-3   # fp32 partial sums regroup
+    assert rel(d["dW"], a["dW"]) <= 1e-4 and rel(ch["dW"], a["dW"]) <= 2e-3   # fp32 partial sums regroup (K order changes)
 
 
 def test_fused_matches_recompute():
-    """The two gradient strategies see the same bf16 logits: losses identical, gradients equal to rounding."""
+    """The two gradient strategies see the same bf16 logits: alignment loss identical, divergence equal to fp32
+    summation order (online partial sums vs one pass over the kept logits), gradients equal to rounding."""
     t, _ = _synth(seed=11)
     a = _run_cuda(t, backward="fused")
     b = _run_cuda(t, backward="recompute")
-    assert a["loss"] == b["loss"] and a["align"] == b["align"] and a["div"] == b["div"]
+    assert a["align"] == b["align"] and _close(a["div"], b["div"], 1e-5) and _close(a["loss"], b["loss"], 1e-6)
     for k in ("dH_pair", "dH_ref", "dW"):
         assert rel(a[k], b[k]) <= 1e-3, (k, rel(a[k], b[k]))
     with torch.no_grad():                                  # evaluation: statistics only, no gradient work, same loss
         from halva_b200 import dpa_loss
         l, _, _ = dpa_loss(t["h_pair"], t["labels_pair"], t["signs_pair"], t["h_ref_pol"], t["labels_ref"], t["W"],
                            h_ref_frozen=t["h_ref_frz"], alpha=t["alpha"])
-    assert l.item() == a["loss"]
+    assert _close(l.item(), a["loss"], 1e-6)
 
 
 @pytest.mark.parametrize("bwd", ["fused", "recompute"])
