@@ -193,6 +193,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from halva_b200 import _lib, dpa_loss, read_status
+    from halva_b200.dist import average_gradients
     from halva_b200.synth import CONFIGS, algorithmic_flops, make_inputs
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -223,7 +224,7 @@ def run_ours(args):
                                     backward=args.backward)
         loss.backward()
         if world > 1 and need_dw:          # data parallel: average the lm_head gradient over ranks (NCCL over NVLink)
-            dist.all_reduce(W.grad, op=dist.ReduceOp.AVG)
+            average_gradients([W.grad])
         return loss, align, div
 
     def barrier():

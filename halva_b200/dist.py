@@ -1,0 +1,95 @@
+"""Host-side helpers for the two ways the DPA-loss path shards across the GPUs of one box.
+
+Data parallel   -- sample pairs (+ their reference samples) are independent units: each rank runs ``dpa_loss`` on its
+                   shard with no data-path collective; the only exchange is the all-reduce of trainable gradients
+                   (what DeepSpeed ZeRO / DDP do for the reference, /root/reference/src/hallava_7b.sh:30-34).
+Vocab parallel  -- lm_head rows are split over a process group; ``dpa_loss(..., vocab_group=g)`` exchanges one
+                   all-gather of per-row statistics in the forward and all-reduces dH in the backward.
+
+Everything here is backend-agnostic torch.distributed (NCCL on the GPUs, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def vocab_shard_bounds(vocab: int, world: int, rank: int, multiple: int = 8) -> Tuple[int, int]:
+    """[v0, v1) of this rank's lm_head rows: contiguous, sizes differ by at most `multiple`, every boundary except the
+    last is a multiple of `multiple` (16-byte rows for the TMA descriptors of the bf16 dz scratch)."""
+    if not 0 <= rank < world:
+        raise ValueError("rank outside the group")
+    units = -(-vocab // multiple)
+    lo = (units * rank) // world * multiple
+    hi = (units * (rank + 1)) // world * multiple
+    return min(lo, vocab), min(hi, vocab)
+
+
+def dp_shard(n_samples: int, world: int, rank: int) -> range:
+    """Sample pairs (and their reference samples) owned by `rank`: contiguous, as even as possible."""
+    lo = (n_samples * rank) // world
+    hi = (n_samples * (rank + 1)) // world
+    return range(lo, hi)
+
+
+def average_gradients(tensors: Iterable[torch.Tensor], group=None, bucket_bytes: int = 512 << 20) -> None:
+    """In-place mean over the group of every tensor (gradients of the trainable parameters the path produced, e.g.
+    dW [V,H]).  Tensors are packed into flat buckets so that small ones share a launch; NVSwitch makes the cost
+    latency + bytes / (per-GPU bandwidth), so buckets are sized for overlap, not for link count."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    world = dist.get_world_size(group)
+    bucket: List[torch.Tensor] = []
+    size = 0
+
+    def flush():
+        nonlocal bucket, size
+        if not bucket:
+            return
+        if len(bucket) == 1 and bucket[0].is_contiguous():
+            dist.all_reduce(bucket[0], group=group)
+            bucket[0].div_(world)
+        else:
+            flat = torch.cat([t.reshape(-1) for t in bucket])
+            dist.all_reduce(flat, group=group)
+            flat.div_(world)
+            off = 0
+            for t in bucket:
+                t.copy_(flat[off:off + t.numel()].view_as(t))
+                off += t.numel()
+        bucket, size = [], 0
+
+    for t in tensors:
+        if t is None:
+            continue
+        nbytes = t.numel() * t.element_size()
+        if bucket and (size + nbytes > bucket_bytes or t.dtype != bucket[0].dtype):
+            flush()
+        bucket.append(t)
+        size += nbytes
+    flush()
+
+
+# ---- layout of the vocab-parallel exchange record (dpa_row_stats_view): [cap_pair x {m,s,z_y,0}] [cap_ref x {m_p,s_p,m_r,s_r}]
+#      [cap_ref x u] fp32.  merge_row_stats is the host restatement of merge_strided_kernel, used by the CPU protocol test.
+def row_stats_record_floats(cap_pair: int, cap_ref: int) -> int:
+    return 4 * cap_pair + 4 * cap_ref + cap_ref
+
+
+def merge_row_stats(records: Sequence[torch.Tensor], cap_pair: int, cap_ref: int):
+    """records: one flat fp32 tensor per vocab shard.  Returns (pair [cap_pair,3] = m,s,z_y; ref [cap_ref,5] = m_p,s_p,m_r,s_r,u)
+    with the shards' partial (max, sum-exp) rescaled to the common maximum and z_y / u summed."""
+    pair = torch.stack([r[:4 * cap_pair].view(cap_pair, 4) for r in records])                          # [G,cap,4]
+    ref = torch.stack([r[4 * cap_pair:4 * cap_pair + 4 * cap_ref].view(cap_ref, 4) for r in records])
+    u = torch.stack([r[4 * cap_pair + 4 * cap_ref:].view(cap_ref) for r in records])
+    m = pair[..., 0].max(0).values
+    s = (pair[..., 1] * torch.exp(pair[..., 0] - m)).sum(0)
+    zy = pair[..., 2].sum(0)
+    mp, mr = ref[..., 0].max(0).values, ref[..., 2].max(0).values
+    wr = torch.exp(ref[..., 2] - mr)
+    sp = (ref[..., 1] * torch.exp(ref[..., 0] - mp)).sum(0)
+    sr = (ref[..., 3] * wr).sum(0)
+    uu = (u * wr).sum(0)
+    return torch.stack([m, s, zy], -1), torch.stack([mp, sp, mr, sr, uu], -1)

@@ -1,0 +1,85 @@
+"""Two-GPU checks (NCCL): vocab-parallel lm_head equals the single-GPU result on the same rows; data-parallel
+gradient averaging equals the mean of per-shard gradients.  Skipped on boxes with fewer than 2 GPUs
+(run with `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _rel(a, b):
+    return float((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-30))
+
+
+def _worker(rank, world, port, out):
+    import dataclasses
+    import torch.distributed as dist
+    from halva_b200 import dpa_loss
+    from halva_b200.dist import average_gradients, dp_shard, vocab_shard_bounds
+    from halva_b200.synth import CONFIGS, make_inputs
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        shape = dataclasses.replace(CONFIGS["small"], V=1024, B=4, B_ref=4)
+        t = make_inputs(shape, seed=5, device=dev, shared_head=False)       # identical on every rank (same seed)
+
+        def run(W, W_ref, sel_pair=None, sel_ref=None, **kw):
+            hp = (t["h_pair"] if sel_pair is None else t["h_pair"][sel_pair]).clone().requires_grad_(True)
+            hr = (t["h_ref_pol"] if sel_ref is None else t["h_ref_pol"][sel_ref]).clone().requires_grad_(True)
+            Wl = W.clone().requires_grad_(True)
+            pick = lambda k, s: t[k] if s is None else t[k][s]
+            loss, align, div = dpa_loss(hp, pick("labels_pair", sel_pair), pick("signs_pair", sel_pair), hr, pick("labels_ref", sel_ref),
+                                        Wl, h_ref_frozen=pick("h_ref_frz", sel_ref), W_ref=W_ref, alpha=t["alpha"], **kw)
+            loss.backward()
+            return loss.detach(), div.detach(), hp.grad, hr.grad, Wl.grad
+
+        # ---- vocab parallel: each rank holds V/2 rows of W and W_ref, all rows of h
+        full = run(t["W"], t["W_ref"], backward="recompute")
+        v0, v1 = vocab_shard_bounds(shape.V, world, rank)
+        part = run(t["W"][v0:v1].contiguous(), t["W_ref"][v0:v1].contiguous(), vocab_group=dist.group.WORLD, v_offset=v0, vocab_size=shape.V)
+        assert abs(part[0].item() - full[0].item()) <= 1e-5 * abs(full[0].item()), (part[0].item(), full[0].item())
+        assert abs(part[1].item() - full[1].item()) <= 1e-4 * abs(full[1].item()) + 1e-7
+        assert _rel(part[2], full[2]) <= 5e-3 and _rel(part[3], full[3]) <= 5e-3        # bf16 partial sums all-reduced
+        assert _rel(part[4], full[4][v0:v1]) <= 1e-3                                    # dW stays sharded
+        # ---- data parallel: pairs split over ranks, lm_head gradient averaged
+        B = shape.B
+        mine = list(dp_shard(B, world, rank))
+        sel = torch.tensor(mine + [B + i for i in mine], device=dev)
+        selr = torch.tensor(mine, device=dev)
+        loc = run(t["W"], t["W_ref"], sel, selr)
+        dW = loc[4].clone()
+        average_gradients([dW])
+        others = []
+        for r in range(world):
+            m = list(dp_shard(B, world, r))
+            others.append(run(t["W"], t["W_ref"], torch.tensor(m + [B + i for i in m], device=dev), torch.tensor(m, device=dev))[4].float())
+        want = sum(others) / world
+        assert _rel(dW, want) <= 1e-2
+        out[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_gpu_vocab_parallel_and_data_parallel():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    world = 2
+    out = mp.get_context("spawn").Manager().dict()
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert dict(out) == {0: 1, 1: 1}
