@@ -112,7 +112,7 @@ struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN_CTA * BK * 2;
   static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (DUAL ? 2 : 1);
-  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;   // 6 x 32 KiB (pair), 4 x 48 KiB, 3 x 64 KiB (dual)
+  static constexpr int STAGES_RAW = (227 * 1024 - 1280) / STAGE_BYTES;   // 7 x 32 KiB (pair), 4 x 48 KiB, 3 x 64 KiB (dual)
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int ACC_COLS = DUAL ? 2 * BN : BN;             // TMEM columns per accumulator stage
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
@@ -134,13 +134,12 @@ __device__ __forceinline__ void load_operand(uint8_t* dst, const CUtensorMap* tm
     }
   }
 }
-template <int MAJ>
-__device__ __forceinline__ uint64_t operand_desc(uint32_t saddr, int kstep) {
-  if constexpr (MAJ == KMAJOR)     // rows of 128 B, 8-row swizzle atoms 1024 B apart; K advances inside the row
-    return make_smem_desc_sw128(saddr + kstep * (UMMA_K * 2), 0, 1024);
-  else                             // atoms [64 mn x 8 k] 1024 B apart along K, BK*128 B apart along MN
-    return make_smem_desc_sw128(saddr + kstep * (UMMA_K * 128), BK * 128, 1024);
-}
+// K-major: rows of 128 B, 8-row swizzle atoms 1024 B apart, K advances inside the row (UMMA_K * 2 bytes per MMA).
+// MN-major: atoms [64 mn x 8 k] 1024 B apart along K, BK * 128 B apart along MN (UMMA_K * 128 bytes per MMA).
+template <int MAJ> struct OperandDesc {
+  static constexpr uint64_t HI = MAJ == KMAJOR ? smem_desc_hi_sw128(0, 1024) : smem_desc_hi_sw128(BK * 128, 1024);
+  static constexpr uint32_t KSTEP = (MAJ == KMAJOR ? UMMA_K * 2 : UMMA_K * 128) >> 4;   // in the >>4 address field
+};
 
 template <class Cfg, class Epi>
 __global__ void __launch_bounds__(kNumThreads, 1)
@@ -210,7 +209,7 @@ dpa_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int nt = ng * tpu; nt < nt_end; ++nt) {
         for (int kb = 0; kb < tr.k_blocks; ++kb) {
           mbar_wait(&empty[st], ph ^ 1);
-          if (lane == 0) {
+          if (elect_one()) {
             if constexpr (CG == 1) mbar_arrive_expect_tx(&full[st], Cfg::STAGE_BYTES);
             load_operand<Cfg::AMAJ, BM, CG>(sA + st * Cfg::A_BYTES, &tmA, &full[st], tr.a_row0 + mt * BM, tr.a_k0 + kb * BK);
             load_operand<Cfg::BMAJ, Cfg::BN_CTA, CG>(sB + st * Cfg::B_BYTES, &tmB, &full[st], nt * BN + cta_rank * Cfg::BN_CTA,
@@ -233,6 +232,10 @@ dpa_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp == 1 && leader) {
     // ------------------------------------------------------------- MMA issuer (leader CTA only)
     constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN, Cfg::AMAJ, Cfg::BMAJ);
+    using DA = OperandDesc<Cfg::AMAJ>;
+    using DB = OperandDesc<Cfg::BMAJ>;
+    const uint32_t a_base = smem_u32(sA) >> 4, b_base = smem_u32(sB) >> 4;
+    const uint32_t a2_base = smem_u32(sA2) >> 4, b2_base = smem_u32(sB2) >> 4;
     int st = 0; uint32_t ph = 0; uint32_t it = 0;
     for (int u = group_id; u < n_units; u += n_cta_groups) {
       int mu, ng; decode(u, mu, ng);
@@ -245,16 +248,17 @@ dpa_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int kb = 0; kb < tr.k_blocks; ++kb) {
           mbar_wait(&full[st], ph);
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t a0 = smem_u32(sA + st * Cfg::A_BYTES), b0 = smem_u32(sB + st * Cfg::B_BYTES);
+          if (elect_one()) {
+            const uint32_t a_lo = a_base + st * (Cfg::A_BYTES >> 4), b_lo = b_base + st * (Cfg::B_BYTES >> 4);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k)
-              umma_bf16<CG>(acc, operand_desc<Cfg::AMAJ>(a0, k), operand_desc<Cfg::BMAJ>(b0, k), idesc, (kb | k) != 0);
+              umma_bf16<CG>(acc, DA::HI | (uint64_t)(a_lo + k * DA::KSTEP), DB::HI | (uint64_t)(b_lo + k * DB::KSTEP), idesc, (kb | k) != 0);
             if constexpr (Cfg::DUAL) {
-              const uint32_t a2 = smem_u32(sA2 + st * Cfg::A_BYTES), b2 = smem_u32(sB2 + st * Cfg::B_BYTES);
+              const uint32_t a2_lo = a2_base + st * (Cfg::A_BYTES >> 4), b2_lo = b2_base + st * (Cfg::B_BYTES >> 4);
 #pragma unroll
               for (int k = 0; k < BK / UMMA_K; ++k)
-                umma_bf16<CG>(acc + BN, operand_desc<Cfg::AMAJ>(a2, k), operand_desc<Cfg::BMAJ>(b2, k), idesc, (kb | k) != 0);
+                umma_bf16<CG>(acc + BN, DA::HI | (uint64_t)(a2_lo + k * DA::KSTEP), DB::HI | (uint64_t)(b2_lo + k * DB::KSTEP), idesc,
+                              (kb | k) != 0);
             }
             umma_commit<CG>(&empty[st]);              // smem slot reusable (in both CTAs) once these MMAs retire
             if (kb == tr.k_blocks - 1) umma_commit<CG>(&tfull[as]);

@@ -16,6 +16,17 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+// One lane of the (converged) warp.  ptxas knows the guarded region runs on a single thread, so tensor-core / TMA
+// operands move to uniform registers once instead of through an ELECT + vote loop per instruction.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -191,6 +202,12 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
   return d;
+}
+// The same descriptor split for hot loops: constant upper part (LBO, SBO, version, layout) | 14-bit start-address field
+// (bytes >> 4) that the issuer advances with plain adds.
+__host__ __device__ constexpr uint64_t smem_desc_hi_sw128(uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
 }
 // Instruction descriptor for kind::f16 with bf16 A/B and fp32 D.
 //   [4,6) D fmt (1=f32) | [7,10) A fmt (1=bf16) | [10,13) B fmt | [15] A MN-major | [16] B MN-major |
