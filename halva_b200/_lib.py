@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libhalva_dpa.so")
+LIB_PATH = os.environ.get("HALVA_DPA_LIB") or os.path.join(HERE, "libhalva_dpa.so")   # override: A/B builds of the kernels
 
 DPA_BF16 = 0
 DPA_I64, DPA_I32 = 0, 1

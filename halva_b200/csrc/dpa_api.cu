@@ -311,7 +311,8 @@ int run_forward_gemms(const dpa_args_t* a, const Layout& L, const DeviceInfo* d,
   {
     using Epi = EpiStatsPair<kBnPair, ROUND>;
     GemmWork w{meta, KIND_FWD_PAIR, 0, 0, 0, s.V_local, s.H, kTpuPair};
-    typename Epi::Params ep{at<int>(a->state, L.lab_pair), at<float4>(a->scratch, L.f_part_pair), L.cap_pair, s.V_local, s.v_offset};
+    typename Epi::Params ep{at<int>(a->state, L.lab_pair), at<float4>(a->scratch, L.f_part_pair), L.cap_pair, s.V_local, s.v_offset,
+                            nullptr, 0, 0};
     ProfScope ps(PK_FWD_PAIR, 1, st);
     if ((rc = launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHp, tmW256, tmW128, w, ep, "fwd_pair"))) return rc;
   }
@@ -511,7 +512,9 @@ int forward_fused_impl(const dpa_args_t* a, cudaStream_t st) {
   {
     using Epi = EpiStatsPair<kBnPair, true>;
     GemmWork w{meta, KIND_FWD_PAIR, 0, 0, 0, s.V_local, s.H, kTpuPair};
-    typename Epi::Params ep{at<int>(a->state, L.lab_pair), at<float4>(a->scratch, L.u_part_pair), L.cap_pair, s.V_local, s.v_offset};
+    // pair rows that fall into row chunk 0 keep their logits in the chunk's dz buffer (nothing else touches it until then)
+    typename Epi::Params ep{at<int>(a->state, L.lab_pair), at<float4>(a->scratch, L.u_part_pair), L.cap_pair, s.V_local, s.v_offset,
+                            dz, L.ldz, L.chunk_rows};
     ProfScope ps(PK_FWD_PAIR, 1, st);
     if ((rc = launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHp, tmW256, tmW128, w, ep, "fwd_pair"))) return rc;
   }
@@ -532,7 +535,13 @@ int forward_fused_impl(const dpa_args_t* a, cudaStream_t st) {
 
   // ---- row chunks of the packed space [pair rows | reference-sample rows]
   for (int ch = 0; ch < L.n_chunks; ++ch) {
-    {
+    if (ch == 0) {
+      DzPairElemArgs e{meta, L.chunk_rows, dz, L.ldz, s.V_local, s.v_offset, at<int>(a->state, L.lab_pair),
+                       at<float>(a->state, L.lse_pair), at<float>(a->state, L.coef_pair)};
+      ProfScope ps(PK_DZ_ELEM, 1, st);
+      dz_pair_elem_kernel<<<d->sms * 8, 256, 0, st>>>(e);
+      LAUNCH_CHECK("dz_pair_elem");
+    } else if ((long long)ch * L.chunk_rows < L.cap_pair) {      // pair rows beyond chunk 0 (if any): recompute
       using Epi = EpiDzPair<kBnPair, true>;
       GemmWork w{meta, KIND_DZ_PAIR, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair};
       typename Epi::Params ep{at<int>(a->state, L.lab_pair), at<float>(a->state, L.lse_pair), at<float>(a->state, L.coef_pair),

@@ -452,6 +452,50 @@ __global__ void __launch_bounds__(256) dz_kl_elem_kernel(DzElemArgs a) {
   }
 }
 
+// ---- fused-gradient forward, pair rows of row chunk 0: dz = coef (onehot(y) - softmax(z)) in place over the logits the
+//      statistics GEMM kept (2 B read + 2 B written per logit) -- the recompute GEMM only runs for pair rows beyond chunk 0
+struct DzPairElemArgs {
+  const DpaMeta* meta; int chunk_rows;
+  __nv_bfloat16* dz; int ldz, v_local, v_offset;
+  const int* labels; const float* lse; const float* coef;        // indexed by packed row
+};
+__device__ __forceinline__ uint32_t dzp_pack2(uint32_t z, float c, float nl, int col, int y) {
+  const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&z));
+  float a = -c * fast_exp2(fmaf(f.x, kLog2e, nl)), b = -c * fast_exp2(fmaf(f.y, kLog2e, nl));
+  a += (col == y) ? c : 0.f;
+  b += (col + 1 == y) ? c : 0.f;
+  return pack_bf16x2(a, b);
+}
+__global__ void __launch_bounds__(256) dz_pair_elem_kernel(DzPairElemArgs a) {
+  const int hi = min(a.meta->p0, a.chunk_rows);
+  const int nvec = (a.v_local + 7) >> 3;
+  constexpr int U = 4;
+  for (int r = blockIdx.x; r < hi; r += gridDim.x) {
+    uint4* pz = reinterpret_cast<uint4*>(a.dz + (size_t)r * a.ldz);
+    const float c = a.coef[r];
+    if (c == 0.f) {                                   // padding rows (and ignored rows in dense mode)
+      for (int v = threadIdx.x; v < nvec; v += blockDim.x) pz[v] = make_uint4(0, 0, 0, 0);
+      continue;
+    }
+    const float nl = -a.lse[r] * kLog2e;
+    const int y = a.labels[r] - a.v_offset;
+    for (int v0 = threadIdx.x; v0 < nvec; v0 += U * blockDim.x) {
+      uint4 z[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) { const int v = v0 + u * blockDim.x; if (v < nvec) z[u] = pz[v]; }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int v = v0 + u * blockDim.x;
+        if (v < nvec) {
+          const int col = v * 8;
+          pz[v] = make_uint4(dzp_pack2(z[u].x, c, nl, col, y), dzp_pack2(z[u].y, c, nl, col + 2, y),
+                             dzp_pack2(z[u].z, c, nl, col + 4, y), dzp_pack2(z[u].w, c, nl, col + 6, y));
+        }
+      }
+    }
+  }
+}
+
 // ---- fused-gradient backward: the gradients were formed for d_loss = 1 during the forward; scale them by the
 //      upstream gradient (a device scalar) unless it is exactly 1
 __global__ void scale_bf16_kernel(__nv_bfloat16* x, size_t n, const float* __restrict__ d_loss) {

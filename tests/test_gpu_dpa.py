@@ -128,9 +128,11 @@ def test_dense_equals_compact_and_chunking_invariant(bwd):
     a = _run_cuda(t, backward=bwd)
     d = _run_cuda(t, dense=True, backward=bwd)
     ch = _run_cuda(t, chunk_rows=256, backward=bwd)
-    assert _close(d["loss"], a["loss"], 1e-6) and _close(ch["loss"], a["loss"], 1e-6)
+    dch = _run_cuda(t, dense=True, chunk_rows=256, backward=bwd)    # pair rows spill past chunk 0: kept-logits + recompute mix
+    assert _close(d["loss"], a["loss"], 1e-6) and _close(ch["loss"], a["loss"], 1e-6) and _close(dch["loss"], a["loss"], 1e-6)
     for k in ("dH_pair", "dH_ref"):
         assert np.array_equal(a[k], d[k]) and np.array_equal(a[k], ch[k]), k
+        assert rel(dch[k], a[k]) <= 1e-3, k
     assert rel(d["dW"], a["dW"]) <= 1e-4 and rel(ch["dW"], a["dW"]) <= 2e-3   # fp32 partial sums regroup (K order changes)
 
 
