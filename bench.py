@@ -33,6 +33,18 @@ def load_peaks():
     return dict(bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
 
 
+def load_traffic(kernel_class):
+    """DRAM bytes (read + write) of the largest launch of `kernel_class` from the committed ncu --set full capture."""
+    p = os.path.join(ROOT, "profiles", "kernel_metrics.json")
+    if not os.path.exists(p):
+        return None, "no ncu capture committed"
+    d = json.load(open(p))
+    k = d.get("kernels", {}).get(kernel_class)
+    if not k:
+        return None, f"no {kernel_class} launch in {d.get('source')}"
+    return k["dram_bytes"], f"largest {kernel_class} launch in {d.get('source')} ({k['launch']})"
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
     REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
@@ -261,6 +273,32 @@ def run_ours(args):
         ms = tt.item()
     loss_val = loss.item()
 
+    # ---- variant: lm_head frozen (the shipped LoRA recipe, /root/reference/llava/train/train_halva.py:167-168): no dW
+    ms_frozen = None
+    if need_dw and not args.no_variants:
+        Wf = W.detach()
+
+        def step_frozen():
+            hp.grad = None
+            hr.grad = None
+            l, _, _ = dpa_loss(hp, t["labels_pair"], t["signs_pair"], hr, t["labels_ref"], Wf, h_ref_frozen=t["h_ref_frz"],
+                               alpha=shape.alpha, dense=args.dense, chunk_rows=args.chunk_rows, backward=args.backward)
+            l.backward()
+
+        for _ in range(3):
+            step_frozen()
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step_frozen()
+        e1.record()
+        barrier()
+        ms_frozen = e0.elapsed_time(e1) / args.steps
+        if world > 1:
+            tt = torch.tensor([ms_frozen], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms_frozen = tt.item()
+
     # ---- end to end: host (pinned) buffers in, losses out, H2D double-buffered against the previous step's compute
     ms_e2e, h2d_bytes = None, 0
     if not args.no_e2e:
@@ -290,12 +328,17 @@ def run_ours(args):
         exec_flops.update(stash_ref=2 * n_r * unit_flops)
     else:
         exec_flops.update(fwd_ref=2 * n_r * unit_flops, dz_ref=2 * n_r * unit_flops)
+    if fused and (args.chunk_rows or 16384) >= n_p:
+        exec_flops.pop("dz_pair")          # every pair row sits in row chunk 0: its logits were kept, no recompute GEMM ran
     kernels = {}
     for k, (t_ms, launches) in prof.items():
         per_step = t_ms / K
+        if launches == 0 and per_step == 0:
+            continue
         kernels[k] = dict(ms_per_step=round(per_step, 4), launches_per_step=launches / K,
                           tflops=round(exec_flops[k] / (per_step * 1e-3) / 1e12, 1) if k in exec_flops and per_step > 0 else None)
-    gemm_kinds = [k for k in exec_flops if kernels.get(k, {}).get("ms_per_step", 0) > 0]
+    exec_flops = {k: v for k, v in exec_flops.items() if kernels.get(k, {}).get("ms_per_step", 0) > 0}
+    gemm_kinds = list(exec_flops)
     dom = max(gemm_kinds, key=lambda k: kernels[k]["ms_per_step"])
     n_launch_dom = max(1.0, kernels[dom]["launches_per_step"])
     dom_ms_launch = kernels[dom]["ms_per_step"] / n_launch_dom
@@ -303,8 +346,11 @@ def run_ours(args):
     f_alg_dense = algorithmic_flops(shape, need_dw)
     f_alg_active = algorithmic_flops(shape, need_dw, rows_pair, rows_ref)
     gemm_ms = sum(kernels[k]["ms_per_step"] for k in gemm_kinds)
+    traffic, traffic_note = load_traffic(dom)
     roofline = dict(bound="tensor", kernel=dom, achieved=round(achieved, 1), peak=peaks["bf16_tflops"], unit="TFLOP/s",
-                    frac=round(achieved / peaks["bf16_tflops"], 4), traffic=None, peak_source=peaks["source"],
+                    frac=round(achieved / peaks["bf16_tflops"], 4), traffic=traffic, traffic_note=traffic_note,
+                    peak_source=peaks["source"], frac_of_sustained=round(achieved / peaks["bf16_tflops_sustained"], 4)
+                    if peaks.get("bf16_tflops_sustained") else None,
                     flops_per_launch=exec_flops[dom] / n_launch_dom, ms_per_launch=round(dom_ms_launch, 4),
                     share_of_step=round(kernels[dom]["ms_per_step"] / ms_step, 3),
                     note="FLOPs executed by this kernel for the rows it processed (row compaction: only rows with a non-zero "
@@ -323,6 +369,9 @@ def run_ours(args):
                 step_tc_frac_active_alg=round(f_alg_active / (ms_step * 1e-3) / 1e12 / peaks["bf16_tflops"], 4),
                 step_tc_frac_executed=round(sum(exec_flops.values()) / (ms_step * 1e-3) / 1e12 / peaks["bf16_tflops"], 4),
                 gemm_share_of_step=round(gemm_ms / ms_step, 3), loss=loss_val)
+    if ms_frozen:
+        line["variants"] = dict(lm_head_frozen=dict(ms_per_step=ms_frozen, value=tokens_step / (ms_frozen * 1e-3), unit=UNIT,
+                                                    note="same batch, lm_head not trainable (LoRA recipe): no dW GEMM"))
     if world == 1 and not args.no_cpu_baseline:
         r = time_cpu_port(2, 1)
         line["cpu_baseline"] = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="port", sample=r["sample"],
@@ -347,6 +396,7 @@ def main():
     ap.add_argument("--backward", default="auto", choices=["auto", "fused", "recompute"],
                     help="gradient strategy of dpa_loss (auto = fused)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the lm_head-frozen variant timing")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end loop (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
