@@ -22,6 +22,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "DPA loss fwd+bwd tokens/s (7B lm_head shape)"
 UNIT = "tokens/s"
+PLANT = 5.0     # synthetic hidden states give their targets a realistic (high) probability, see halva_b200/synth.py
 
 
 def load_peaks():
@@ -101,7 +102,7 @@ def cpu_sample_inputs():
     import torch
     from halva_b200.synth import CONFIGS, make_inputs
     shape = CONFIGS["cfg1"]
-    return shape, make_inputs(shape, seed=1234, dtype=torch.float32, device="cpu")
+    return shape, make_inputs(shape, seed=1234, dtype=torch.float32, device="cpu", plant=PLANT)
 
 
 def time_cpu_port(steps, warmup):
@@ -140,7 +141,8 @@ def config_dict(args, shape):
     from halva_b200.synth import CONFIGS
     shape = shape or CONFIGS[args.config]
     return dict(workload=f"HALVA-7B DPA loss at training shape ({args.config}): {shape.B} pairs + {shape.B_ref} reference samples per GPU, "
-                         f"T={shape.T} incl. {shape.n_img} image tokens, H={shape.H}, V={shape.V}, bf16, phrase density {shape.density:.2f}",
+                         f"T={shape.T} incl. {shape.n_img} image tokens, H={shape.H}, V={shape.V}, bf16, phrase density {shape.density:.2f}, "
+                         f"seeded synthetic hidden states (targets planted, gain {PLANT})",
                 parallelism=f"dp{args.gpus}", need_dW=not args.no_dw, dense=bool(args.dense),
                 backward="recompute" if args.backward == "recompute" else "fused (gradients formed in the forward pass)",
                 l2="inputs (1.3 GB hidden states + 262 MB lm_head) exceed the 126 MB L2; no explicit flush")
@@ -221,7 +223,7 @@ def run_ours(args):
         shape = dataclasses.replace(shape, density=args.density)
     if args.pairs is not None:
         shape = dataclasses.replace(shape, B=args.pairs, B_ref=args.pairs)
-    t = make_inputs(shape, seed=1234 + rank, device=dev)
+    t = make_inputs(shape, seed=1234 + rank, device=dev, plant=PLANT)
     hp, hr = t["h_pair"].requires_grad_(True), t["h_ref_pol"].requires_grad_(True)
     W = t["W"].requires_grad_(need_dw)
     tensors = dict(h_pair=hp, h_ref_pol=hr, h_ref_frz=t["h_ref_frz"], labels_pair=t["labels_pair"], signs_pair=t["signs_pair"],

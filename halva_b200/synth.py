@@ -101,9 +101,12 @@ def make_labels_signs(shape: DPAShape, g: torch.Generator):
 
 
 def make_inputs(shape: DPAShape, seed: int = 1234, dtype=torch.bfloat16, device="cpu",
-                shared_head: bool = True, hidden_scale: float = 1.5):
+                shared_head: bool = True, hidden_scale: float = 1.5, plant: float = 0.0):
     """SURVEY.md section 8(d): W ~ N(0, 0.02^2); h ~ 1.5 N(0,1); h_ref_frozen = h_ref_pol + 0.1 N(0,1);
-    W_ref = W (LoRA recipe, lm_head shared and frozen) or W + 0.002 N(0,1) (full fine-tune)."""
+    W_ref = W (LoRA recipe, lm_head shared and frozen) or W + 0.002 N(0,1) (full fine-tune).
+    plant > 0 adds `plant * W[label]` to the hidden row that predicts a valid label, which lifts the target logit by
+    about plant * |W_y|^2 -- a trained LM gives its targets high probability, purely random hidden states give every
+    target ~1/V, and then long phrases make the reference's literal log(1+exp(N-P)) overflow to +inf."""
     g = torch.Generator().manual_seed(seed)
     labels, signs, labels_ref = make_labels_signs(shape, g)
     dev = torch.device(device)
@@ -118,6 +121,17 @@ def make_inputs(shape: DPAShape, seed: int = 1234, dtype=torch.bfloat16, device=
     h_ref_frz = (h_ref_pol32 + 0.1 * randn(shape.B_ref, shape.T_ref, shape.H)).to(dtype)
     h_ref_pol = h_ref_pol32.to(dtype)
     del h_ref_pol32
+    if plant > 0:
+        def planted(h, labels, noise=0.0):
+            y = labels[:, 1:].to(dev)
+            ok = (y != IGNORE).unsqueeze(-1)
+            add = plant * W.float()[y.clamp_min(0)] * ok
+            h32 = h.float()
+            h32[:, :-1] += add
+            return h32.to(dtype)
+        h_pair = planted(h_pair, labels)
+        h_ref_pol = planted(h_ref_pol, labels_ref)
+        h_ref_frz = planted(h_ref_frz, labels_ref)
     W_ref = W if shared_head else (W.float() + 0.002 * randn(shape.V, shape.H)).to(dtype)
     return dict(h_pair=h_pair, labels_pair=labels.to(dev), signs_pair=signs.to(dev),
                 h_ref_pol=h_ref_pol, h_ref_frz=h_ref_frz, labels_ref=labels_ref.to(dev),

@@ -1,0 +1,87 @@
+"""Full-size checks at BASELINE.json configs[1] (16 pairs + 16 reference samples, T 2048, H 4096, V 32000, bf16):
+the CUDA path against the reference op chain (oracle/dpa_port.py on the same GPU) and size-independent properties."""
+import dataclasses
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return float((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-30))
+
+
+@pytest.fixture(scope="module")
+def cfg2():
+    from halva_b200.synth import CONFIGS, make_inputs
+    free, _ = torch.cuda.mem_get_info()
+    if free < 80e9:
+        pytest.skip("needs ~80 GB free for the reference op chain at full size")
+    shape = CONFIGS["cfg2"]
+    t = make_inputs(shape, seed=4321, device="cuda", plant=5.0)
+    return shape, t
+
+
+def _ours(t, shape, grad_out=1.0, perm=None, **kw):
+    from halva_b200 import dpa_loss, read_status
+    sel = slice(None) if perm is None else perm
+    hp = t["h_pair"][sel].clone().requires_grad_(True)
+    hr = t["h_ref_pol"].clone().requires_grad_(True)
+    W = t["W"].clone().requires_grad_(True)
+    loss, align, div = dpa_loss(hp, t["labels_pair"][sel], t["signs_pair"][sel], hr, t["labels_ref"], W, h_ref_frozen=t["h_ref_frz"],
+                                alpha=shape.alpha, **kw)
+    (loss * grad_out).backward()
+    st = read_status(loss)
+    assert st["status"] == 0, st
+    return dict(loss=loss.item(), align=align.item(), div=div.item(), dH_pair=hp.grad, dH_ref=hr.grad, dW=W.grad, st=st)
+
+
+def test_cfg2_vs_reference_op_chain(cfg2):
+    """Loss and gradients of the fused path vs the reference's ATen sequence in bf16, at the full training shape."""
+    from oracle import dpa_port
+    shape, t = cfg2
+    a = _ours(t, shape)
+    assert np.isfinite(a["loss"])
+    hp = t["h_pair"].clone().requires_grad_(True)
+    hr = t["h_ref_pol"].clone().requires_grad_(True)
+    W = t["W"].clone().requires_grad_(True)
+    loss, align, div = dpa_port.dpa_loss_torch(hp, t["labels_pair"], t["signs_pair"], hr, t["h_ref_frz"], t["labels_ref"], W, W.detach(), shape.alpha)
+    loss.backward()
+    assert abs(a["loss"] - loss.item()) <= 1e-3 * abs(loss.item()), (a["loss"], loss.item())
+    assert abs(a["align"] - align.item()) <= 1e-3 * abs(align.item())
+    assert abs(a["div"] - div.item()) <= 1e-3 * abs(div.item()), (a["div"], div.item())
+    for k, g in (("dH_pair", hp.grad), ("dH_ref", hr.grad), ("dW", W.grad)):
+        assert _rel(a[k], g) <= 1e-2, (k, _rel(a[k], g))
+    # rows the reference gives exactly zero gradient get exactly zero here too
+    assert torch.equal(a["dH_pair"] == 0, hp.grad == 0) or _rel((a["dH_pair"] != 0).float(), (hp.grad != 0).float()) < 1e-3
+    assert (a["dH_pair"][:, -1] == 0).all() and (a["dH_ref"][:, -1] == 0).all()
+
+
+def test_cfg2_strategies_and_scaling(cfg2):
+    shape, t = cfg2
+    a = _ours(t, shape)
+    b = _ours(t, shape, backward="recompute")
+    assert a["align"] == b["align"] and abs(a["div"] - b["div"]) <= 1e-5 * abs(b["div"])
+    for k in ("dH_pair", "dH_ref", "dW"):
+        assert _rel(a[k], b[k]) <= 2e-3, (k, _rel(a[k], b[k]))
+    s = _ours(t, shape, grad_out=0.25)                  # exact: bf16 scaling by a power of two
+    assert torch.equal(s["dH_ref"], (a["dH_ref"].float() * 0.25).to(torch.bfloat16))
+    assert torch.equal(s["dW"], (a["dW"].float() * 0.25).to(torch.bfloat16))
+    c = _ours(t, shape)                                  # bit-reproducible
+    assert c["loss"] == a["loss"] and torch.equal(c["dW"], a["dW"]) and torch.equal(c["dH_pair"], a["dH_pair"])
+
+
+def test_cfg2_pair_permutation(cfg2):
+    """The loss is a mean over (sample, phrase): permuting the sample pairs permutes dH rows and leaves loss and dW alone."""
+    shape, t = cfg2
+    B = shape.B
+    g = torch.Generator().manual_seed(0)
+    p = torch.randperm(B, generator=g)
+    perm = torch.cat([p, p + B]).cuda()
+    a = _ours(t, shape)
+    b = _ours(t, shape, perm=perm)
+    assert abs(a["loss"] - b["loss"]) <= 2e-6 * abs(a["loss"])
+    assert _rel(b["dH_pair"], a["dH_pair"][perm]) <= 1e-3
+    assert _rel(b["dW"], a["dW"]) <= 1e-3

@@ -48,7 +48,7 @@ def main():
     for B in [int(x) for x in args.pairs.split(",")]:
         for dens in [float(x) for x in args.densities.split(",")]:
             shape = dataclasses.replace(CONFIGS["cfg2"], B=B, B_ref=B, density=dens)
-            t = make_inputs(shape, seed=1234, device=dev)
+            t = make_inputs(shape, seed=1234, device=dev, plant=5.0)
             hp, hr = t["h_pair"].requires_grad_(True), t["h_ref_pol"].requires_grad_(True)
             W = t["W"].requires_grad_(not args.no_dw)
 
