@@ -149,23 +149,27 @@ def config_dict(args, shape):
 
 
 def run_e2e(args, tensors, step, barrier, dev, world):
-    """Same step driven from HOST buffers: pinned hidden states / labels copied to the device every step
-    (double-buffered against the previous step's compute), the three losses read back every step."""
+    """Same step driven from HOST buffers: every step the pinned hidden states / labels / phrase ids are copied to the
+    device (halva_b200.host.HostStager: labels in full, hidden rows span-wise -- only rows that predict a contributing
+    label are ever read by the kernels), double-buffered against the previous step's compute on a copy stream, and the
+    three losses are read back to the host."""
     import torch
     import torch.distributed as dist
+    from halva_b200.host import HostStager
     host = {k: v.detach().cpu().pin_memory() for k, v in tensors.items()}
+    stager = HostStager(host["labels_pair"], host["signs_pair"], host["labels_ref"], dense=bool(args.dense or args.e2e_full_copy))
     sets = []
     for _ in range(2):
-        s = {k: torch.empty_like(v.detach()) for k, v in tensors.items()}
+        s = {k: torch.zeros_like(v.detach()) for k, v in tensors.items()}
         s["h_pair"].requires_grad_(True)
         s["h_ref_pol"].requires_grad_(True)
         sets.append(s)
-    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
     out_host = torch.empty(4, dtype=torch.float32).pin_memory()
     copy_stream = torch.cuda.Stream(device=dev)
     ev_copied = [torch.cuda.Event() for _ in range(2)]
     ev_done = [torch.cuda.Event() for _ in range(2)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h2d = [0]
 
     def e2e_loop(n):
         cur = torch.cuda.current_stream()
@@ -174,8 +178,7 @@ def run_e2e(args, tensors, step, barrier, dev, world):
                 b = i % 2
                 with torch.cuda.stream(copy_stream):
                     copy_stream.wait_event(ev_done[b])           # buffer set b free again (step i-2 finished)
-                    for k, v in host.items():
-                        sets[b][k].detach().copy_(v, non_blocking=True)
+                    h2d[0] = stager.stage(host, sets[b])
                     ev_copied[b].record(copy_stream)
             if i > 0:
                 b = (i - 1) % 2
@@ -198,7 +201,7 @@ def run_e2e(args, tensors, step, barrier, dev, world):
         tt = torch.tensor([ms_e2e], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms_e2e = tt.item()
-    return ms_e2e, h2d_bytes
+    return ms_e2e, h2d[0], float(out_host[0])
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -302,9 +305,9 @@ def run_ours(args):
             ms_frozen = tt.item()
 
     # ---- end to end: host (pinned) buffers in, losses out, H2D double-buffered against the previous step's compute
-    ms_e2e, h2d_bytes = None, 0
+    ms_e2e, h2d_bytes, loss_e2e = None, 0, None
     if not args.no_e2e:
-        ms_e2e, h2d_bytes = run_e2e(args, tensors, step, barrier, dev, world)
+        ms_e2e, h2d_bytes, loss_e2e = run_e2e(args, tensors, step, barrier, dev, world)
     clocks = sampler.finish() if sampler else None
 
 
@@ -362,8 +365,10 @@ def run_ours(args):
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
                 config=config_dict(args, shape),
                 e2e=dict(value=tokens_step / (e2e_ms_step * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=12,
-                         ms_per_step=e2e_ms_step, note="pinned host hidden states/labels -> device every step (double-buffered), "
-                         "losses read back every step") if e2e_ms_step else None,
+                         ms_per_step=e2e_ms_step, loss=loss_e2e,
+                         note="pinned host hidden states/labels -> device every step (labels in full; hidden rows span-wise: only rows "
+                              "that predict a contributing label are transferred, the kernels never read the others), double-buffered "
+                              "on a copy stream; losses read back every step") if e2e_ms_step else None,
                 gpu_launches=int(round(sum(v["launches_per_step"] for v in kernels.values()) * K)),
                 roofline=roofline, kernels=kernels, clocks=clocks,
                 rows=dict(pair_active=rows_pair, ref_active=rows_ref, pair_fed=2 * shape.B * shape.T, ref_fed=shape.B_ref * shape.T_ref),
@@ -399,6 +404,7 @@ def main():
                     help="gradient strategy of dpa_loss (auto = fused)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the lm_head-frozen variant timing")
+    ap.add_argument("--e2e-full-copy", action="store_true", help="e2e: copy every hidden row, not only contributing spans")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end loop (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
