@@ -30,7 +30,10 @@ constexpr int kProducerWarp = 4, kMmaWarp = 5, kAllocWarp = 6, kEpiWarp0 = 0;
 #else   // experiment: single-lane roles below the epilogue warps
 constexpr int kProducerWarp = 0, kMmaWarp = 1, kAllocWarp = 2, kEpiWarp0 = 4;
 #endif
-constexpr int kSuperM = 16;  // row tiles per L2 super-block of the unit order
+#ifndef DPA_SUPER_M
+#define DPA_SUPER_M 16
+#endif
+constexpr int kSuperM = DPA_SUPER_M;  // row-tile units per L2 super-block of the unit order
 
 enum : int { KMAJOR = 0, MNMAJOR = 1 };
 

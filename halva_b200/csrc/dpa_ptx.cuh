@@ -72,11 +72,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #if DPA_WATCHDOG
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) {   // each try_wait suspends for a HW time slice; this is seconds
-      printf("dpa: mbarrier watchdog: block %d thread %d bar %u parity %u\n", (int)blockIdx.x, (int)threadIdx.x,
-             smem_u32(bar), parity);
-      __trap();
-    }
+    if (++spins > (1u << 24)) __trap();   // each try_wait suspends for a HW time slice; this is seconds
   }
 #else
   while (!mbar_try_wait(bar, parity)) {

@@ -2,7 +2,8 @@
 """BASELINE.json configs[4]: tokens x phrase-density sweep at the 7B shape, fused CUDA path vs the reference op chain
 (oracle/dpa_port.py: the same ATen sequence the reference trainer issues) run on the SAME GPU in bf16.
 
-    python tools/sweep_cfg5.py [--out profiles/r01_cfg5_sweep.md]
+    python tests/sweep_cfg5.py [--out gpurun_out/cfg5_sweep.md]      (a script, not collected by pytest; it lives under
+    tests/ because it runs the oracle's torch port as the comparison arm)
 
 The reference chain materialises fp32 [rows, 32000] tensors several times over and runs out of memory at the top end;
 that is recorded as OOM, not skipped.
@@ -86,7 +87,7 @@ def main():
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as f:
         f.write("# cfg-5 sweep: tokens x phrase density at the 7B lm_head shape (H 4096, V 32000, T 2048), one B200, bf16\n\n")
-        f.write("`python tools/sweep_cfg5.py` -- `ours` = halva_b200.dpa_loss forward+backward (fused-gradient, lm_head trainable); `reference chain` =\n"
+        f.write("`python tests/sweep_cfg5.py` -- `ours` = halva_b200.dpa_loss forward+backward (fused-gradient, lm_head trainable); `reference chain` =\n"
                 "the reference's ATen op sequence (oracle/dpa_port.py) on the same GPU. tokens = every fed position (2B*T + B*T).\n\n")
         f.write("| pairs | tokens | density | active rows (pair+ref) | ours ms | ours Mtok/s | reference chain ms | speed-up | rel. loss diff |\n|---:|---:|---:|---:|---:|---:|---:|---:|---:|\n")
         for r in rows:
