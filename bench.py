@@ -143,7 +143,7 @@ def config_dict(args, shape):
     return dict(workload=f"HALVA-7B DPA loss at training shape ({args.config}): {shape.B} pairs + {shape.B_ref} reference samples per GPU, "
                          f"T={shape.T} incl. {shape.n_img} image tokens, H={shape.H}, V={shape.V}, bf16, phrase density {shape.density:.2f}, "
                          f"seeded synthetic hidden states (targets planted, gain {PLANT})",
-                parallelism=f"dp{args.gpus}", need_dW=not args.no_dw, dense=bool(args.dense),
+                parallelism=f"{args.parallelism}{args.gpus}", need_dW=not args.no_dw, dense=bool(args.dense),
                 backward="recompute" if args.backward == "recompute" else "fused (gradients formed in the forward pass)",
                 l2="inputs (1.3 GB hidden states + 262 MB lm_head) exceed the 126 MB L2; no explicit flush")
 
@@ -226,8 +226,16 @@ def run_ours(args):
         shape = dataclasses.replace(shape, density=args.density)
     if args.pairs is not None:
         shape = dataclasses.replace(shape, B=args.pairs, B_ref=args.pairs)
-    t = make_inputs(shape, seed=1234 + rank, device=dev, plant=PLANT)
+    vp = args.parallelism == "vp" and world > 1
+    # dp: every rank its own batch (weak scaling);  vp: the SAME rows on every rank, lm_head rows split over the ranks
+    t = make_inputs(shape, seed=1234 + (0 if vp else rank), device=dev, plant=PLANT)
     hp, hr = t["h_pair"].requires_grad_(True), t["h_ref_pol"].requires_grad_(True)
+    vp_kw = {}
+    if vp:
+        from halva_b200.dist import vocab_shard_bounds
+        v0, v1 = vocab_shard_bounds(shape.V, world, rank)
+        t["W"] = t["W"][v0:v1].contiguous()
+        vp_kw = dict(vocab_group=dist.group.WORLD, v_offset=v0, vocab_size=shape.V)
     W = t["W"].requires_grad_(need_dw)
     tensors = dict(h_pair=hp, h_ref_pol=hr, h_ref_frz=t["h_ref_frz"], labels_pair=t["labels_pair"], signs_pair=t["signs_pair"],
                    labels_ref=t["labels_ref"])
@@ -238,9 +246,9 @@ def run_ours(args):
         W.grad = None
         loss, align, div = dpa_loss(src["h_pair"], src["labels_pair"], src["signs_pair"], src["h_ref_pol"], src["labels_ref"], W,
                                     h_ref_frozen=src["h_ref_frz"], alpha=shape.alpha, dense=args.dense, chunk_rows=args.chunk_rows,
-                                    backward=args.backward)
+                                    backward="recompute" if vp else args.backward, **vp_kw)
         loss.backward()
-        if world > 1 and need_dw:          # data parallel: average the lm_head gradient over ranks (NCCL over NVLink)
+        if world > 1 and need_dw and not vp:   # data parallel: average the lm_head gradient over ranks (NCCL over NVLink)
             average_gradients([W.grad])
         return loss, align, div
 
@@ -318,10 +326,12 @@ def run_ours(args):
 
     peaks = load_peaks()
     K = args.steps
-    tokens_step = shape.tokens * world
+    tokens_step = shape.tokens * (1 if vp else world)
+    if vp:
+        args.backward = "recompute"
     ms_step = ms / K
     value = tokens_step / (ms_step * 1e-3)
-    unit_flops = 2.0 * shape.H * shape.V
+    unit_flops = 2.0 * shape.H * W.shape[0]          # per GPU: this rank's lm_head rows
     # executed tensor-core FLOPs of each GEMM class per step (rows actually processed, tile padding not counted)
     n_p, n_r = (2 * shape.B * (shape.T - 1), shape.B_ref * (shape.T_ref - 1)) if args.dense else (rows_pair, rows_ref)
     fused = args.backward != "recompute"
@@ -348,8 +358,9 @@ def run_ours(args):
     n_launch_dom = max(1.0, kernels[dom]["launches_per_step"])
     dom_ms_launch = kernels[dom]["ms_per_step"] / n_launch_dom
     achieved = exec_flops[dom] / n_launch_dom / (dom_ms_launch * 1e-3) / 1e12
-    f_alg_dense = algorithmic_flops(shape, need_dw)
-    f_alg_active = algorithmic_flops(shape, need_dw, rows_pair, rows_ref)
+    share = world if vp else 1                       # vp: the algorithmic FLOPs of the batch are split over the ranks
+    f_alg_dense = algorithmic_flops(shape, need_dw) / share
+    f_alg_active = algorithmic_flops(shape, need_dw, rows_pair, rows_ref) / share
     gemm_ms = sum(kernels[k]["ms_per_step"] for k in gemm_kinds)
     traffic, traffic_note = load_traffic(dom)
     roofline = dict(bound="tensor", kernel=dom, achieved=round(achieved, 1), peak=peaks["bf16_tflops"], unit="TFLOP/s",
@@ -362,7 +373,7 @@ def run_ours(args):
                          "contribution are run). Whole-step figures: step_tc_frac_*")
     e2e_ms_step = ms_e2e / K if ms_e2e else None
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=max(args.warmup, 3), ms_per_step=ms_step,
-                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+                higher_is_better=True, scaling="strong" if vp else "weak", vs_baseline=None, dtype="bf16", data="synthetic",
                 config=config_dict(args, shape),
                 e2e=dict(value=tokens_step / (e2e_ms_step * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=12,
                          ms_per_step=e2e_ms_step, loss=loss_e2e,
@@ -398,6 +409,8 @@ def main():
     ap.add_argument("--density", type=float, default=None)
     ap.add_argument("--pairs", type=int, default=None)
     ap.add_argument("--chunk-rows", type=int, default=0)
+    ap.add_argument("--parallelism", default="dp", choices=["dp", "vp"],
+                    help="dp: data parallel over sample pairs (default); vp: vocab-parallel lm_head (same rows on every rank)")
     ap.add_argument("--no-dw", action="store_true", help="lm_head frozen (the shipped LoRA recipe): no dW")
     ap.add_argument("--dense", action="store_true", help="process every fed position (no row compaction)")
     ap.add_argument("--backward", default="auto", choices=["auto", "fused", "recompute"],
