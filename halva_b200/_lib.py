@@ -9,8 +9,8 @@ LIB_PATH = os.environ.get("HALVA_DPA_LIB") or os.path.join(HERE, "libhalva_dpa.s
 
 DPA_BF16 = 0
 DPA_I64, DPA_I32 = 0, 1
-FLAG_ROUND_LOGITS, FLAG_NEED_DW, FLAG_DENSE, FLAG_FUSED_GRAD = 1, 2, 4, 8
-ABI_VERSION = 2
+FLAG_ROUND_LOGITS, FLAG_NEED_DW, FLAG_DENSE, FLAG_FUSED_GRAD, FLAG_FUSED_NORM = 1, 2, 4, 8, 16
+ABI_VERSION = 3
 STATUS_BAD_SIGN, STATUS_K_MISMATCH, STATUS_K_ZERO, STATUS_BAD_LABEL = 1, 2, 4, 8
 EXPORTS = ["dpa_version", "dpa_last_error", "dpa_query_workspace", "dpa_forward", "dpa_backward",
            "dpa_forward_stats", "dpa_forward_finish", "dpa_row_stats_view", "dpa_debug_gemm",
@@ -34,7 +34,8 @@ class Args(C.Structure):
                 ("state", C.c_void_p), ("state_bytes", C.c_size_t),
                 ("scratch", C.c_void_p), ("scratch_bytes", C.c_size_t),
                 ("losses", C.c_void_p), ("status", C.c_void_p),
-                ("d_loss", C.c_void_p), ("dH_pair", C.c_void_p), ("dH_ref", C.c_void_p), ("dW", C.c_void_p)]
+                ("d_loss", C.c_void_p), ("dH_pair", C.c_void_p), ("dH_ref", C.c_void_p), ("dW", C.c_void_p),
+                ("norm_w", C.c_void_p), ("norm_w_ref", C.c_void_p), ("d_norm_w", C.c_void_p), ("norm_eps", C.c_float)]
 
 
 class DPAError(RuntimeError):

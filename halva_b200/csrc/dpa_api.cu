@@ -165,7 +165,7 @@ struct Layout {
   int n_pos_pair, n_pos_ref, cap_pair, cap_ref, nblk_pair, nblk_ref, ng_pair, ng_ref, ldz, chunk_rows, n_chunks;
   // state offsets
   size_t meta, bitmap, block_counts, src_pair, lab_pair, col_pair, src_ref, act_ref, stats_pair, stats_ref, stats_u,
-      lse_pair, logp_pair, lse_ref_p, lse_ref_r, kl_row, PN, sigma, coef_pair, coef_ref, state_total;
+      lse_pair, logp_pair, lse_ref_p, lse_ref_r, kl_row, PN, sigma, coef_pair, coef_ref, rinv, dnw32, state_total;
   size_t row_stats_bytes;
   // forward scratch offsets
   size_t f_Hp, f_Hf, f_part_pair, f_part_ref, f_part_u, fwd_total;
@@ -216,6 +216,8 @@ int make_layout(const dpa_shape_t& s, Layout& L) {
   L.PN = take((size_t)2 * s.B * (kMaxSign + 1) * 4);
   L.sigma = take((size_t)s.B * (kMaxSign + 1) * 4);
   L.coef_pair = take((size_t)L.cap_pair * 4); L.coef_ref = take((size_t)L.cap_ref * 4);
+  L.rinv = take((size_t)cap_tot * 4);             // DPA_FLAG_FUSED_NORM: rsqrt(var + eps) of the packed policy rows
+  L.dnw32 = take((size_t)s.H * 4);                //                      fp32 accumulator of d_norm_w
   L.state_total = o;
 
   o = 0;
@@ -263,6 +265,12 @@ int check_common(const dpa_args_t* a, Layout& L, DeviceInfo** dev) {
   }
   if (!a->state || a->state_bytes < L.state_total) return fail(DPA_ERR_WORKSPACE, "state workspace: need %zu bytes, got %zu", L.state_total, a->state_bytes);
   if (!aligned16(a->state) || (a->scratch && !aligned16(a->scratch))) return fail(DPA_ERR_ALIGN, "workspaces must be 16-byte aligned (256 recommended)");
+  if (a->shape.flags & DPA_FLAG_FUSED_NORM) {
+    if (!a->norm_w || !a->norm_w_ref) return fail(DPA_ERR_ARG, "DPA_FLAG_FUSED_NORM set but norm_w / norm_w_ref is NULL");
+    if (!aligned16(a->norm_w) || !aligned16(a->norm_w_ref) || (a->d_norm_w && !aligned16(a->d_norm_w)))
+      return fail(DPA_ERR_ALIGN, "norm weights must be 16-byte aligned");
+    if (!(a->norm_eps >= 0.f)) return fail(DPA_ERR_ARG, "norm_eps must be >= 0");
+  }
   return DPA_OK;
 }
 
@@ -289,9 +297,38 @@ int run_gather(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, void* 
   g.h_ref_pol = static_cast<const __nv_bfloat16*>(a->h_ref_pol);
   g.h_ref_frz = static_cast<const __nv_bfloat16*>(a->h_ref_frz);
   g.Hp = at<__nv_bfloat16>(scratch, oHp); g.Hf = at<__nv_bfloat16>(scratch, oHf); g.H = a->shape.H;
+  g.norm_w = static_cast<const __nv_bfloat16*>(a->norm_w); g.norm_w_ref = static_cast<const __nv_bfloat16*>(a->norm_w_ref);
+  g.norm_eps = a->norm_eps; g.rinv = at<float>(a->state, L.rinv);
   ProfScope ps(PK_GATHER, 1, st);
-  gather_rows_kernel<<<d->sms * 8, 256, 0, st>>>(g);
+  if (a->shape.flags & DPA_FLAG_FUSED_NORM) gather_rows_kernel<true><<<d->sms * 8, 256, 0, st>>>(g);
+  else gather_rows_kernel<false><<<d->sms * 8, 256, 0, st>>>(g);
   LAUNCH_CHECK("gather_rows");
+  return DPA_OK;
+}
+
+// DPA_FLAG_FUSED_NORM: turn the dH rows (gradients w.r.t. the normed hidden states) into gradients w.r.t. the pre-norm
+// stream, in place, and finish d_norm_w.  Runs once every dH chunk is complete.
+int run_norm_backward(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, cudaStream_t st) {
+  if (!(a->shape.flags & DPA_FLAG_FUSED_NORM)) return DPA_OK;
+  const dpa_shape_t& s = a->shape;
+  float* dnw32 = a->d_norm_w ? at<float>(a->state, L.dnw32) : nullptr;
+  ProfScope ps(PK_MISC, a->d_norm_w ? 2 : 1, st);
+  if (dnw32) CUDA_TRY(cudaMemsetAsync(dnw32, 0, (size_t)s.H * 4, st));
+  NormBwdArgs n{at<DpaMeta>(a->state, L.meta), at<int>(a->state, L.src_pair), at<int>(a->state, L.src_ref),
+                static_cast<const __nv_bfloat16*>(a->h_pair), static_cast<const __nv_bfloat16*>(a->h_ref_pol),
+                static_cast<__nv_bfloat16*>(a->dH_pair), static_cast<__nv_bfloat16*>(a->dH_ref),
+                static_cast<const __nv_bfloat16*>(a->norm_w), at<float>(a->state, L.rinv), dnw32, s.H};
+  const size_t smem = dnw32 ? (size_t)s.H * 4 : 0;
+  if (smem > 48 * 1024) {
+    static std::once_flag once;
+    std::call_once(once, [] { cudaFuncSetAttribute(norm_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); });
+  }
+  norm_backward_kernel<<<d->sms * 2, 256, smem, st>>>(n);
+  LAUNCH_CHECK("norm_backward");
+  if (dnw32) {
+    f32_to_bf16_kernel<<<(s.H / 4 + 255) / 256, 256, 0, st>>>(dnw32, static_cast<__nv_bfloat16*>(a->d_norm_w), (size_t)s.H);
+    LAUNCH_CHECK("d_norm_w convert");
+  }
   return DPA_OK;
 }
 
@@ -588,6 +625,7 @@ int forward_fused_impl(const dpa_args_t* a, cudaStream_t st) {
     }
   }
   if ((rc = run_losses(a, L, st, LOSS_TOTAL))) return rc;
+  if ((rc = run_norm_backward(a, L, d, st))) return rc;
   if (need_dw) {
     const size_t n = (size_t)s.V_local * s.H;
     ProfScope ps(PK_MISC, 1, st);
@@ -610,6 +648,8 @@ int backward_scale_impl(const dpa_args_t* a, cudaStream_t st) {
   scale_bf16_kernel<<<d->sms * 8, 256, 0, st>>>(static_cast<__nv_bfloat16*>(a->dH_ref), (size_t)s.B_ref * s.T_ref * s.H, a->d_loss);
   if (s.flags & DPA_FLAG_NEED_DW)
     scale_bf16_kernel<<<d->sms * 8, 256, 0, st>>>(static_cast<__nv_bfloat16*>(a->dW), (size_t)s.V_local * s.H, a->d_loss);
+  if ((s.flags & DPA_FLAG_FUSED_NORM) && a->d_norm_w)
+    scale_bf16_kernel<<<1, 256, 0, st>>>(static_cast<__nv_bfloat16*>(a->d_norm_w), (size_t)s.H, a->d_loss);
   LAUNCH_CHECK("scale_grads");
   return DPA_OK;
 }
@@ -685,6 +725,7 @@ int run_backward(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, cuda
       if ((rc = launch_single<Epi, MNMAJOR, MNMAJOR>(st, d, tmDzMN, tmHpMN, tmHpMN, w, ep, "dW"))) return rc;
     }
   }
+  if ((rc = run_norm_backward(a, L, d, st))) return rc;
   if (need_dw) {
     const size_t n = (size_t)s.V_local * s.H;
     ProfScope ps(PK_MISC, 1, st);

@@ -204,7 +204,9 @@ __global__ void meta_pad_kernel(MetaArgs a) {
   }
 }
 
-// ---- gather active hidden rows into the packed, tile-padded operand buffers (one warp per row, 16 B vectors)
+// ---- gather active hidden rows into the packed, tile-padded operand buffers (one warp per row, 16 B vectors).
+//      NORM: the rows are the pre-norm residual stream and the decoder's final RMSNorm is applied on the way
+//      (modelling_llama.py:64-69: variance in fp32, x * rsqrt(var + eps) cast back to bf16, then weight * (.) in bf16).
 struct GatherArgs {
   const DpaMeta* meta;
   const int* src_pair; const int* src_ref;
@@ -212,7 +214,11 @@ struct GatherArgs {
   __nv_bfloat16* Hp;   // [cap_pair + cap_ref][H]  policy rows: pair segment [0,p0), reference segment [p0, n_tot)
   __nv_bfloat16* Hf;   // [cap_ref][H]             frozen-model rows of the reference segment
   int H;
+  const __nv_bfloat16* norm_w; const __nv_bfloat16* norm_w_ref; float norm_eps;
+  float* rinv;         // [cap_pair + cap_ref]  rsqrt(var + eps) of the policy rows (kept for the backward)
 };
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t v) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v)); }
+template <bool NORM>
 __global__ void gather_rows_kernel(GatherArgs a) {
   const int p0 = a.meta->p0, n_tot = a.meta->n_tot;
   const int nr_pad = n_tot - p0;
@@ -221,6 +227,7 @@ __global__ void gather_rows_kernel(GatherArgs a) {
   const int vec = a.H / 8;                                 // uint4 per row
   for (int r = wid; r < n_tot + nr_pad; r += warps) {
     const uint4* src = nullptr; uint4* dst;
+    const __nv_bfloat16* w = a.norm_w;
     if (r < p0) {
       const int s = a.src_pair[r];
       if (s >= 0) src = reinterpret_cast<const uint4*>(a.h_pair + (size_t)s * a.H);
@@ -234,8 +241,100 @@ __global__ void gather_rows_kernel(GatherArgs a) {
       const int s = a.src_ref[j];
       if (s >= 0) src = reinterpret_cast<const uint4*>(a.h_ref_frz + (size_t)s * a.H);
       dst = reinterpret_cast<uint4*>(a.Hf + (size_t)j * a.H);
+      w = a.norm_w_ref;
     }
-    for (int i = lane; i < vec; i += 32) dst[i] = src ? __ldg(src + i) : make_uint4(0, 0, 0, 0);
+    if (!src) {
+      for (int i = lane; i < vec; i += 32) dst[i] = make_uint4(0, 0, 0, 0);
+      if (NORM && lane == 0 && r < n_tot) a.rinv[r] = 0.f;
+      continue;
+    }
+    if constexpr (!NORM) {
+      for (int i = lane; i < vec; i += 32) dst[i] = __ldg(src + i);
+    } else {
+      float ss = 0.f;
+      for (int i = lane; i < vec; i += 32) {
+        const uint4 v = __ldg(src + i);
+        const uint32_t q[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const float2 f = bf2_to_f2(q[k]); ss = fmaf(f.x, f.x, ss); ss = fmaf(f.y, f.y, ss); }
+      }
+      for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float ri = rsqrtf(ss / (float)a.H + a.norm_eps);
+      if (lane == 0 && r < n_tot) a.rinv[r] = ri;
+      const uint4* wv = reinterpret_cast<const uint4*>(w);
+      for (int i = lane; i < vec; i += 32) {
+        const uint4 v = __ldg(src + i), g = __ldg(wv + i);     // second pass over the 8 KB row hits L1
+        const uint32_t q[4] = {v.x, v.y, v.z, v.w}, gq[4] = {g.x, g.y, g.z, g.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = bf2_to_f2(q[k]), gw = bf2_to_f2(gq[k]);
+          o[k] = pack_bf16x2(gw.x * bf16_round_f32(f.x * ri), gw.y * bf16_round_f32(f.y * ri));
+        }
+        dst[i] = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+}
+
+// ---- backward of the folded final RMSNorm, in place over the dH rows of the active policy rows:
+//      dn = bf16(dy * w), dx = r dn - x r^3 mean(dn x), d_norm_w += dy * bf16(x r)   (autograd of modelling_llama.py:64-69)
+struct NormBwdArgs {
+  const DpaMeta* meta;
+  const int* src_pair; const int* src_ref;
+  const __nv_bfloat16* h_pair; const __nv_bfloat16* h_ref_pol;     // pre-norm rows
+  __nv_bfloat16* dH_pair; __nv_bfloat16* dH_ref;                    // in: dy, out: dx
+  const __nv_bfloat16* norm_w; const float* rinv;
+  float* dnw32;        // [H] fp32 accumulator or nullptr
+  int H;
+};
+__global__ void __launch_bounds__(256) norm_backward_kernel(NormBwdArgs a) {
+  extern __shared__ float sm_dnw[];                                 // [H] when dnw32
+  const int p0 = a.meta->p0, n_pair = a.meta->n_pair, n_ref = a.meta->n_ref;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int vec = a.H / 8;
+  if (a.dnw32) { for (int i = threadIdx.x; i < a.H; i += blockDim.x) sm_dnw[i] = 0.f; __syncthreads(); }
+  const uint4* wv = reinterpret_cast<const uint4*>(a.norm_w);
+  const int total = n_pair + n_ref;
+  for (int q = blockIdx.x * wpb + wib; q < total; q += gridDim.x * wpb) {
+    const bool is_pair = q < n_pair;
+    const int r = is_pair ? q : p0 + (q - n_pair);
+    const int s = is_pair ? a.src_pair[q] : a.src_ref[q - n_pair];
+    const uint4* x = reinterpret_cast<const uint4*>((is_pair ? a.h_pair : a.h_ref_pol) + (size_t)s * a.H);
+    uint4* dy = reinterpret_cast<uint4*>((is_pair ? a.dH_pair : a.dH_ref) + (size_t)s * a.H);
+    const float ri = a.rinv[r];
+    float acc = 0.f;
+    for (int i = lane; i < vec; i += 32) {
+      const uint4 dv = dy[i], xv = __ldg(x + i), g = __ldg(wv + i);
+      const uint32_t dq[4] = {dv.x, dv.y, dv.z, dv.w}, xq[4] = {xv.x, xv.y, xv.z, xv.w}, gq[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 d = bf2_to_f2(dq[k]), xx = bf2_to_f2(xq[k]), gw = bf2_to_f2(gq[k]);
+        acc = fmaf(bf16_round_f32(d.x * gw.x), xx.x, acc);
+        acc = fmaf(bf16_round_f32(d.y * gw.y), xx.y, acc);
+      }
+    }
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    const float c = acc / (float)a.H * ri * ri * ri;
+    for (int i = lane; i < vec; i += 32) {
+      const uint4 dv = dy[i], xv = __ldg(x + i), g = __ldg(wv + i);
+      const uint32_t dq[4] = {dv.x, dv.y, dv.z, dv.w}, xq[4] = {xv.x, xv.y, xv.z, xv.w}, gq[4] = {g.x, g.y, g.z, g.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 d = bf2_to_f2(dq[k]), xx = bf2_to_f2(xq[k]), gw = bf2_to_f2(gq[k]);
+        o[k] = pack_bf16x2(ri * bf16_round_f32(d.x * gw.x) - xx.x * c, ri * bf16_round_f32(d.y * gw.y) - xx.y * c);
+        if (a.dnw32) {
+          atomicAdd(&sm_dnw[i * 8 + 2 * k], d.x * bf16_round_f32(xx.x * ri));
+          atomicAdd(&sm_dnw[i * 8 + 2 * k + 1], d.y * bf16_round_f32(xx.y * ri));
+        }
+      }
+      dy[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+  if (a.dnw32) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < a.H; i += blockDim.x) if (sm_dnw[i] != 0.f) atomicAdd(&a.dnw32[i], sm_dnw[i]);
   }
 }
 

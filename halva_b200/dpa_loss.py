@@ -47,17 +47,23 @@ class _Call:
     """Owns the ctypes argument block and the tensors it points to for one forward/backward pair."""
 
     def __init__(self, h_pair, labels_pair, signs_pair, h_ref_pol, h_ref_frozen, labels_ref, W, W_ref, alpha,
-                 round_logits, need_dW, dense, chunk_rows, v_offset, V_global, fused):
+                 round_logits, need_dW, dense, chunk_rows, v_offset, V_global, fused, norm=None):
         lib = _lib.load()
         self.lib = lib
         dev = h_pair.device
         self.keep = [t.contiguous() for t in (h_pair, labels_pair, signs_pair, h_ref_pol, h_ref_frozen, labels_ref, W, W_ref)]
-        hp, lp, sp, hr, hf, lr, w, wr = self.keep
+        hp, lp, sp, hr, hf, lr, w, wr = self.keep[:8]
         B2, T, H = hp.shape
         Br, Tr, _ = hr.shape
         flags = (_lib.FLAG_ROUND_LOGITS if round_logits else 0) | (_lib.FLAG_NEED_DW if need_dW else 0) | \
-                (_lib.FLAG_DENSE if dense else 0) | (_lib.FLAG_FUSED_GRAD if fused else 0)
+                (_lib.FLAG_DENSE if dense else 0) | (_lib.FLAG_FUSED_GRAD if fused else 0) | \
+                (_lib.FLAG_FUSED_NORM if norm is not None else 0)
         self.fused = fused
+        self.norm = None
+        if norm is not None:                  # (weight, frozen model's weight, eps, weight needs grad)
+            nw, nwr, eps, need = norm
+            self.norm = (nw.contiguous(), nwr.contiguous(), float(eps), bool(need))
+            self.keep += [self.norm[0], self.norm[1]]
         self.grads = None
         self.shape = Shape(B=B2 // 2, T=T, B_ref=Br, T_ref=Tr, H=H, V=V_global, V_local=w.shape[0], v_offset=v_offset,
                            dtype=_lib.DPA_BF16, index_dtype=_lib.DPA_I64 if lp.dtype == torch.int64 else _lib.DPA_I32,
@@ -73,7 +79,9 @@ class _Call:
                          h_pair=_ptr(hp), labels_pair=_ptr(lp), signs_pair=_ptr(sp), h_ref_pol=_ptr(hr), h_ref_frz=_ptr(hf),
                          labels_ref=_ptr(lr), W=_ptr(w), W_ref=_ptr(wr),
                          state=_ptr(self.state), state_bytes=ws.state_bytes, scratch=None, scratch_bytes=0,
-                         losses=_ptr(self.losses), status=_ptr(self.status), d_loss=None, dH_pair=None, dH_ref=None, dW=None)
+                         losses=_ptr(self.losses), status=_ptr(self.status), d_loss=None, dH_pair=None, dH_ref=None, dW=None,
+                         norm_w=_ptr(self.norm[0]) if self.norm else None, norm_w_ref=_ptr(self.norm[1]) if self.norm else None,
+                         d_norm_w=None, norm_eps=self.norm[2] if self.norm else 0.0)
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.state.device).cuda_stream)
@@ -85,11 +93,12 @@ class _Call:
         return scratch
 
     def _alloc_grads(self):
-        hp, _, _, hr, _, _, w, _ = self.keep
+        hp, _, _, hr, _, _, w, _ = self.keep[:8]
         dH_pair, dH_ref = torch.empty_like(hp), torch.empty_like(hr)
         dW = torch.empty_like(w) if self.need_dW else None
-        self.args.dH_pair, self.args.dH_ref, self.args.dW = _ptr(dH_pair), _ptr(dH_ref), _ptr(dW)
-        return dH_pair, dH_ref, dW
+        dnw = torch.empty_like(self.norm[0]) if self.norm and self.norm[3] else None
+        self.args.dH_pair, self.args.dH_ref, self.args.dW, self.args.d_norm_w = _ptr(dH_pair), _ptr(dH_ref), _ptr(dW), _ptr(dnw)
+        return dH_pair, dH_ref, dW, dnw
 
     def forward(self, vocab_group=None):
         with torch.cuda.device(self.state.device):
@@ -128,23 +137,24 @@ class _Call:
                 _lib.check(self.lib.dpa_backward(C.byref(self.args), self._stream()), "dpa_backward[fused]")
                 grads, self.grads = self.grads, None
                 return grads
-            dH_pair, dH_ref, dW = self._alloc_grads()
+            dH_pair, dH_ref, dW, dnw = self._alloc_grads()
             scratch = self._with_scratch(self.ws.bwd_bytes)
             _lib.check(self.lib.dpa_backward(C.byref(self.args), self._stream()), "dpa_backward")
             del scratch
         self.args.scratch, self.args.scratch_bytes = None, 0
-        return dH_pair, dH_ref, dW
+        return dH_pair, dH_ref, dW, dnw
 
 
 class DPALossFn(torch.autograd.Function):
-    """(h_pair, h_ref_pol, W) -> (loss, align, div); integer inputs and the frozen branch get no gradient."""
+    """(h_pair, h_ref_pol, W, norm_weight) -> (loss, align, div); integer inputs and the frozen branch get no gradient."""
 
     @staticmethod
-    def forward(ctx, h_pair, h_ref_pol, W, labels_pair, signs_pair, labels_ref, h_ref_frozen, W_ref, alpha, round_logits,
-                need_dW, dense, chunk_rows, vocab_group, v_offset, V_global, fused):
-        fused = bool(fused and any(ctx.needs_input_grad[:3]))      # no gradient wanted (eval): statistics only
+    def forward(ctx, h_pair, h_ref_pol, W, norm_w, labels_pair, signs_pair, labels_ref, h_ref_frozen, W_ref, alpha, round_logits,
+                need_dW, dense, chunk_rows, vocab_group, v_offset, V_global, fused, norm_w_ref, norm_eps):
+        fused = bool(fused and any(ctx.needs_input_grad[:4]))      # no gradient wanted (eval): statistics only
+        norm = None if norm_w is None else (norm_w.detach(), norm_w_ref.detach(), norm_eps, ctx.needs_input_grad[3])
         call = _Call(h_pair.detach(), labels_pair, signs_pair, h_ref_pol.detach(), h_ref_frozen.detach(), labels_ref,
-                     W.detach(), W_ref.detach(), alpha, round_logits, need_dW, dense, chunk_rows, v_offset, V_global, fused)
+                     W.detach(), W_ref.detach(), alpha, round_logits, need_dW, dense, chunk_rows, v_offset, V_global, fused, norm)
         call.forward(vocab_group)
         ctx.call = call
         ctx.status_t = call.status
@@ -156,13 +166,13 @@ class DPALossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss, g_align, g_div):
         call = ctx.call
-        dH_pair, dH_ref, dW = call.backward(g_loss)
+        dH_pair, dH_ref, dW, dnw = call.backward(g_loss)
         if ctx.vocab_group is not None:
             import torch.distributed as dist
             dist.all_reduce(dH_pair, group=ctx.vocab_group)      # partial sums over vocab shards
             dist.all_reduce(dH_ref, group=ctx.vocab_group)
         ctx.call = None
-        return (dH_pair, dH_ref, dW) + (None,) * 14
+        return (dH_pair, dH_ref, dW, dnw) + (None,) * 16
 
 
 def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.Tensor,
@@ -170,7 +180,9 @@ def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.
              h_ref_frozen: torch.Tensor, W_ref: Optional[torch.Tensor] = None, alpha: float,
              round_logits: bool = True, need_dW: Optional[bool] = None, dense: bool = False, chunk_rows: int = 0,
              vocab_group=None, v_offset: Optional[int] = None, vocab_size: Optional[int] = None,
-             backward: str = "auto") -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+             backward: str = "auto", norm_weight: Optional[torch.Tensor] = None,
+             norm_weight_ref: Optional[torch.Tensor] = None, norm_eps: float = 1e-6,
+             ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """Fused DPA loss.  Returns (loss, alignment_loss, divergence) as 0-dim fp32 CUDA tensors; `loss` carries grad.
 
     h_pair       [2B, T, H] bf16   final hidden states; first B sequences "pos" (correct), last B "neg"
@@ -188,6 +200,11 @@ def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.
     need_dW                        default W.requires_grad (False under the shipped LoRA recipe: lm_head frozen)
     dense                          process every fed position instead of compacting to rows with a non-zero
                                    contribution (what the reference executes; benchmarking only)
+    norm_weight [H]                when given, h_pair / h_ref_pol / h_ref_frozen are the PRE-norm residual stream and the
+                                   decoder's final RMSNorm (weight `norm_weight`, frozen model `norm_weight_ref`, `norm_eps`)
+                                   is applied to the active rows inside the op (llava/model/language_model/
+                                   modelling_llama.py:55-70, :691); gradients come back w.r.t. the pre-norm stream and,
+                                   if it requires grad, norm_weight
     backward                       "recompute": forward keeps only per-row statistics, backward recomputes the logits
                                    chunk-wise (BASELINE north star);  "fused": the forward pass also forms the gradients
                                    (for d_loss = 1) -- reference-sample logits of one row chunk are kept in bf16 and
@@ -208,14 +225,21 @@ def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.
         vocab_size = G * W.shape[0] if vocab_size is None else vocab_size
     else:
         v_offset, vocab_size = 0, W.shape[0]
+    if norm_weight is not None:
+        if vocab_group is not None:
+            raise ValueError("norm_weight (fused final RMSNorm) is not supported together with vocab_group")
+        norm_weight_ref = norm_weight if norm_weight_ref is None else norm_weight_ref
+        for name, t in (("norm_weight", norm_weight), ("norm_weight_ref", norm_weight_ref)):
+            if not t.is_cuda or t.dtype != torch.bfloat16 or t.numel() != h_pair.shape[2]:
+                raise TypeError(f"{name} must be a CUDA bf16 tensor of H elements")
     if backward not in ("auto", "recompute", "fused"):
         raise ValueError("backward must be 'auto', 'recompute' or 'fused'")
     if backward == "fused" and (not round_logits or vocab_group is not None):
         raise ValueError("backward='fused' needs round_logits=True and no vocab_group")
     fused = backward == "fused" or (backward == "auto" and round_logits and vocab_group is None)
-    out = DPALossFn.apply(h_pair, h_ref_pol, W, labels_pair, signs_pair, labels_ref, h_ref_frozen, W_ref, float(alpha),
+    out = DPALossFn.apply(h_pair, h_ref_pol, W, norm_weight, labels_pair, signs_pair, labels_ref, h_ref_frozen, W_ref, float(alpha),
                           bool(round_logits), bool(need_dW), bool(dense), int(chunk_rows), vocab_group, int(v_offset),
-                          int(vocab_size), fused)
+                          int(vocab_size), fused, norm_weight_ref, float(norm_eps))
     return out
 
 

@@ -102,8 +102,24 @@ def stack_pair_batch(inputs: Dict[str, torch.Tensor]):
             stack(inputs["pos_signs"], inputs["neg_signs"], 0))
 
 
-def final_hidden_states(model, input_ids, images, labels, attention_mask, signs=None):
-    """Splice the image features in and run the decoder up to (and including) its final norm.
+@contextlib.contextmanager
+def _final_norm_bypassed(inner, bypass: bool):
+    """LlamaModel applies `self.norm` as its last step (llava/model/language_model/modelling_llama.py:543,691).  With
+    `bypass` the decoder returns the pre-norm residual stream and the norm is applied inside dpa_loss to the rows that
+    matter."""
+    if not bypass:
+        yield None
+        return
+    norm = inner.norm
+    inner.norm = torch.nn.Identity()
+    try:
+        yield norm
+    finally:
+        inner.norm = norm
+
+
+def final_hidden_states(model, input_ids, images, labels, attention_mask, signs=None, skip_final_norm: bool = False):
+    """Splice the image features in and run the decoder up to (and including, unless skip_final_norm) its final norm.
     Returns (hidden [S,T',H], labels [S,T'], signs [S,T'] or None) aligned row for row, post-splice."""
     mm = unwrap_model(model)
     inner, _, flavour = decoder_and_head(mm)
@@ -118,14 +134,16 @@ def final_hidden_states(model, input_ids, images, labels, attention_mask, signs=
         # VILA's patched Llama takes the per-sequence lengths for its varlen flash-attention
         # (vila/model/language_model/llava_llama.py:150-166)
         kw["seqlens_in_batch"] = attention_mask.sum(-1).int()
-    out = inner(**kw)
+    with _final_norm_bypassed(inner, skip_final_norm):
+        out = inner(**kw)
     hidden = out.last_hidden_state if hasattr(out, "last_hidden_state") else out[0]
     return hidden, labels, signs
 
 
 # ----------------------------------------------------------------------------------------------- the override
 def fused_compute_loss(trainer, model, inputs, return_outputs: bool = False, num_items_in_batch: Optional[int] = None,
-                       *, round_logits: bool = True, backward: str = "auto", sync_logging: bool = False):
+                       *, round_logits: bool = True, backward: str = "auto", sync_logging: bool = False,
+                       fuse_final_norm: bool = False):
     """Same contract as ``HalvaTrainer.compute_loss(model, inputs)``: returns the 0-dim fp32 loss (with grad).
 
     The LLaVA flavour of the reference ignores its ``model`` argument and calls ``self.model``
@@ -133,6 +151,8 @@ def fused_compute_loss(trainer, model, inputs, return_outputs: bool = False, num
     argument is used when it wraps a multimodal model, else ``trainer.model``.  ``return_outputs`` is accepted and, like
     in the reference, does not change the return value unless True (then ``(loss, {"align", "div"})``).
     ``num_items_in_batch`` (newer transformers) is accepted and ignored, as the reference would.
+    ``fuse_final_norm``: run the decoders without their final RMSNorm and let dpa_loss apply it (and its backward) to
+    the contributing rows only.
     """
     try:
         policy = unwrap_model(model)
@@ -145,23 +165,29 @@ def fused_compute_loss(trainer, model, inputs, return_outputs: bool = False, num
 
     ids, labels, mask, signs = stack_pair_batch(inputs)
     images = inputs["images"]
-    h_pair, labels_pair, signs_pair = final_hidden_states(policy, ids, torch.cat([images, images], dim=0), labels, mask, signs)
+    fn = fuse_final_norm
+    h_pair, labels_pair, signs_pair = final_hidden_states(policy, ids, torch.cat([images, images], dim=0), labels, mask, signs, fn)
 
     ref_images = inputs["ref_images"]
     if flavour == "vila":
         ref_images = ref_images.squeeze(1)                                    # vila halva_trainer.py:760 (no-op unless dim 1 is 1)
     h_ref_pol, labels_ref, _ = final_hidden_states(policy, inputs["ref_input_ids"], ref_images, inputs["ref_labels"],
-                                                   inputs["ref_attention_mask"])
+                                                   inputs["ref_attention_mask"], None, fn)
     with torch.no_grad():
         h_ref_frz, _, _ = final_hidden_states(frozen, inputs["ref_input_ids"], ref_images, inputs["ref_labels"],
-                                              inputs["ref_attention_mask"])
+                                              inputs["ref_attention_mask"], None, fn)
+    norm_kw = {}
+    if fn:
+        n_pol, n_frz = decoder_and_head(policy)[0].norm, decoder_and_head(frozen)[0].norm
+        norm_kw = dict(norm_weight=n_pol.weight, norm_weight_ref=n_frz.weight.detach(),
+                       norm_eps=float(getattr(n_pol, "variance_epsilon", getattr(n_pol, "eps", 1e-6))))
 
     W, W_ref = head.weight, ref_head.weight
     with gathered_weight(W, W_ref):
         loss, align, div = _dpa_loss_mod.dpa_loss(
             h_pair, labels_pair, signs_pair, h_ref_pol, labels_ref, W, h_ref_frozen=h_ref_frz,
             W_ref=None if W_ref is W else W_ref.detach(), alpha=alpha, round_logits=round_logits,
-            need_dW=bool(W.requires_grad), backward=backward)
+            need_dW=bool(W.requires_grad), backward=backward, **norm_kw)
 
     holder = getattr(trainer, "loss_holder", None)
     if isinstance(holder, dict) and all(k in holder for k in ("contrastive_loss", "divergence", "loss")):

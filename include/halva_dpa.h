@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DPA_ABI_VERSION 2
+#define DPA_ABI_VERSION 3
 
 typedef enum {
   DPA_OK = 0,
@@ -61,6 +61,11 @@ typedef enum { DPA_I64 = 0, DPA_I32 = 1 } dpa_index_t;
                                      bf16 per row chunk instead of being recomputed); dpa_backward then only scales by
                                      *d_loss.  Needs DPA_FLAG_ROUND_LOGITS, the gradient pointers at forward time and
                                      `fused_bytes` of scratch. */
+
+#define DPA_FLAG_FUSED_NORM   16  /* h_pair / h_ref_pol / h_ref_frz are the PRE-norm residual stream: the decoder's final
+                                     RMSNorm (llava/model/language_model/modelling_llama.py:55-70: fp32 variance, cast back,
+                                     weight multiply) is applied while the active rows are gathered, and its backward to
+                                     the dH rows.  Needs norm_w / norm_w_ref / norm_eps. */
 
 typedef struct {
   int32_t B;          /* sample pairs; h_pair holds 2B sequences, first B "pos"(correct), last B "neg"(hallucinated) */
@@ -107,6 +112,11 @@ typedef struct {
   void* dH_pair;               /* [2B, T, H]  (fully written, zeros for inactive rows) */
   void* dH_ref;                /* [B_ref, T_ref, H] */
   void* dW;                    /* [V_local, H] or NULL */
+  /* DPA_FLAG_FUSED_NORM only */
+  const void* norm_w;          /* [H] final-norm weight of the policy model */
+  const void* norm_w_ref;      /* [H] final-norm weight of the frozen reference model (may alias norm_w) */
+  void* d_norm_w;              /* [H] gradient of norm_w, or NULL (frozen under the LoRA recipe) */
+  float norm_eps;
 } dpa_args_t;
 
 int dpa_version(void);

@@ -61,8 +61,33 @@ def phrase_columns(signs_half: np.ndarray):
     return U[1:], col
 
 
+def rmsnorm_fwd(x, w, eps, mode):
+    """llava/model/language_model/modelling_llama.py:64-69: fp32 variance, x * rsqrt(var + eps) cast back to the input
+    dtype, then weight * (.)  -- two bf16 rounding points in the reference's bf16 execution."""
+    r = 1.0 / np.sqrt((x * x).mean(-1, keepdims=True) + eps)
+    n = x * r
+    if mode == "bf16":
+        n = bf16_round(n)
+    y = w * n
+    if mode == "bf16":
+        y = bf16_round(y)
+    return y, n, r
+
+
+def rmsnorm_bwd(dy, x, w, n, r, mode):
+    """autograd of rmsnorm_fwd: dn = dy * w (a bf16 tensor in bf16 mode), dx = r dn - x r^3 mean(dn x), dw = sum_rows dy n."""
+    dn = dy * w
+    if mode == "bf16":
+        dn = bf16_round(dn)
+    dx = r * dn - x * (r ** 3) * (dn * x).mean(-1, keepdims=True)
+    dw = (dy * n).reshape(-1, x.shape[-1]).sum(0)
+    if mode == "bf16":
+        dx, dw = bf16_round(dx), bf16_round(dw)
+    return dx, dw
+
+
 def dpa_loss(h_pair, labels_pair, signs_pair, h_ref_pol, h_ref_frz, labels_ref, W, W_ref, alpha,
-             mode="fp64", need_dW=True, grad_output=1.0):
+             mode="fp64", need_dW=True, grad_output=1.0, norm_w=None, norm_w_ref=None, norm_eps=1e-6, norm_mode=None):
     """Forward + closed-form backward of compute_loss.
 
     h_pair [2B,T,H]: first B sequences "pos"(correct), last B "neg"(hallucinated)  (:485-487)
@@ -75,6 +100,16 @@ def dpa_loss(h_pair, labels_pair, signs_pair, h_ref_pol, h_ref_frz, labels_ref, 
     rz = bf16_round if mode == "bf16" else (lambda a: a)
     f64 = lambda a: np.asarray(a, dtype=np.float64)
     h_pair, h_ref_pol, h_ref_frz, W, W_ref = map(f64, (h_pair, h_ref_pol, h_ref_frz, W, W_ref))
+    fused_norm = norm_w is not None
+    norm_mode = mode if norm_mode is None else norm_mode    # "bf16": the norm's own rounding points even when the
+    if fused_norm:        # logits maths is exact (the GEMM operand is a bf16 tensor either way)
+        # h_* are the pre-norm residual stream (final RMSNorm of the decoder folded into this path)
+        norm_w = f64(norm_w)
+        norm_w_ref = norm_w if norm_w_ref is None else f64(norm_w_ref)
+        x_pair, x_ref_pol = h_pair, h_ref_pol
+        h_pair, n_pair_, r_pair_ = rmsnorm_fwd(x_pair, norm_w, norm_eps, norm_mode)
+        h_ref_pol, n_ref_, r_ref_ = rmsnorm_fwd(x_ref_pol, norm_w, norm_eps, norm_mode)
+        h_ref_frz, _, _ = rmsnorm_fwd(h_ref_frz, norm_w_ref, norm_eps, norm_mode)
     labels_pair = np.asarray(labels_pair).astype(np.int64)
     signs_pair = np.asarray(signs_pair).astype(np.int64)
     labels_ref = np.asarray(labels_ref).astype(np.int64)
@@ -148,7 +183,12 @@ def dpa_loss(h_pair, labels_pair, signs_pair, h_ref_pol, h_ref_frz, labels_ref, 
     if mode == "bf16":
         dH_pair, dH_ref = bf16_round(dH_pair), bf16_round(dH_ref)
         dW = bf16_round(dW) if dW is not None else None
-    return dict(loss=loss, align=align, div=div, P=P, N=N, dH_pair=dH_pair, dH_ref=dH_ref, dW=dW,
+    d_norm_w = None
+    if fused_norm:
+        dH_pair, dw1 = rmsnorm_bwd(dH_pair, x_pair, norm_w, n_pair_, r_pair_, norm_mode)
+        dH_ref, dw2 = rmsnorm_bwd(dH_ref, x_ref_pol, norm_w, n_ref_, r_ref_, norm_mode)
+        d_norm_w = dw1 + dw2
+    return dict(loss=loss, align=align, div=div, P=P, N=N, dH_pair=dH_pair, dH_ref=dH_ref, dW=dW, d_norm_w=d_norm_w,
                 logp_pair=logp, kl_rows=kl_rows, lse_pair=lse, lse_ref_pol=lp, lse_ref_frz=lr,
                 active_pair=active, active_ref=vr, col=col, coef_pair=coef)
 

@@ -69,11 +69,26 @@ def _case_inputs(name):
             s[half * B, t0 + 3:t0 + 5] = 3
         inp["signs_pair"] = s
         return inp, torch.float32
+    if name in ("norm_fp32", "norm_bf16"):   # final RMSNorm folded in: h_* are the PRE-norm stream
+        dt = torch.float32 if name.endswith("fp32") else torch.bfloat16
+        inp = make_inputs(DPAShape(B=2, T=64, H=128, V=512, n_sys=3, n_img=8, n_q=3, k_max=3, density=0.2),
+                          seed=21, dtype=dt, shared_head=name.endswith("bf16"))
+        g = torch.Generator().manual_seed(77)
+        for k in ("h_pair", "h_ref_pol", "h_ref_frz"):          # un-normalised residual stream: rows of very different scale
+            scale = (0.5 + 3.0 * torch.rand(inp[k].shape[:2] + (1,), generator=g))
+            inp[k] = (inp[k].float() * scale).to(dt)
+        inp["norm_w"] = (1.0 + 0.2 * torch.randn(128, generator=g)).to(dt)
+        inp["norm_w_ref"] = inp["norm_w"] if name.endswith("bf16") else (inp["norm_w"].float() + 0.05 * torch.randn(128, generator=g)).to(dt)
+        inp["norm_eps"] = 1e-5
+        # keep the logits in the usual range: the normalised rows have unit RMS, the synthetic W assumes |h| ~ 1.5
+        inp["W"] = (inp["W"].float() * 1.5).to(dt)
+        inp["W_ref"] = inp["W"] if name.endswith("bf16") else (inp["W_ref"].float() * 1.5).to(dt)
+        return inp, dt
     raise KeyError(name)
 
 
 CASES = ["tiny_fp32", "tiny_bf16", "small_fp32_fullft", "small_bf16", "k1_alpha0_fp32", "sparse_ids_fp32",
-         "no_zero_sign_fp32"]
+         "no_zero_sign_fp32", "norm_fp32", "norm_bf16"]
 
 
 def _np(t):
@@ -85,12 +100,16 @@ def generate(name):
     args = (inp["h_pair"], inp["labels_pair"], inp["signs_pair"], inp["h_ref_pol"], inp["h_ref_frz"],
             inp["labels_ref"], inp["W"], inp["W_ref"])
     torch.manual_seed(0)
-    ref = run_reference(*args, alpha=inp["alpha"])
-    ref0 = run_reference(*args, alpha=0.0, need_grad=False)          # loss at alpha 0 == alignment term
+    nk = {}
+    if "norm_w" in inp:
+        nk = dict(norm_w=inp["norm_w"], norm_w_ref=inp["norm_w_ref"], norm_eps=inp["norm_eps"])
+    ref = run_reference(*args, alpha=inp["alpha"], **nk)
+    ref0 = run_reference(*args, alpha=0.0, need_grad=False, **nk)    # loss at alpha 0 == alignment term
     # the same reference code fed fp32 copies of the same (bf16-valued) tensors: "fp32 maths" comparator
     f32 = [a.float() if a.is_floating_point() else a for a in args]
-    ref32 = run_reference(*f32, alpha=inp["alpha"])
-    ref32_0 = run_reference(*f32, alpha=0.0, need_grad=False)
+    nk32 = {k: (v.float() if torch.is_tensor(v) else v) for k, v in nk.items()}
+    ref32 = run_reference(*f32, alpha=inp["alpha"], **nk32)
+    ref32_0 = run_reference(*f32, alpha=0.0, need_grad=False, **nk32)
     out = dict(
         dtype=np.array("bf16" if dtype == torch.bfloat16 else "fp32"),
         alpha=np.float64(inp["alpha"]),
@@ -102,6 +121,9 @@ def generate(name):
         ref32_loss=np.float64(ref32["loss"].item()), ref32_align=np.float64(ref32_0["loss"].item()),
         ref32_dH_pair=_np(ref32["dH_pair"]), ref32_dH_ref=_np(ref32["dH_ref"]), ref32_dW=_np(ref32["dW"]),
     )
+    if nk:
+        out.update(norm_w=_np(inp["norm_w"]), norm_w_ref=_np(inp["norm_w_ref"]), norm_eps=np.float64(inp["norm_eps"]),
+                   ref_d_norm_w=_np(ref["d_norm_w"]), ref32_d_norm_w=_np(ref32["d_norm_w"]))
     path = os.path.join(GOLDEN_DIR, name + ".npz")
     np.savez_compressed(path, **out)
     print(f"{name:22s} loss={out['ref_loss']:.7f} align={out['ref_align']:.7f} "
@@ -145,6 +167,9 @@ if __name__ == "__main__":
         sys.exit("needs /root/reference (build container only)")
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(8)
+    only = sys.argv[1:]
     for c in CASES:
-        generate(c)
-    generate_quirks()
+        if not only or c in only:
+            generate(c)
+    if not only:
+        generate_quirks()

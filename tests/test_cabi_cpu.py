@@ -24,7 +24,8 @@ def test_exports_match_header():
     assert declared == set(EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.dpa_version() == 2
+    from halva_b200._lib import ABI_VERSION
+    assert lib.dpa_version() == ABI_VERSION == 3
 
 
 def test_workspace_query_and_shape_validation():

@@ -19,8 +19,11 @@ TOL_LOSS_BF16, TOL_GRAD_BF16, TOL_LOSS_FP32, TOL_DIV_FP32 = 1e-3, 1e-2, 2e-5, 2e
 def _to_cuda(g):
     bf = lambda k: torch.from_numpy(g[k]).to(torch.bfloat16).cuda()
     ix = lambda k: torch.from_numpy(g[k]).cuda()
-    return dict(h_pair=bf("h_pair"), labels_pair=ix("labels_pair"), signs_pair=ix("signs_pair"), h_ref_pol=bf("h_ref_pol"),
-                h_ref_frz=bf("h_ref_frz"), labels_ref=ix("labels_ref"), W=bf("W"), W_ref=bf("W_ref"), alpha=float(g["alpha"]))
+    t = dict(h_pair=bf("h_pair"), labels_pair=ix("labels_pair"), signs_pair=ix("signs_pair"), h_ref_pol=bf("h_ref_pol"),
+             h_ref_frz=bf("h_ref_frz"), labels_ref=ix("labels_ref"), W=bf("W"), W_ref=bf("W_ref"), alpha=float(g["alpha"]))
+    if "norm_w" in g:      # final RMSNorm folded into the op: the hidden states are the pre-norm stream
+        t.update(norm_w=bf("norm_w"), norm_w_ref=bf("norm_w_ref"), norm_eps=float(g["norm_eps"]))
+    return t
 
 
 def _run_cuda(t, round_logits=True, need_dW=True, grad_out=1.0, **kw):
@@ -29,18 +32,27 @@ def _run_cuda(t, round_logits=True, need_dW=True, grad_out=1.0, **kw):
     hr = t["h_ref_pol"].clone().requires_grad_(True)
     W = t["W"].clone().requires_grad_(need_dW)
     W_ref = W if t["W_ref"] is t["W"] else t["W_ref"]
+    nw = None
+    if "norm_w" in t:
+        nw = t["norm_w"].clone().requires_grad_(True)
+        kw = dict(kw, norm_weight=nw, norm_weight_ref=t["norm_w_ref"], norm_eps=t["norm_eps"])
     loss, align, div = dpa_loss(hp, t["labels_pair"], t["signs_pair"], hr, t["labels_ref"], W, h_ref_frozen=t["h_ref_frz"],
                                 W_ref=W_ref.detach() if W_ref is not W else None, alpha=t["alpha"], round_logits=round_logits, **kw)
     (loss * grad_out).backward()
     torch.cuda.synchronize()
     f = lambda x: None if x is None else x.float().cpu().numpy()
-    return dict(loss=loss.item(), align=align.item(), div=div.item(), dH_pair=f(hp.grad), dH_ref=f(hr.grad), dW=f(W.grad))
+    return dict(loss=loss.item(), align=align.item(), div=div.item(), dH_pair=f(hp.grad), dH_ref=f(hr.grad), dW=f(W.grad),
+                d_norm_w=None if nw is None else f(nw.grad))
 
 
 def _oracle(t, mode):
     f = lambda x: x.float().cpu().numpy()
+    nk = {}
+    if "norm_w" in t:
+        # the normed rows are the bf16 GEMM operand in every mode: keep the norm's own rounding points
+        nk = dict(norm_w=f(t["norm_w"]), norm_w_ref=f(t["norm_w_ref"]), norm_eps=t["norm_eps"], norm_mode="bf16")
     return dpa_oracle.dpa_loss(f(t["h_pair"]), t["labels_pair"].cpu().numpy(), t["signs_pair"].cpu().numpy(), f(t["h_ref_pol"]),
-                               f(t["h_ref_frz"]), t["labels_ref"].cpu().numpy(), f(t["W"]), f(t["W_ref"]), t["alpha"], mode=mode)
+                               f(t["h_ref_frz"]), t["labels_ref"].cpu().numpy(), f(t["W"]), f(t["W_ref"]), t["alpha"], mode=mode, **nk)
 
 
 def _close(a, b, tol):
@@ -61,7 +73,7 @@ def test_golden_inputs_vs_oracle(name):
         assert _close(c["align"], o["align"], tol), (name, mode, bwd, c["align"], o["align"])
         tol_div = TOL_DIV_FP32 if mode == "fp64" else tol
         assert abs(c["div"] - o["div"]) <= tol_div * abs(o["div"]) + 1e-7, (name, mode, bwd, c["div"], o["div"])
-        for k in ("dH_pair", "dH_ref", "dW"):
+        for k in ("dH_pair", "dH_ref", "dW") + (("d_norm_w",) if "norm_w" in t else ()):
             assert rel(c[k], o[k]) <= TOL_GRAD_BF16, (name, mode, bwd, k, rel(c[k], o[k]))
         # structural zeros: last position and rows without contribution get exactly zero gradient
         assert np.all(c["dH_pair"][:, -1] == 0) and np.all(c["dH_ref"][:, -1] == 0)
@@ -70,15 +82,17 @@ def test_golden_inputs_vs_oracle(name):
 
 
 @pytest.mark.parametrize("bwd", ["fused", "recompute"])
-@pytest.mark.parametrize("name", ["tiny_bf16", "small_bf16"])
+@pytest.mark.parametrize("name", ["tiny_bf16", "small_bf16", "norm_bf16"])
 def test_golden_reference_outputs_bf16(name, bwd):
     """bf16 golden cases: CUDA vs what the reference itself produced in bf16 (tests/golden, oracle/gen_golden.py)."""
     g = load_golden(name)
     c = _run_cuda(_to_cuda(g), round_logits=True, backward=bwd)
     assert _close(c["loss"], float(g["ref_loss"]), TOL_LOSS_BF16)
     assert _close(c["align"], float(g["ref_align"]), TOL_LOSS_BF16)
-    for k in ("dH_pair", "dH_ref", "dW"):
+    for k in ("dH_pair", "dH_ref", "dW") + (("d_norm_w",) if "norm_w" in g else ()):
         assert rel(c[k], g["ref_" + k]) <= TOL_GRAD_BF16, (k, rel(c[k], g["ref_" + k]))
+    if "norm_w" in g:
+        return      # the reference's fp32 execution keeps the normed rows in fp32; here they are the bf16 GEMM operand
     # and against the reference's fp32 execution on the same bf16 values
     c32 = _run_cuda(_to_cuda(g), round_logits=False)
     assert _close(c32["loss"], float(g["ref32_loss"]), TOL_LOSS_FP32)

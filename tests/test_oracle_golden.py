@@ -7,12 +7,12 @@ import numpy as np
 import pytest
 
 from oracle import dpa_oracle
-from dpa_testutil import golden_path, rel
+from dpa_testutil import golden_path, norm_kwargs, rel
 
 
 def _run(g, mode):
     return dpa_oracle.dpa_loss(g["h_pair"], g["labels_pair"], g["signs_pair"], g["h_ref_pol"], g["h_ref_frz"],
-                               g["labels_ref"], g["W"], g["W_ref"], float(g["alpha"]), mode=mode)
+                               g["labels_ref"], g["W"], g["W_ref"], float(g["alpha"]), mode=mode, **norm_kwargs(g))
 
 
 def test_oracle_matches_reference_fp32_maths(golden):
@@ -23,6 +23,8 @@ def test_oracle_matches_reference_fp32_maths(golden):
     assert rel(o["dH_pair"], golden["ref32_dH_pair"]) <= 1e-4
     assert rel(o["dH_ref"], golden["ref32_dH_ref"]) <= 1e-4
     assert rel(o["dW"], golden["ref32_dW"]) <= 1e-4
+    if "norm_w" in golden:          # final RMSNorm folded in: gradients w.r.t. the pre-norm stream and the norm weight
+        assert rel(o["d_norm_w"], golden["ref32_d_norm_w"]) <= 1e-4
     # structural zeros: last position and inactive rows get exactly no gradient in the reference
     assert np.all(golden["ref32_dH_pair"][:, -1] == 0) and np.all(o["dH_pair"][:, -1] == 0)
     inactive = ~o["active_pair"]
@@ -40,6 +42,8 @@ def test_oracle_bf16_mode_matches_reference_bf16(golden):
     assert rel(o["dH_pair"], golden["ref_dH_pair"]) <= 1e-2
     assert rel(o["dH_ref"], golden["ref_dH_ref"]) <= 1e-2
     assert rel(o["dW"], golden["ref_dW"]) <= 1e-2
+    if "norm_w" in golden:
+        assert rel(o["d_norm_w"], golden["ref_d_norm_w"]) <= 1e-2
 
 
 def test_divergence_component(golden):

@@ -29,6 +29,21 @@ class _Inner(nn.Module):
         return types.SimpleNamespace(last_hidden_state=self.norm(torch.tanh(self.fc(inputs_embeds))))
 
 
+class _RMSNorm(nn.Module):
+    """Same arithmetic as the reference's LlamaRMSNorm (modelling_llama.py:55-70)."""
+
+    def __init__(self, H, eps=1e-5):
+        super().__init__()
+        self.weight = nn.Parameter(1.0 + 0.1 * torch.randn(H))
+        self.variance_epsilon = eps
+
+    def forward(self, x):
+        dt = x.dtype
+        x = x.to(torch.float32)
+        x = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + self.variance_epsilon)
+        return self.weight * x.to(dt)
+
+
 class FakeLlava(nn.Module):
     """LlavaLlamaForCausalLM look-alike: embeds ids, splices N_IMG 'image' rows after position 2 (labels and signs
     become -100 there, llava_arch.py:322-323), decoder, lm_head."""
@@ -223,6 +238,33 @@ def test_patch_installs_override():
     assert T._reference_compute_loss is orig and T.compute_loss is not orig
     import inspect
     assert "num_items_in_batch" in inspect.signature(T.compute_loss).parameters
+
+
+@pytest.mark.gpu
+def test_shim_cuda_fused_final_norm():
+    """fuse_final_norm: decoder run without its RMSNorm, the op applies it to the contributing rows; same loss and
+    parameter gradients (incl. the norm weight) as the unfused shim."""
+    from halva_b200 import trainer as shim
+    pol, frz = _models(seed=4, dtype=torch.bfloat16, device="cuda")
+    for m in (pol, frz):
+        m.inner.norm = _RMSNorm(64).to(device="cuda", dtype=torch.bfloat16)
+    frz.inner.norm.load_state_dict(pol.inner.norm.state_dict())
+    frz.requires_grad_(False)
+    inputs = make_inputs(B=3, Tp=40, Tn=37, Tr=33, seed=4, device="cuda")
+    tr = _trainer(pol, frz)
+    la = shim.fused_compute_loss(tr, pol, inputs)
+    la.backward()
+    ga = _grads(pol)
+    pol.zero_grad()
+    lb = shim.fused_compute_loss(tr, pol, inputs, fuse_final_norm=True)
+    lb.backward()
+    gb = _grads(pol)
+    assert isinstance(pol.inner.norm, _RMSNorm)                      # restored after the call
+    assert abs(la.item() - lb.item()) <= 1e-3 * abs(la.item())
+    rel = lambda a, b: float((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-30))
+    assert set(ga) == set(gb)
+    for n in ga:
+        assert rel(gb[n], ga[n]) <= 3e-2, (n, rel(gb[n], ga[n]))
 
 
 @pytest.mark.gpu
