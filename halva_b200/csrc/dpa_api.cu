@@ -155,6 +155,17 @@ int launch_single(cudaStream_t st, const DeviceInfo* d, const CUtensorMap& tmA, 
   return launch_gemm<GemmCfg<256, false, AMAJ, BMAJ, 1>, Epi>(st, d->sms, tmA, tmB1, tmA, tmB1, work, ep, what);
 }
 
+// dual-accumulator GEMMs (policy + frozen logits of the same rows): 128-wide tiles; tmB*_1 boxes hold 128 rows of W
+// (cta_group 1), tmB*_2 boxes 64 rows (cta_group 2: a CTA pair shares a 256 x 128 x 2 tile)
+template <class Epi>
+int launch_dual(cudaStream_t st, const DeviceInfo* d, const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB_1,
+                const CUtensorMap& tmB2_1, const CUtensorMap& tmB_2, const CUtensorMap& tmB2_2, const GemmWork& work,
+                const typename Epi::Params& ep, const char* what) {
+  if (cta_group() == 2)
+    return launch_gemm<GemmCfg<128, true, KMAJOR, KMAJOR, 2>, Epi>(st, d->sms, tmA, tmB_2, tmA2, tmB2_2, work, ep, what);
+  return launch_gemm<GemmCfg<128, true, KMAJOR, KMAJOR, 1>, Epi>(st, d->sms, tmA, tmB_1, tmA2, tmB2_1, work, ep, what);
+}
+
 // ---------------------------------------------------------------------------------- workspace layout
 constexpr int kTpuPair = 5;     // 256-wide column tiles per unit  (V=32000: 125 tiles -> 25 groups)
 constexpr int kTpuRef = 10;     // 128-wide column tiles per unit  (V=32000: 250 tiles -> 25 groups)
@@ -336,8 +347,10 @@ template <bool ROUND>
 int run_forward_gemms(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, cudaStream_t st) {
   const dpa_shape_t& s = a->shape;
   const int cap_tot = L.cap_pair + L.cap_ref;
-  CUtensorMap tmHp, tmHpD, tmHf, tmW256, tmW128, tmWr128;
+  CUtensorMap tmHp, tmHpD, tmHf, tmW256, tmW128, tmWr128, tmW64, tmWr64;
   int rc;
+  if ((rc = make_operand_tmap(d, &tmW64, a->W, KMAJOR, s.V_local, s.H, s.H, 64))) return rc;
+  if ((rc = make_operand_tmap(d, &tmWr64, a->W_ref, KMAJOR, s.V_local, s.H, s.H, 64))) return rc;
   if ((rc = make_operand_tmap(d, &tmHp, at<char>(a->scratch, L.f_Hp), KMAJOR, cap_tot, s.H, s.H, BM))) return rc;
   if ((rc = make_operand_tmap(d, &tmHf, at<char>(a->scratch, L.f_Hf), KMAJOR, L.cap_ref, s.H, s.H, BM))) return rc;
   if ((rc = make_operand_tmap(d, &tmW256, a->W, KMAJOR, s.V_local, s.H, s.H, kBnPair))) return rc;
@@ -354,12 +367,11 @@ int run_forward_gemms(const dpa_args_t* a, const Layout& L, const DeviceInfo* d,
     if ((rc = launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHp, tmW256, tmW128, w, ep, "fwd_pair"))) return rc;
   }
   {
-    using Cfg = GemmCfg<kBnRef, true, KMAJOR, KMAJOR>;
     using Epi = EpiStatsRef<kBnRef, ROUND>;
     GemmWork w{meta, KIND_FWD_REF, 0, 0, 0, s.V_local, s.H, kTpuRef};
     typename Epi::Params ep{at<float4>(a->scratch, L.f_part_ref), at<float>(a->scratch, L.f_part_u), L.cap_ref, s.V_local};
     ProfScope ps(PK_FWD_REF, 1, st);
-    if ((rc = launch_gemm<Cfg, Epi>(st, d->sms, tmHpD, tmW128, tmHf, tmWr128, w, ep, "fwd_ref"))) return rc;
+    if ((rc = launch_dual<Epi>(st, d, tmHpD, tmHf, tmW128, tmWr128, tmW64, tmWr64, w, ep, "fwd_ref"))) return rc;
   }
   return DPA_OK;
 }
@@ -678,7 +690,9 @@ int run_backward(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, cuda
   }
 
   __nv_bfloat16* dz = at<__nv_bfloat16>(a->scratch, L.b_dz);
-  CUtensorMap tmHp, tmHf, tmW256, tmW128, tmWr128, tmDzK, tmWmn, tmDzMN, tmHpMN;
+  CUtensorMap tmHp, tmHf, tmW256, tmW128, tmWr128, tmW64, tmWr64, tmDzK, tmWmn, tmDzMN, tmHpMN;
+  if ((rc = make_operand_tmap(d, &tmW64, a->W, KMAJOR, s.V_local, s.H, s.H, 64))) return rc;
+  if ((rc = make_operand_tmap(d, &tmWr64, a->W_ref, KMAJOR, s.V_local, s.H, s.H, 64))) return rc;
   if ((rc = make_operand_tmap(d, &tmHp, at<char>(a->scratch, L.b_Hp), KMAJOR, cap_tot, s.H, s.H, BM))) return rc;
   if ((rc = make_operand_tmap(d, &tmHf, at<char>(a->scratch, L.b_Hf), KMAJOR, L.cap_ref, s.H, s.H, BM))) return rc;
   if ((rc = make_operand_tmap(d, &tmW256, a->W, KMAJOR, s.V_local, s.H, s.H, kBnPair))) return rc;
@@ -701,13 +715,12 @@ int run_backward(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, cuda
       if ((rc = launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHp, tmW256, tmW128, w, ep, "dz_pair"))) return rc;
     }
     {
-      using Cfg = GemmCfg<kBnRef, true, KMAJOR, KMAJOR>;
       using Epi = EpiDzRef<kBnRef, ROUND>;
       GemmWork w{meta, KIND_DZ_REF, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuRef};
       typename Epi::Params ep{meta, at<float>(a->state, L.lse_ref_p), at<float>(a->state, L.lse_ref_r), at<float>(a->state, L.coef_ref),
                               dz, L.ldz, ch * L.chunk_rows, s.V_local};
       ProfScope ps(PK_DZ_REF, 1, st);
-      if ((rc = launch_gemm<Cfg, Epi>(st, d->sms, tmHp, tmW128, tmHf, tmWr128, w, ep, "dz_ref"))) return rc;
+      if ((rc = launch_dual<Epi>(st, d, tmHp, tmHf, tmW128, tmWr128, tmW64, tmWr64, w, ep, "dz_ref"))) return rc;
     }
     {
       using Epi = EpiStoreRows<256>;

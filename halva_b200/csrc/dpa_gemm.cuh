@@ -122,13 +122,13 @@ struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN_CTA * BK * 2;
   static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (DUAL ? 2 : 1);
-  static constexpr int STAGES_RAW = (227 * 1024 - 1280) / STAGE_BYTES;   // 7 x 32 KiB (pair), 4 x 48 KiB, 3 x 64 KiB (dual)
+  static constexpr int STAGES_RAW = (227 * 1024 - 1280) / STAGE_BYTES;   // 7 x 32 KiB (pair), 4 x 48 KiB (single CTA / dual pair), 3 x 64 KiB (dual single CTA)
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int ACC_COLS = DUAL ? 2 * BN : BN;             // TMEM columns per accumulator stage
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static_assert(2 * ACC_COLS <= 512, "two accumulator stages must fit TMEM");
   static_assert(BN % 64 == 0 && BN <= 256 && BN_CTA % 64 == 0, "BN");
-  static_assert(CG == 1 || (CG == 2 && !DUAL), "cta_group");
+  static_assert(CG == 1 || CG == 2, "cta_group");
 };
 
 // issue the TMA loads of one operand tile for one K block
@@ -226,7 +226,8 @@ dpa_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                                      tr.b_k0 + kb * BK);
             if constexpr (Cfg::DUAL) {
               load_operand<Cfg::AMAJ, BM, CG>(sA2 + st * Cfg::A_BYTES, &tmA2, &full[st], tr.a2_row0 + mt * BM, tr.a_k0 + kb * BK);
-              load_operand<Cfg::BMAJ, Cfg::BN_CTA, CG>(sB2 + st * Cfg::B_BYTES, &tmB2, &full[st], nt * BN, tr.b_k0 + kb * BK);
+              load_operand<Cfg::BMAJ, Cfg::BN_CTA, CG>(sB2 + st * Cfg::B_BYTES, &tmB2, &full[st], nt * BN + cta_rank * Cfg::BN_CTA,
+                                                       tr.b_k0 + kb * BK);
             }
             if constexpr (CG == 2) {
               // both CTAs' bytes are accounted on the leader's barrier (the .cta_group::2 loads signal it)
