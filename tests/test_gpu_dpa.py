@@ -110,7 +110,7 @@ def _synth(name="small", seed=3, **over):
 
 
 @pytest.mark.parametrize("over", [dict(), dict(T=129, T_ref=77), dict(V=1000 - 8, H=192), dict(B=1, B_ref=3, k_max=1),
-                                  dict(H=4096, V=2048, T=64, T_ref=64, B=1)])
+                                  dict(H=4096, V=2048, T=64, T_ref=64, B=1), dict(V=1003, H=128), dict(V=77, H=64, T=40, T_ref=33)])
 def test_synthetic_shapes_vs_oracle(over):
     """Ragged T, V not a multiple of the tile, H not a multiple of 256, B_ref != B."""
     t, shape = _synth(**over)
@@ -121,6 +121,28 @@ def test_synthetic_shapes_vs_oracle(over):
         assert _close(c["div"], o["div"], TOL_LOSS_BF16), bwd
         for k in ("dH_pair", "dH_ref", "dW"):
             assert rel(c[k], o[k]) <= TOL_GRAD_BF16, (bwd, k, rel(c[k], o[k]))
+
+
+def test_no_reference_labels_and_single_position():
+    """Every reference-sample label ignored -> divergence exactly 0 and no reference-sample gradient (the reference sums an
+    all-masked tensor); T = 2 leaves one predicting position per sequence."""
+    t, _ = _synth()
+    t = dict(t)
+    t["labels_ref"] = torch.full_like(t["labels_ref"], -100)
+    c = _run_cuda(t)
+    o = _oracle(t, "bf16")
+    assert c["div"] == 0.0 and o["div"] == 0.0 and _close(c["loss"], o["loss"], TOL_LOSS_BF16)
+    assert not c["dH_ref"].any() and rel(c["dH_pair"], o["dH_pair"]) <= TOL_GRAD_BF16
+    g = torch.Generator(device="cuda").manual_seed(0)
+    rn = lambda *s: torch.randn(*s, generator=g, device="cuda")
+    W2 = (0.05 * rn(200, 64)).to(torch.bfloat16)
+    t2 = dict(h_pair=rn(4, 2, 64).to(torch.bfloat16), h_ref_pol=rn(2, 2, 64).to(torch.bfloat16), h_ref_frz=rn(2, 2, 64).to(torch.bfloat16),
+              labels_pair=torch.tensor([[-100, 5], [-100, 6], [-100, 7], [-100, 8]], device="cuda"),
+              # one phrase token per half; the other sequence carries sign 0, else the smallest id (1) would be the one dropped
+              signs_pair=torch.tensor([[0, 1], [0, 0], [0, 1], [0, 0]], device="cuda"),
+              labels_ref=torch.tensor([[-100, 3], [-100, -100]], device="cuda"), W=W2, W_ref=W2, alpha=0.4)
+    c, o = _run_cuda(t2), _oracle(t2, "bf16")
+    assert _close(c["loss"], o["loss"], TOL_LOSS_BF16) and rel(c["dW"], o["dW"]) <= TOL_GRAD_BF16
 
 
 def test_int32_labels_and_frozen_head():
