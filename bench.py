@@ -265,7 +265,7 @@ def run_ours(args):
         step()
     barrier()
 
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local) if rank == 0 and not os.environ.get("BENCH_NO_SAMPLER") else None
     if sampler:
         sampler.start()
     _lib.profile_enable(True)
@@ -285,6 +285,49 @@ def run_ours(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = tt.item()
     loss_val = loss.item()
+    ms_eager = ms
+
+    # ---- the same K steps replayed from a CUDA graph: the path is stream-ordered with no host sync (row counts live on
+    #      the device), so one capture removes the ~65 launch gaps of a step.  Falls back to the eager timing on any error.
+    graph_info = dict(used=False)
+    del loss                      # an alive loss keeps the leaves' AccumulateGrad nodes bound to the default stream,
+    import gc                     # which a capture on a side stream must not touch
+    gc.collect()
+    if args.graph and world == 1:      # opt-in, single process only: NCCL collectives must not be captured here
+        try:
+            cap_stream = torch.cuda.Stream(device=dev)
+            cap_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(cap_stream):
+                step()
+            torch.cuda.current_stream().wait_stream(cap_stream)
+            barrier()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                loss_g, _, _ = step()
+            for _ in range(2):
+                g.replay()
+            barrier()
+            e0.record()
+            for _ in range(args.steps):
+                g.replay()
+            e1.record()
+            barrier()
+            ms_g = e0.elapsed_time(e1)
+            if world > 1:
+                tt = torch.tensor([ms_g], device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                ms_g = tt.item()
+            lg = loss_g.item()
+            if abs(lg - loss_val) > 1e-6 * abs(loss_val):
+                raise RuntimeError(f"graph replay loss {lg} != eager loss {loss_val}")
+            graph_info = dict(used=True, ms_per_step_eager=ms_eager / args.steps, ms_per_step_graph=ms_g / args.steps)
+            ms = ms_g
+        except Exception as e:  # noqa: BLE001
+            graph_info = dict(used=False, error=repr(e)[:200])
+            if os.environ.get("BENCH_DEBUG"):
+                import traceback
+                traceback.print_exc()
+            torch.cuda.synchronize()
 
     # ---- variant: lm_head frozen (the shipped LoRA recipe, /root/reference/llava/train/train_halva.py:167-168): no dW
     ms_frozen = None
@@ -374,7 +417,7 @@ def run_ours(args):
                     if peaks.get("bf16_tflops_sustained") else None,
                     flops_per_launch=exec_flops[dom] / n_launch_dom, ms_per_launch=round(dom_ms_launch, 4),
                     launches_with_rows_per_step=n_launch_dom,
-                    share_of_step=round(kernels[dom]["ms_per_step"] / ms_step, 3),
+                    share_of_step=round(kernels[dom]["ms_per_step"] / (ms_eager / K), 3),
                     note="FLOPs executed by this kernel for the rows it processed (row compaction: only rows with a non-zero "
                          "contribution are run). Whole-step figures: step_tc_frac_*")
     e2e_ms_step = ms_e2e / K if ms_e2e else None
@@ -392,7 +435,7 @@ def run_ours(args):
                 step_tc_frac_dense_alg=round(f_alg_dense / (ms_step * 1e-3) / 1e12 / peaks["bf16_tflops"], 4),
                 step_tc_frac_active_alg=round(f_alg_active / (ms_step * 1e-3) / 1e12 / peaks["bf16_tflops"], 4),
                 step_tc_frac_executed=round(sum(exec_flops.values()) / (ms_step * 1e-3) / 1e12 / peaks["bf16_tflops"], 4),
-                gemm_share_of_step=round(gemm_ms / ms_step, 3), loss=loss_val)
+                gemm_share_of_step=round(gemm_ms / (ms_eager / K), 3), loss=loss_val, cuda_graph=graph_info)
     if ms_frozen:
         line["variants"] = dict(lm_head_frozen=dict(ms_per_step=ms_frozen, value=tokens_step / (ms_frozen * 1e-3), unit=UNIT,
                                                     note="same batch, lm_head not trainable (LoRA recipe): no dW GEMM"))
@@ -424,6 +467,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the lm_head-frozen variant timing")
     ap.add_argument("--e2e-full-copy", action="store_true", help="e2e: copy every hidden row, not only contributing spans")
+    ap.add_argument("--graph", action="store_true", help="(1 GPU) also time the K steps as CUDA-graph replays and report that")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end loop (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
