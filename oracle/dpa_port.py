@@ -63,4 +63,4 @@ def step_cpu(inputs, need_dW=True):
     loss, align, div = dpa_loss_torch(hp, inputs["labels_pair"], inputs["signs_pair"], hr, inputs["h_ref_frz"],
                                       inputs["labels_ref"], W, W_ref, inputs["alpha"])
     loss.backward()
-    return dict(loss=float(loss), align=float(align), div=float(div), dH_pair=hp.grad, dH_ref=hr.grad, dW=W.grad)
+    return dict(loss=loss.item(), align=align.item(), div=div.item(), dH_pair=hp.grad, dH_ref=hr.grad, dW=W.grad)
