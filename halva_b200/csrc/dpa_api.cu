@@ -343,39 +343,6 @@ int run_norm_backward(const dpa_args_t* a, const Layout& L, const DeviceInfo* d,
   return DPA_OK;
 }
 
-template <bool ROUND>
-int run_forward_gemms(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, cudaStream_t st) {
-  const dpa_shape_t& s = a->shape;
-  const int cap_tot = L.cap_pair + L.cap_ref;
-  CUtensorMap tmHp, tmHpD, tmHf, tmW256, tmW128, tmWr128, tmW64, tmWr64;
-  int rc;
-  if ((rc = make_operand_tmap(d, &tmW64, a->W, KMAJOR, s.V_local, s.H, s.H, 64))) return rc;
-  if ((rc = make_operand_tmap(d, &tmWr64, a->W_ref, KMAJOR, s.V_local, s.H, s.H, 64))) return rc;
-  if ((rc = make_operand_tmap(d, &tmHp, at<char>(a->scratch, L.f_Hp), KMAJOR, cap_tot, s.H, s.H, BM))) return rc;
-  if ((rc = make_operand_tmap(d, &tmHf, at<char>(a->scratch, L.f_Hf), KMAJOR, L.cap_ref, s.H, s.H, BM))) return rc;
-  if ((rc = make_operand_tmap(d, &tmW256, a->W, KMAJOR, s.V_local, s.H, s.H, kBnPair))) return rc;
-  if ((rc = make_operand_tmap(d, &tmW128, a->W, KMAJOR, s.V_local, s.H, s.H, kBnRef))) return rc;
-  if ((rc = make_operand_tmap(d, &tmWr128, a->W_ref, KMAJOR, s.V_local, s.H, s.H, kBnRef))) return rc;
-  tmHpD = tmHp;
-  const DpaMeta* meta = at<DpaMeta>(a->state, L.meta);
-  {
-    using Epi = EpiStatsPair<kBnPair, ROUND>;
-    GemmWork w{meta, KIND_FWD_PAIR, 0, 0, 0, s.V_local, s.H, kTpuPair};
-    typename Epi::Params ep{at<int>(a->state, L.lab_pair), at<float4>(a->scratch, L.f_part_pair), L.cap_pair, s.V_local, s.v_offset,
-                            nullptr, 0, 0};
-    ProfScope ps(PK_FWD_PAIR, 1, st);
-    if ((rc = launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHp, tmW256, tmW128, w, ep, "fwd_pair"))) return rc;
-  }
-  {
-    using Epi = EpiStatsRef<kBnRef, ROUND>;
-    GemmWork w{meta, KIND_FWD_REF, 0, 0, 0, s.V_local, s.H, kTpuRef};
-    typename Epi::Params ep{at<float4>(a->scratch, L.f_part_ref), at<float>(a->scratch, L.f_part_u), L.cap_ref, s.V_local};
-    ProfScope ps(PK_FWD_REF, 1, st);
-    if ((rc = launch_dual<Epi>(st, d, tmHpD, tmHf, tmW128, tmWr128, tmW64, tmWr64, w, ep, "fwd_ref"))) return rc;
-  }
-  return DPA_OK;
-}
-
 int run_merge(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, const float4* part_pair, const float4* part_ref,
               const float* part_u, int n_pair, int n_ref, size_t stride_pair, size_t stride_ref, size_t stride_u, cudaStream_t st,
               RowRange rr = RowRange{SEG_ALL, 0, 0});
@@ -494,6 +461,152 @@ int run_meta(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, cudaStre
   return DPA_OK;
 }
 
+int check_grad_outputs(const dpa_args_t* a) {
+  if (!a->dH_pair || !a->dH_ref) return fail(DPA_ERR_ARG, "dH_pair/dH_ref is NULL");
+  if ((a->shape.flags & DPA_FLAG_NEED_DW) && !a->dW) return fail(DPA_ERR_ARG, "DPA_FLAG_NEED_DW set but dW is NULL");
+  if (!aligned16(a->dH_pair) || !aligned16(a->dH_ref) || (a->dW && !aligned16(a->dW))) return fail(DPA_ERR_ALIGN, "gradient buffers must be 16-byte aligned");
+  return DPA_OK;
+}
+
+// ---------------------------------------------------------------------------------- one call's GEMM plan
+// Tensor maps over the packed operands of this call and one method per GEMM class.  `scratch` offsets differ between
+// the forward / backward / fused-forward layouts, everything else is shared.
+struct Plan {
+  const dpa_args_t* a; const Layout& L; const DeviceInfo* d; cudaStream_t st;
+  const dpa_shape_t& s;
+  const DpaMeta* meta;
+  __nv_bfloat16* dz = nullptr; __nv_bfloat16* zr = nullptr; float* dW32 = nullptr;
+  float4* part_pair = nullptr; float4* part_ref = nullptr; float* part_u = nullptr;
+  CUtensorMap tmHp, tmHf, tmW256, tmW128, tmW64, tmWr256, tmWr128, tmWr64, tmDzK, tmWmn, tmDzMN, tmHpMN;
+
+  Plan(const dpa_args_t* a_, const Layout& L_, const DeviceInfo* d_, cudaStream_t st_)
+      : a(a_), L(L_), d(d_), st(st_), s(a_->shape), meta(at<DpaMeta>(a_->state, L_.meta)) {}
+
+  int init(size_t oHp, size_t oHf, size_t oPartPair, size_t oPartRef, size_t oPartU, bool has_parts, __nv_bfloat16* dz_, __nv_bfloat16* zr_,
+           float* dW32_) {
+    const int cap_tot = L.cap_pair + L.cap_ref;
+    dz = dz_; zr = zr_; dW32 = dW32_;
+    if (has_parts) {
+      part_pair = at<float4>(a->scratch, oPartPair); part_ref = at<float4>(a->scratch, oPartRef); part_u = at<float>(a->scratch, oPartU);
+    }
+    int rc;
+    char* Hp = at<char>(a->scratch, oHp);
+    if ((rc = make_operand_tmap(d, &tmHp, Hp, KMAJOR, cap_tot, s.H, s.H, BM))) return rc;
+    if ((rc = make_operand_tmap(d, &tmHf, at<char>(a->scratch, oHf), KMAJOR, L.cap_ref, s.H, s.H, BM))) return rc;
+    // lm_head rows as the K-major B operand: boxes of 256 (single CTA), 128 (CTA pair / dual single CTA), 64 (dual pair)
+    if ((rc = make_operand_tmap(d, &tmW256, a->W, KMAJOR, s.V_local, s.H, s.H, 256))) return rc;
+    if ((rc = make_operand_tmap(d, &tmW128, a->W, KMAJOR, s.V_local, s.H, s.H, 128))) return rc;
+    if ((rc = make_operand_tmap(d, &tmW64, a->W, KMAJOR, s.V_local, s.H, s.H, 64))) return rc;
+    if ((rc = make_operand_tmap(d, &tmWr256, a->W_ref, KMAJOR, s.V_local, s.H, s.H, 256))) return rc;
+    if ((rc = make_operand_tmap(d, &tmWr128, a->W_ref, KMAJOR, s.V_local, s.H, s.H, 128))) return rc;
+    if ((rc = make_operand_tmap(d, &tmWr64, a->W_ref, KMAJOR, s.V_local, s.H, s.H, 64))) return rc;
+    if (dz) {
+      // dH = dZ[rows x V] * W[V x H]:      A = dz K-major (K = vocab),  B = W MN-major (N = hidden contiguous)
+      // dW = dZ^T[V x rows] * H[rows x H]: A = dz MN-major (M = vocab), B = packed hidden rows MN-major
+      if ((rc = make_operand_tmap(d, &tmDzK, dz, KMAJOR, L.chunk_rows, s.V_local, L.ldz, BM))) return rc;
+      if ((rc = make_operand_tmap(d, &tmWmn, a->W, MNMAJOR, s.H, s.V_local, s.H, 0))) return rc;
+      if ((rc = make_operand_tmap(d, &tmDzMN, dz, MNMAJOR, s.V_local, L.chunk_rows, L.ldz, 0))) return rc;
+      if ((rc = make_operand_tmap(d, &tmHpMN, Hp, MNMAJOR, s.H, cap_tot, s.H, 0))) return rc;
+    }
+    return DPA_OK;
+  }
+
+  // statistics of every pair row; store_rows > 0 also keeps the bf16 logits of the first store_rows packed rows in dz
+  template <bool ROUND> int fwd_pair(int store_rows) {
+    using Epi = EpiStatsPair<kBnPair, ROUND>;
+    GemmWork w{meta, KIND_FWD_PAIR, 0, 0, 0, s.V_local, s.H, kTpuPair};
+    typename Epi::Params ep{at<int>(a->state, L.lab_pair), part_pair, L.cap_pair, s.V_local, s.v_offset,
+                            store_rows > 0 ? dz : nullptr, L.ldz, store_rows};
+    ProfScope ps(PK_FWD_PAIR, 1, st);
+    return launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHp, tmW256, tmW128, w, ep, "fwd_pair");
+  }
+  // policy + frozen logits of every reference-sample row side by side: statistics incl. the KL numerator
+  template <bool ROUND> int fwd_ref() {
+    using Epi = EpiStatsRef<kBnRef, ROUND>;
+    GemmWork w{meta, KIND_FWD_REF, 0, 0, 0, s.V_local, s.H, kTpuRef};
+    typename Epi::Params ep{part_ref, part_u, L.cap_ref, s.V_local};
+    ProfScope ps(PK_FWD_REF, 1, st);
+    return launch_dual<Epi>(st, d, tmHp, tmHf, tmW128, tmWr128, tmW64, tmWr64, w, ep, "fwd_ref");
+  }
+  // recompute the pair rows of chunk ch -> dz
+  template <bool ROUND> int dz_pair(int ch) {
+    using Epi = EpiDzPair<kBnPair, ROUND>;
+    GemmWork w{meta, KIND_DZ_PAIR, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair};
+    typename Epi::Params ep{at<int>(a->state, L.lab_pair), at<float>(a->state, L.lse_pair), at<float>(a->state, L.coef_pair),
+                            dz, L.ldz, ch * L.chunk_rows, s.V_local, s.v_offset};
+    ProfScope ps(PK_DZ_PAIR, 1, st);
+    return launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHp, tmW256, tmW128, w, ep, "dz_pair");
+  }
+  // recompute the reference-sample rows of chunk ch (both models) -> dz
+  template <bool ROUND> int dz_ref(int ch) {
+    using Epi = EpiDzRef<kBnRef, ROUND>;
+    GemmWork w{meta, KIND_DZ_REF, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuRef};
+    typename Epi::Params ep{meta, at<float>(a->state, L.lse_ref_p), at<float>(a->state, L.lse_ref_r), at<float>(a->state, L.coef_ref),
+                            dz, L.ldz, ch * L.chunk_rows, s.V_local};
+    ProfScope ps(PK_DZ_REF, 1, st);
+    return launch_dual<Epi>(st, d, tmHp, tmHf, tmW128, tmWr128, tmW64, tmWr64, w, ep, "dz_ref");
+  }
+  // fused-gradient forward: policy and frozen logits of chunk ch's reference-sample rows: statistics + the bf16 logits
+  int stash_ref(int ch) {
+    using Epi = EpiStatsStore<256>;
+    float2* part2 = reinterpret_cast<float2*>(part_ref);
+    ProfScope ps(PK_STASH_REF, 2, st);
+    GemmWork wp{meta, KIND_STASH_POL, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair};
+    typename Epi::Params epp{meta, part2, dz, L.cap_ref, s.V_local, L.ldz, ch * L.chunk_rows, 0};
+    int rc = launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHp, tmW256, tmW128, wp, epp, "stash_pol");
+    if (rc) return rc;
+    GemmWork wf{meta, KIND_STASH_FRZ, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair};
+    typename Epi::Params epf{meta, part2, zr, L.cap_ref, s.V_local, L.ldz, ch * L.chunk_rows, 1};
+    return launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHf, tmWr256, tmWr128, wf, epf, "stash_frz");
+  }
+  // dH = dz W (rows scattered to their [s,t] positions) and, if lm_head is trainable, dW += dz^T H for chunk ch
+  int grad_gemms(int ch) {
+    {
+      using Epi = EpiStoreRows<256>;
+      GemmWork w{meta, KIND_DH, ch, L.chunk_rows, 0, s.H, s.V_local, 1};
+      typename Epi::Params ep{meta, at<int>(a->state, L.src_pair), at<int>(a->state, L.src_ref),
+                              static_cast<__nv_bfloat16*>(a->dH_pair), static_cast<__nv_bfloat16*>(a->dH_ref), s.H};
+      ProfScope ps(PK_DH, 1, st);
+      int rc = launch_single<Epi, KMAJOR, MNMAJOR>(st, d, tmDzK, tmWmn, tmWmn, w, ep, "dH");
+      if (rc) return rc;
+    }
+    if (dW32) {
+      using Epi = EpiAccumF32<256>;
+      GemmWork w{meta, KIND_DW, ch, L.chunk_rows, s.V_local, s.H, 0, 1};
+      typename Epi::Params ep{dW32, s.H, s.V_local, s.H, 1};
+      ProfScope ps(PK_DW, 1, st);
+      return launch_single<Epi, MNMAJOR, MNMAJOR>(st, d, tmDzMN, tmHpMN, tmHpMN, w, ep, "dW");
+    }
+    return DPA_OK;
+  }
+  int zero_grad_outputs() {
+    ProfScope ps(PK_MISC, 0, st);
+    CUDA_TRY(cudaMemsetAsync(a->dH_pair, 0, (size_t)2 * s.B * s.T * s.H * 2, st));
+    CUDA_TRY(cudaMemsetAsync(a->dH_ref, 0, (size_t)s.B_ref * s.T_ref * s.H * 2, st));
+    if (dW32) CUDA_TRY(cudaMemsetAsync(dW32, 0, (size_t)s.V_local * s.H * 4, st));
+    return DPA_OK;
+  }
+  int finish_dW() {
+    if (!dW32) return DPA_OK;
+    ProfScope ps(PK_MISC, 1, st);
+    f32_to_bf16_kernel<<<d->sms * 8, 256, 0, st>>>(dW32, static_cast<__nv_bfloat16*>(a->dW), (size_t)s.V_local * s.H);
+    LAUNCH_CHECK("dW convert");
+    return DPA_OK;
+  }
+  int coef(const float* d_loss) {
+    CoefArgs c{meta, at<int>(a->state, L.col_pair), at<int>(a->state, L.act_ref), at<float>(a->state, L.sigma), d_loss,
+               at<float>(a->state, L.coef_pair), at<float>(a->state, L.coef_ref), s.B, s.B_ref, a->alpha};
+    ProfScope ps(PK_COEF, 1, st);
+    coef_kernel<<<d->sms * 2, 256, 0, st>>>(c);
+    LAUNCH_CHECK("coef");
+    return DPA_OK;
+  }
+  int merge(RowRange rr, bool with_u) {
+    return run_merge(a, L, d, part_pair, part_ref, with_u ? part_u : nullptr, L.ng_pair, L.ng_ref, L.cap_pair, L.cap_ref, L.cap_ref, st, rr);
+  }
+};
+
+// ---------------------------------------------------------------------------------- statistics-only forward
 int forward_stats_impl(const dpa_args_t* a, cudaStream_t st, Layout& L, DeviceInfo** dev) {
   int rc = check_common(a, L, dev);
   if (rc) return rc;
@@ -502,24 +615,20 @@ int forward_stats_impl(const dpa_args_t* a, cudaStream_t st, Layout& L, DeviceIn
   if (!a->losses || !a->status) return fail(DPA_ERR_ARG, "losses/status is NULL");
   if ((rc = run_meta(a, L, d, st))) return rc;
   if ((rc = run_gather(a, L, d, a->scratch, L.f_Hp, L.f_Hf, st))) return rc;
-  rc = (a->shape.flags & DPA_FLAG_ROUND_LOGITS) ? run_forward_gemms<true>(a, L, d, st) : run_forward_gemms<false>(a, L, d, st);
-  if (rc) return rc;
-  return run_merge(a, L, d, at<float4>(a->scratch, L.f_part_pair), at<float4>(a->scratch, L.f_part_ref),
-                   at<float>(a->scratch, L.f_part_u), L.ng_pair, L.ng_ref, L.cap_pair, L.cap_ref, L.cap_ref, st);
-}
-
-int check_grad_outputs(const dpa_args_t* a) {
-  if (!a->dH_pair || !a->dH_ref) return fail(DPA_ERR_ARG, "dH_pair/dH_ref is NULL");
-  if ((a->shape.flags & DPA_FLAG_NEED_DW) && !a->dW) return fail(DPA_ERR_ARG, "DPA_FLAG_NEED_DW set but dW is NULL");
-  if (!aligned16(a->dH_pair) || !aligned16(a->dH_ref) || (a->dW && !aligned16(a->dW))) return fail(DPA_ERR_ALIGN, "gradient buffers must be 16-byte aligned");
-  return DPA_OK;
+  Plan p(a, L, d, st);
+  if ((rc = p.init(L.f_Hp, L.f_Hf, L.f_part_pair, L.f_part_ref, L.f_part_u, true, nullptr, nullptr, nullptr))) return rc;
+  const bool round = (a->shape.flags & DPA_FLAG_ROUND_LOGITS) != 0;
+  if ((rc = round ? p.fwd_pair<true>(0) : p.fwd_pair<false>(0))) return rc;
+  if ((rc = round ? p.fwd_ref<true>() : p.fwd_ref<false>())) return rc;
+  return p.merge(RowRange{SEG_ALL, 0, 0}, true);
 }
 
 // ---------------------------------------------------------------------------------- fused-gradient forward
-// Loss AND gradients (for d_loss = 1) in one pass; dpa_backward then only scales.  Pair rows: statistics GEMM, then
-// the recompute GEMM writes dz once sigma is known (they are few).  Reference-sample rows, chunk by chunk: ONE dual
-// GEMM produces the statistics and keeps the chunk's bf16 logits, an elementwise pass turns them into dz in place.
-// Every chunk ends with dH = dz W and dW += dz^T H.  Per row that is 3 (pair: 4) GEMM units instead of 6 (4).
+// Loss AND gradients (for d_loss = 1) in one pass; dpa_backward then only scales.  Pair rows: the statistics GEMM keeps
+// the bf16 logits of the pair rows of row chunk 0 and an elementwise pass turns them into dz once sigma is known (pair
+// rows beyond chunk 0 are recomputed).  Reference-sample rows, chunk by chunk: two GEMMs produce the statistics and
+// keep the chunk's bf16 logits of both models, an elementwise pass turns them into dz and the KL rows.  Every chunk
+// ends with dH = dz W and dW += dz^T H.  Executed GEMM units per row = the algorithmic count (pair 3, reference 4).
 int forward_fused_impl(const dpa_args_t* a, cudaStream_t st) {
   Layout L; DeviceInfo* d;
   int rc = check_common(a, L, &d);
@@ -529,122 +638,48 @@ int forward_fused_impl(const dpa_args_t* a, cudaStream_t st) {
   if (!a->scratch || a->scratch_bytes < L.fused_total) return fail(DPA_ERR_WORKSPACE, "fused scratch: need %zu bytes, got %zu", L.fused_total, a->scratch_bytes);
   if (!a->losses || !a->status) return fail(DPA_ERR_ARG, "losses/status is NULL");
   if ((rc = check_grad_outputs(a))) return rc;
-  const bool need_dw = (s.flags & DPA_FLAG_NEED_DW) != 0;
-  const int cap_tot = L.cap_pair + L.cap_ref;
-  const DpaMeta* meta = at<DpaMeta>(a->state, L.meta);
-  __nv_bfloat16* dz = at<__nv_bfloat16>(a->scratch, L.u_dz);
-  __nv_bfloat16* zr = at<__nv_bfloat16>(a->scratch, L.u_zr);
-  float* dW32 = need_dw ? at<float>(a->scratch, L.u_dW32) : nullptr;
+  Plan p(a, L, d, st);
+  if ((rc = p.init(L.u_Hp, L.u_Hf, L.u_part_pair, L.u_part_ref, L.u_part_u, true, at<__nv_bfloat16>(a->scratch, L.u_dz),
+                   at<__nv_bfloat16>(a->scratch, L.u_zr), (s.flags & DPA_FLAG_NEED_DW) ? at<float>(a->scratch, L.u_dW32) : nullptr))) return rc;
 
   if ((rc = run_meta(a, L, d, st))) return rc;
   if ((rc = run_gather(a, L, d, a->scratch, L.u_Hp, L.u_Hf, st))) return rc;
-  {
-    ProfScope ps(PK_MISC, 0, st);
-    CUDA_TRY(cudaMemsetAsync(a->dH_pair, 0, (size_t)2 * s.B * s.T * s.H * 2, st));
-    CUDA_TRY(cudaMemsetAsync(a->dH_ref, 0, (size_t)s.B_ref * s.T_ref * s.H * 2, st));
-    if (need_dw) CUDA_TRY(cudaMemsetAsync(dW32, 0, (size_t)s.V_local * s.H * 4, st));
-  }
-
-  CUtensorMap tmHp, tmHf, tmW256, tmW128, tmWr128, tmWr256, tmDzK, tmWmn, tmDzMN, tmHpMN;
-  if ((rc = make_operand_tmap(d, &tmHp, at<char>(a->scratch, L.u_Hp), KMAJOR, cap_tot, s.H, s.H, BM))) return rc;
-  if ((rc = make_operand_tmap(d, &tmHf, at<char>(a->scratch, L.u_Hf), KMAJOR, L.cap_ref, s.H, s.H, BM))) return rc;
-  if ((rc = make_operand_tmap(d, &tmW256, a->W, KMAJOR, s.V_local, s.H, s.H, kBnPair))) return rc;
-  if ((rc = make_operand_tmap(d, &tmW128, a->W, KMAJOR, s.V_local, s.H, s.H, kBnRef))) return rc;
-  if ((rc = make_operand_tmap(d, &tmWr128, a->W_ref, KMAJOR, s.V_local, s.H, s.H, kBnRef))) return rc;
-  if ((rc = make_operand_tmap(d, &tmWr256, a->W_ref, KMAJOR, s.V_local, s.H, s.H, kBnPair))) return rc;
-  if ((rc = make_operand_tmap(d, &tmDzK, dz, KMAJOR, L.chunk_rows, s.V_local, L.ldz, BM))) return rc;
-  if ((rc = make_operand_tmap(d, &tmWmn, a->W, MNMAJOR, s.H, s.V_local, s.H, 0))) return rc;
-  if ((rc = make_operand_tmap(d, &tmDzMN, dz, MNMAJOR, s.V_local, L.chunk_rows, L.ldz, 0))) return rc;
-  if ((rc = make_operand_tmap(d, &tmHpMN, at<char>(a->scratch, L.u_Hp), MNMAJOR, s.H, cap_tot, s.H, 0))) return rc;
+  if ((rc = p.zero_grad_outputs())) return rc;
 
   // ---- alignment half: statistics of every pair row -> P, N -> sigma, alignment loss -> row coefficients
-  {
-    using Epi = EpiStatsPair<kBnPair, true>;
-    GemmWork w{meta, KIND_FWD_PAIR, 0, 0, 0, s.V_local, s.H, kTpuPair};
-    // pair rows that fall into row chunk 0 keep their logits in the chunk's dz buffer (nothing else touches it until then)
-    typename Epi::Params ep{at<int>(a->state, L.lab_pair), at<float4>(a->scratch, L.u_part_pair), L.cap_pair, s.V_local, s.v_offset,
-                            dz, L.ldz, L.chunk_rows};
-    ProfScope ps(PK_FWD_PAIR, 1, st);
-    if ((rc = launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHp, tmW256, tmW128, w, ep, "fwd_pair"))) return rc;
-  }
-  const float4* part_pair = at<float4>(a->scratch, L.u_part_pair);
-  const float4* part_ref = at<float4>(a->scratch, L.u_part_ref);
-  const float* part_u = at<float>(a->scratch, L.u_part_u);
-  if ((rc = run_merge(a, L, d, part_pair, part_ref, part_u, L.ng_pair, L.ng_ref, L.cap_pair, L.cap_ref, L.cap_ref, st,
-                      RowRange{SEG_PAIR, 0, 0}))) return rc;
+  if ((rc = p.fwd_pair<true>(L.chunk_rows))) return rc;       // nothing else touches chunk 0's dz buffer until its turn
+  if ((rc = p.merge(RowRange{SEG_PAIR, 0, 0}, true))) return rc;
   if ((rc = run_finish_rows(a, L, d, st, RowRange{SEG_PAIR, 0, 0}))) return rc;
   if ((rc = run_losses(a, L, st, LOSS_ALIGN))) return rc;
-  {
-    CoefArgs c{meta, at<int>(a->state, L.col_pair), at<int>(a->state, L.act_ref), at<float>(a->state, L.sigma), nullptr /* d_loss = 1 */,
-               at<float>(a->state, L.coef_pair), at<float>(a->state, L.coef_ref), s.B, s.B_ref, a->alpha};
-    ProfScope ps(PK_COEF, 1, st);
-    coef_kernel<<<d->sms * 2, 256, 0, st>>>(c);
-    LAUNCH_CHECK("coef");
-  }
+  if ((rc = p.coef(nullptr /* d_loss = 1 */))) return rc;
 
   // ---- row chunks of the packed space [pair rows | reference-sample rows]
   for (int ch = 0; ch < L.n_chunks; ++ch) {
     if (ch == 0) {
-      DzPairElemArgs e{meta, L.chunk_rows, dz, L.ldz, s.V_local, s.v_offset, at<int>(a->state, L.lab_pair),
+      DzPairElemArgs e{p.meta, L.chunk_rows, p.dz, L.ldz, s.V_local, s.v_offset, at<int>(a->state, L.lab_pair),
                        at<float>(a->state, L.lse_pair), at<float>(a->state, L.coef_pair)};
       ProfScope ps(PK_DZ_ELEM, 1, st);
       dz_pair_elem_kernel<<<d->sms * 8, 256, 0, st>>>(e);
       LAUNCH_CHECK("dz_pair_elem");
     } else if ((long long)ch * L.chunk_rows < L.cap_pair) {      // pair rows beyond chunk 0 (if any): recompute
-      using Epi = EpiDzPair<kBnPair, true>;
-      GemmWork w{meta, KIND_DZ_PAIR, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair};
-      typename Epi::Params ep{at<int>(a->state, L.lab_pair), at<float>(a->state, L.lse_pair), at<float>(a->state, L.coef_pair),
-                              dz, L.ldz, ch * L.chunk_rows, s.V_local, s.v_offset};
-      ProfScope ps(PK_DZ_PAIR, 1, st);
-      if ((rc = launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHp, tmW256, tmW128, w, ep, "dz_pair"))) return rc;
+      if ((rc = p.dz_pair<true>(ch))) return rc;
     }
-    {
-      // policy and frozen-model logits of the chunk's reference-sample rows: statistics + the bf16 logits themselves
-      using Epi = EpiStatsStore<256>;
-      float2* part2 = reinterpret_cast<float2*>(at<float4>(a->scratch, L.u_part_ref));
-      ProfScope ps(PK_STASH_REF, 2, st);
-      GemmWork wp{meta, KIND_STASH_POL, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair};
-      typename Epi::Params epp{meta, part2, dz, L.cap_ref, s.V_local, L.ldz, ch * L.chunk_rows, 0};
-      if ((rc = launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHp, tmW256, tmW128, wp, epp, "stash_pol"))) return rc;
-      GemmWork wf{meta, KIND_STASH_FRZ, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair};
-      typename Epi::Params epf{meta, part2, zr, L.cap_ref, s.V_local, L.ldz, ch * L.chunk_rows, 1};
-      if ((rc = launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHf, tmWr256, tmWr128, wf, epf, "stash_frz"))) return rc;
-    }
+    if ((rc = p.stash_ref(ch))) return rc;
     const RowRange rr{SEG_REF_CHUNK, ch, L.chunk_rows};
-    if ((rc = run_merge(a, L, d, part_pair, part_ref, nullptr, L.ng_pair, L.ng_ref, L.cap_pair, L.cap_ref, L.cap_ref, st, rr))) return rc;
+    if ((rc = p.merge(rr, false))) return rc;
     if ((rc = run_finish_rows(a, L, d, st, rr, /*kl_from_stats=*/false))) return rc;
     {
-      DzElemArgs e{meta, ch, L.chunk_rows, dz, zr, L.ldz, s.V_local, at<float>(a->state, L.lse_ref_p), at<float>(a->state, L.lse_ref_r),
+      DzElemArgs e{p.meta, ch, L.chunk_rows, p.dz, p.zr, L.ldz, s.V_local, at<float>(a->state, L.lse_ref_p), at<float>(a->state, L.lse_ref_r),
                    at<float>(a->state, L.coef_ref), at<int>(a->state, L.act_ref), at<float>(a->state, L.kl_row)};
       ProfScope ps(PK_DZ_ELEM, 1, st);
       dz_kl_elem_kernel<<<d->sms * 8, 256, 0, st>>>(e);
       LAUNCH_CHECK("dz_kl_elem");
     }
-    {
-      using Epi = EpiStoreRows<256>;
-      GemmWork w{meta, KIND_DH, ch, L.chunk_rows, 0, s.H, s.V_local, 1};
-      typename Epi::Params ep{meta, at<int>(a->state, L.src_pair), at<int>(a->state, L.src_ref),
-                              static_cast<__nv_bfloat16*>(a->dH_pair), static_cast<__nv_bfloat16*>(a->dH_ref), s.H};
-      ProfScope ps(PK_DH, 1, st);
-      if ((rc = launch_single<Epi, KMAJOR, MNMAJOR>(st, d, tmDzK, tmWmn, tmWmn, w, ep, "dH"))) return rc;
-    }
-    if (need_dw) {
-      using Epi = EpiAccumF32<256>;
-      GemmWork w{meta, KIND_DW, ch, L.chunk_rows, s.V_local, s.H, 0, 1};
-      typename Epi::Params ep{dW32, s.H, s.V_local, s.H, 1};
-      ProfScope ps(PK_DW, 1, st);
-      if ((rc = launch_single<Epi, MNMAJOR, MNMAJOR>(st, d, tmDzMN, tmHpMN, tmHpMN, w, ep, "dW"))) return rc;
-    }
+    if ((rc = p.grad_gemms(ch))) return rc;
   }
   if ((rc = run_losses(a, L, st, LOSS_TOTAL))) return rc;
   if ((rc = run_norm_backward(a, L, d, st))) return rc;
-  if (need_dw) {
-    const size_t n = (size_t)s.V_local * s.H;
-    ProfScope ps(PK_MISC, 1, st);
-    f32_to_bf16_kernel<<<d->sms * 8, 256, 0, st>>>(dW32, static_cast<__nv_bfloat16*>(a->dW), n);
-    LAUNCH_CHECK("dW convert");
-  }
-  return DPA_OK;
+  return p.finish_dW();
 }
 
 // fused-gradient backward: scale what the forward left in dH_pair / dH_ref / dW by the upstream gradient
@@ -666,86 +701,25 @@ int backward_scale_impl(const dpa_args_t* a, cudaStream_t st) {
   return DPA_OK;
 }
 
+// ---------------------------------------------------------------------------------- recompute backward
+// The north star's wording: the forward kept O(rows) statistics; the logits are recomputed chunk-wise into dz, then dH / dW.
 template <bool ROUND>
 int run_backward(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, cudaStream_t st) {
   const dpa_shape_t& s = a->shape;
-  const bool need_dw = (s.flags & DPA_FLAG_NEED_DW) != 0;
-  const int cap_tot = L.cap_pair + L.cap_ref;
-  const DpaMeta* meta = at<DpaMeta>(a->state, L.meta);
   int rc;
-  CoefArgs c{meta, at<int>(a->state, L.col_pair), at<int>(a->state, L.act_ref), at<float>(a->state, L.sigma), a->d_loss,
-             at<float>(a->state, L.coef_pair), at<float>(a->state, L.coef_ref), s.B, s.B_ref, a->alpha};
-  {
-    ProfScope ps(PK_COEF, 1, st);
-    coef_kernel<<<d->sms * 2, 256, 0, st>>>(c);
-    LAUNCH_CHECK("coef");
-  }
+  Plan p(a, L, d, st);
+  if ((rc = p.init(L.b_Hp, L.b_Hf, 0, 0, 0, false, at<__nv_bfloat16>(a->scratch, L.b_dz), nullptr,
+                   (s.flags & DPA_FLAG_NEED_DW) ? at<float>(a->scratch, L.b_dW32) : nullptr))) return rc;
+  if ((rc = p.coef(a->d_loss))) return rc;
   if ((rc = run_gather(a, L, d, a->scratch, L.b_Hp, L.b_Hf, st))) return rc;
-  float* dW32 = need_dw ? at<float>(a->scratch, L.b_dW32) : nullptr;
-  {
-    ProfScope ps(PK_MISC, 0, st);
-    CUDA_TRY(cudaMemsetAsync(a->dH_pair, 0, (size_t)2 * s.B * s.T * s.H * 2, st));
-    CUDA_TRY(cudaMemsetAsync(a->dH_ref, 0, (size_t)s.B_ref * s.T_ref * s.H * 2, st));
-    if (need_dw) CUDA_TRY(cudaMemsetAsync(dW32, 0, (size_t)s.V_local * s.H * 4, st));
-  }
-
-  __nv_bfloat16* dz = at<__nv_bfloat16>(a->scratch, L.b_dz);
-  CUtensorMap tmHp, tmHf, tmW256, tmW128, tmWr128, tmW64, tmWr64, tmDzK, tmWmn, tmDzMN, tmHpMN;
-  if ((rc = make_operand_tmap(d, &tmW64, a->W, KMAJOR, s.V_local, s.H, s.H, 64))) return rc;
-  if ((rc = make_operand_tmap(d, &tmWr64, a->W_ref, KMAJOR, s.V_local, s.H, s.H, 64))) return rc;
-  if ((rc = make_operand_tmap(d, &tmHp, at<char>(a->scratch, L.b_Hp), KMAJOR, cap_tot, s.H, s.H, BM))) return rc;
-  if ((rc = make_operand_tmap(d, &tmHf, at<char>(a->scratch, L.b_Hf), KMAJOR, L.cap_ref, s.H, s.H, BM))) return rc;
-  if ((rc = make_operand_tmap(d, &tmW256, a->W, KMAJOR, s.V_local, s.H, s.H, kBnPair))) return rc;
-  if ((rc = make_operand_tmap(d, &tmW128, a->W, KMAJOR, s.V_local, s.H, s.H, kBnRef))) return rc;
-  if ((rc = make_operand_tmap(d, &tmWr128, a->W_ref, KMAJOR, s.V_local, s.H, s.H, kBnRef))) return rc;
-  // dH = dZ[rows x V] * W[V x H]:  A = dz K-major (K = vocab), B = W MN-major (N = hidden contiguous)
-  if ((rc = make_operand_tmap(d, &tmDzK, dz, KMAJOR, L.chunk_rows, s.V_local, L.ldz, BM))) return rc;
-  if ((rc = make_operand_tmap(d, &tmWmn, a->W, MNMAJOR, s.H, s.V_local, s.H, 0))) return rc;
-  // dW = dZ^T[V x rows] * H[rows x H]: A = dz MN-major (M = vocab contiguous), B = packed hidden rows MN-major
-  if ((rc = make_operand_tmap(d, &tmDzMN, dz, MNMAJOR, s.V_local, L.chunk_rows, L.ldz, 0))) return rc;
-  if ((rc = make_operand_tmap(d, &tmHpMN, at<char>(a->scratch, L.b_Hp), MNMAJOR, s.H, cap_tot, s.H, 0))) return rc;
-
+  if ((rc = p.zero_grad_outputs())) return rc;
   for (int ch = 0; ch < L.n_chunks; ++ch) {
-    {
-      using Epi = EpiDzPair<kBnPair, ROUND>;
-      GemmWork w{meta, KIND_DZ_PAIR, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair};
-      typename Epi::Params ep{at<int>(a->state, L.lab_pair), at<float>(a->state, L.lse_pair), at<float>(a->state, L.coef_pair),
-                              dz, L.ldz, ch * L.chunk_rows, s.V_local, s.v_offset};
-      ProfScope ps(PK_DZ_PAIR, 1, st);
-      if ((rc = launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHp, tmW256, tmW128, w, ep, "dz_pair"))) return rc;
-    }
-    {
-      using Epi = EpiDzRef<kBnRef, ROUND>;
-      GemmWork w{meta, KIND_DZ_REF, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuRef};
-      typename Epi::Params ep{meta, at<float>(a->state, L.lse_ref_p), at<float>(a->state, L.lse_ref_r), at<float>(a->state, L.coef_ref),
-                              dz, L.ldz, ch * L.chunk_rows, s.V_local};
-      ProfScope ps(PK_DZ_REF, 1, st);
-      if ((rc = launch_dual<Epi>(st, d, tmHp, tmHf, tmW128, tmWr128, tmW64, tmWr64, w, ep, "dz_ref"))) return rc;
-    }
-    {
-      using Epi = EpiStoreRows<256>;
-      GemmWork w{meta, KIND_DH, ch, L.chunk_rows, 0, s.H, s.V_local, 1};
-      typename Epi::Params ep{meta, at<int>(a->state, L.src_pair), at<int>(a->state, L.src_ref),
-                              static_cast<__nv_bfloat16*>(a->dH_pair), static_cast<__nv_bfloat16*>(a->dH_ref), s.H};
-      ProfScope ps(PK_DH, 1, st);
-      if ((rc = launch_single<Epi, KMAJOR, MNMAJOR>(st, d, tmDzK, tmWmn, tmWmn, w, ep, "dH"))) return rc;
-    }
-    if (need_dw) {
-      using Epi = EpiAccumF32<256>;
-      GemmWork w{meta, KIND_DW, ch, L.chunk_rows, s.V_local, s.H, 0, 1};
-      typename Epi::Params ep{dW32, s.H, s.V_local, s.H, 1};
-      ProfScope ps(PK_DW, 1, st);
-      if ((rc = launch_single<Epi, MNMAJOR, MNMAJOR>(st, d, tmDzMN, tmHpMN, tmHpMN, w, ep, "dW"))) return rc;
-    }
+    if ((long long)ch * L.chunk_rows < L.cap_pair && (rc = p.dz_pair<ROUND>(ch))) return rc;
+    if ((rc = p.dz_ref<ROUND>(ch))) return rc;
+    if ((rc = p.grad_gemms(ch))) return rc;
   }
   if ((rc = run_norm_backward(a, L, d, st))) return rc;
-  if (need_dw) {
-    const size_t n = (size_t)s.V_local * s.H;
-    ProfScope ps(PK_MISC, 1, st);
-    f32_to_bf16_kernel<<<d->sms * 8, 256, 0, st>>>(dW32, static_cast<__nv_bfloat16*>(a->dW), n);
-    LAUNCH_CHECK("dW convert");
-  }
-  return DPA_OK;
+  return p.finish_dW();
 }
 
 }  // namespace
