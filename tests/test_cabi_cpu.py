@@ -50,3 +50,14 @@ def test_python_op_refuses_cpu_tensors():
     y = torch.zeros(2, 8, dtype=torch.int64)
     with pytest.raises(DPAError):
         dpa_loss(h, y, y, h[:1], y[:1], torch.zeros(64, 64, dtype=torch.bfloat16), h_ref_frozen=h[:1], alpha=0.4)
+
+
+def test_missing_library_fails_loudly():
+    """No CPU / PyTorch fallback: without the built library the product path raises at load time."""
+    import subprocess
+    import sys
+    code = ("import os, sys; sys.path.insert(0, %r); os.environ['HALVA_DPA_LIB'] = '/nonexistent/libhalva_dpa.so'\n"
+            "from halva_b200 import _lib\n"
+            "try:\n    _lib.load()\nexcept _lib.DPAError as e:\n    print('RAISED', 'no CPU or PyTorch fallback' in str(e))\n" % ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert out.stdout.strip() == "RAISED True", (out.stdout, out.stderr[-500:])
