@@ -14,7 +14,8 @@ ABI_VERSION = 3
 STATUS_BAD_SIGN, STATUS_K_MISMATCH, STATUS_K_ZERO, STATUS_BAD_LABEL = 1, 2, 4, 8
 EXPORTS = ["dpa_version", "dpa_last_error", "dpa_query_workspace", "dpa_forward", "dpa_backward",
            "dpa_forward_stats", "dpa_forward_finish", "dpa_row_stats_view", "dpa_debug_gemm",
-           "dpa_profile_enable", "dpa_profile_collect", "dpa_profile_kind_name", "dpa_set_cta_group"]
+           "dpa_profile_enable", "dpa_profile_collect", "dpa_profile_kind_name", "dpa_set_cta_group",
+           "dpa_comm_unique_id", "dpa_comm_init", "dpa_comm_destroy", "dpa_comm_world"]
 
 
 class Shape(C.Structure):
@@ -68,6 +69,9 @@ def load():
                                    C.c_int, C.c_void_p]
     lib.dpa_profile_enable.argtypes = [C.c_int]
     lib.dpa_set_cta_group.argtypes = [C.c_int]
+    lib.dpa_comm_unique_id.argtypes = [C.c_void_p]
+    lib.dpa_comm_init.argtypes = [C.c_int, C.c_int, C.c_void_p]
+    lib.dpa_comm_world.restype = C.c_int
     lib.dpa_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]
     lib.dpa_profile_kind_name.argtypes = [C.c_int]
     lib.dpa_profile_kind_name.restype = C.c_char_p

@@ -1,6 +1,7 @@
 // C ABI of libhalva_dpa.so (include/halva_dpa.h): workspace layout, TMA descriptors, launch sequences.
 #include <cstdio>
 #include <cstdlib>
+#include <dlfcn.h>
 #include <cstring>
 #include <cstdarg>
 #include <mutex>
@@ -179,14 +180,16 @@ struct Layout {
       lse_pair, logp_pair, lse_ref_p, lse_ref_r, kl_row, PN, sigma, coef_pair, coef_ref, rinv, dnw32, state_total;
   size_t row_stats_bytes;
   // forward scratch offsets
-  size_t f_Hp, f_Hf, f_part_pair, f_part_ref, f_part_u, fwd_total;
+  size_t f_Hp, f_Hf, f_part_pair, f_part_ref, f_part_u, f_gather, fwd_total;
   // backward scratch offsets
   size_t b_Hp, b_Hf, b_dz, b_dW32, bwd_total;
   // fused-gradient forward scratch offsets (DPA_FLAG_FUSED_GRAD)
   size_t u_Hp, u_Hf, u_part_pair, u_part_ref, u_part_u, u_dz, u_zr, u_dW32, fused_total;
 };
 
+int g_layout_comm_world = 1;   // set by dpa_comm_init / dpa_comm_destroy (declared before the communicator itself)
 int make_layout(const dpa_shape_t& s, Layout& L) {
+  const int comm_world = g_layout_comm_world;
   if (s.B < 1 || s.T < 2 || s.B_ref < 1 || s.T_ref < 2) return fail(DPA_ERR_BAD_SHAPE, "need B>=1, T>=2, B_ref>=1, T_ref>=2");
   if (s.H < 64 || s.H % 64) return fail(DPA_ERR_BAD_SHAPE, "H=%d must be a positive multiple of 64", s.H);
   if (s.V_local < 1) return fail(DPA_ERR_BAD_SHAPE, "V_local=%d must be positive", s.V_local);
@@ -237,6 +240,8 @@ int make_layout(const dpa_shape_t& s, Layout& L) {
   L.f_part_pair = take((size_t)L.ng_pair * L.cap_pair * 16);
   L.f_part_ref = take((size_t)L.ng_ref * L.cap_ref * 16);
   L.f_part_u = take((size_t)L.ng_ref * L.cap_ref * 4);
+  L.f_gather = o;                       // records of all vocab shards when the library's own communicator exchanges them
+  if (comm_world > 1 && s.V_local < s.V) take((size_t)comm_world * L.row_stats_bytes);
   L.fwd_total = o;
 
   o = 0;
@@ -467,6 +472,45 @@ int check_grad_outputs(const dpa_args_t* a) {
   if (!aligned16(a->dH_pair) || !aligned16(a->dH_ref) || (a->dW && !aligned16(a->dW))) return fail(DPA_ERR_ALIGN, "gradient buffers must be 16-byte aligned");
   return DPA_OK;
 }
+
+// ---------------------------------------------------------------------------------- optional NCCL communicator
+// Vocab-parallel lm_head has one exchange step each way (all-gather of the per-row statistics record in the forward,
+// all-reduce of the dH partial sums in the backward).  With dpa_comm_init() the library issues them itself on the
+// caller's stream, so dpa_forward / dpa_backward stay ONE call each; without it the caller exchanges (dpa_forward_stats /
+// dpa_forward_finish).  NCCL is bound at run time (the copy the process already loaded, else libnccl.so.2): the library
+// has no link-time dependency on it and still loads on a box without NCCL.
+struct NcclId { char internal[128]; };
+typedef void* NcclComm;
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  int (*CommInitRank)(NcclComm*, int, NcclId, int) = nullptr;
+  int (*CommDestroy)(NcclComm) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+struct Comm { NcclComm comm = nullptr; int rank = 0, world = 1, device = -1; };
+Comm g_comm;
+constexpr int kNcclUint8 = 1, kNcclBfloat16 = 9, kNcclSum = 0;
+
+int nccl_bind() {
+  if (g_nccl.lib) return DPA_OK;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);       // the copy torch (or the host program) already loaded
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return fail(DPA_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror());
+#define BIND(field, sym) do { *reinterpret_cast<void**>(&g_nccl.field) = dlsym(h, sym); \
+    if (!g_nccl.field) return fail(DPA_ERR_NCCL, "libnccl: symbol %s missing", sym); } while (0)
+  BIND(GetUniqueId, "ncclGetUniqueId"); BIND(CommInitRank, "ncclCommInitRank"); BIND(CommDestroy, "ncclCommDestroy");
+  BIND(AllGather, "ncclAllGather"); BIND(AllReduce, "ncclAllReduce"); BIND(GetErrorString, "ncclGetErrorString");
+#undef BIND
+  g_nccl.lib = h;
+  return DPA_OK;
+}
+#define NCCL_TRY(x) do { int r_ = (x); if (r_ != 0) return fail(DPA_ERR_NCCL, "%s: %s", #x, g_nccl.GetErrorString(r_)); } while (0)
+bool comm_active(const dpa_shape_t& s) { return g_comm.comm && g_comm.world > 1 && s.V_local < s.V; }
 
 // ---------------------------------------------------------------------------------- one call's GEMM plan
 // Tensor maps over the packed operands of this call and one method per GEMM class.  `scratch` offsets differ between
@@ -772,9 +816,23 @@ int dpa_forward_finish(const dpa_args_t* a, const void* gathered, int n_shards, 
 int dpa_forward(const dpa_args_t* a, void* stream) {
   Layout L; DeviceInfo* d;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (a && (a->shape.flags & DPA_FLAG_FUSED_GRAD)) return forward_fused_impl(a, st);
+  if (a && (a->shape.flags & DPA_FLAG_FUSED_GRAD)) {
+    if (comm_active(a->shape)) return fail(DPA_ERR_ARG, "DPA_FLAG_FUSED_GRAD is not available with a vocab-sharded lm_head");
+    return forward_fused_impl(a, st);
+  }
   int rc = forward_stats_impl(a, st, L, &d);
   if (rc) return rc;
+  if (comm_active(a->shape)) {
+    // the one exchange step of the forward: every shard's per-row statistics record -> all ranks -> max-rescale merge
+    if (a->shape.flags & DPA_FLAG_FUSED_NORM) return fail(DPA_ERR_ARG, "DPA_FLAG_FUSED_NORM is not available with a vocab-sharded lm_head");
+    char* g = at<char>(a->scratch, L.f_gather);
+    const size_t rec = L.row_stats_bytes;
+    NCCL_TRY(g_nccl.AllGather(at<char>(a->state, L.stats_pair), g, rec, kNcclUint8, g_comm.comm, st));
+    const int G = g_comm.world;
+    rc = run_merge(a, L, d, reinterpret_cast<const float4*>(g), reinterpret_cast<const float4*>(g + (L.stats_ref - L.stats_pair)),
+                   reinterpret_cast<const float*>(g + (L.stats_u - L.stats_pair)), G, G, rec / 16, rec / 16, rec / 4, st);
+    if (rc) return rc;
+  }
   return run_finish(a, L, d, st);
 }
 
@@ -786,8 +844,49 @@ int dpa_backward(const dpa_args_t* a, void* stream) {
   if (rc) return rc;
   if (!a->scratch || a->scratch_bytes < L.bwd_total) return fail(DPA_ERR_WORKSPACE, "backward scratch: need %zu bytes, got %zu", L.bwd_total, a->scratch_bytes);
   if ((rc = check_grad_outputs(a))) return rc;
-  return (a->shape.flags & DPA_FLAG_ROUND_LOGITS) ? run_backward<true>(a, L, d, st) : run_backward<false>(a, L, d, st);
+  rc = (a->shape.flags & DPA_FLAG_ROUND_LOGITS) ? run_backward<true>(a, L, d, st) : run_backward<false>(a, L, d, st);
+  if (rc) return rc;
+  if (comm_active(a->shape)) {
+    // the one exchange step of the backward: dH partial sums over the vocab shards (dW stays sharded)
+    const dpa_shape_t& s = a->shape;
+    NCCL_TRY(g_nccl.AllReduce(a->dH_pair, a->dH_pair, (size_t)2 * s.B * s.T * s.H, kNcclBfloat16, kNcclSum, g_comm.comm, st));
+    NCCL_TRY(g_nccl.AllReduce(a->dH_ref, a->dH_ref, (size_t)s.B_ref * s.T_ref * s.H, kNcclBfloat16, kNcclSum, g_comm.comm, st));
+  }
+  return DPA_OK;
 }
+
+int dpa_comm_unique_id(void* out128) {
+  if (!out128) return fail(DPA_ERR_ARG, "NULL argument");
+  int rc = nccl_bind();
+  if (rc) return rc;
+  NCCL_TRY(g_nccl.GetUniqueId(static_cast<NcclId*>(out128)));
+  return DPA_OK;
+}
+
+int dpa_comm_init(int rank, int world, const void* unique_id128) {
+  if (!unique_id128 || world < 1 || rank < 0 || rank >= world) return fail(DPA_ERR_ARG, "bad rank / world / unique id");
+  if (g_comm.comm) return fail(DPA_ERR_ARG, "communicator already initialised (call dpa_comm_destroy first)");
+  int rc = nccl_bind();
+  if (rc) return rc;
+  NcclId id;
+  memcpy(&id, unique_id128, sizeof(id));
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  NcclComm c = nullptr;
+  NCCL_TRY(g_nccl.CommInitRank(&c, world, id, rank));
+  g_comm.comm = c; g_comm.rank = rank; g_comm.world = world; g_comm.device = dev;
+  g_layout_comm_world = world;
+  return DPA_OK;
+}
+
+int dpa_comm_destroy(void) {
+  if (g_comm.comm) NCCL_TRY(g_nccl.CommDestroy(g_comm.comm));
+  g_comm = Comm{};
+  g_layout_comm_world = 1;
+  return DPA_OK;
+}
+
+int dpa_comm_world(void) { return g_comm.comm ? g_comm.world : 1; }
 
 int dpa_set_cta_group(int cg) {
   if (cg != 1 && cg != 2) return fail(DPA_ERR_ARG, "cta_group must be 1 or 2");

@@ -72,6 +72,37 @@ def average_gradients(tensors: Iterable[torch.Tensor], group=None, bucket_bytes:
     flush()
 
 
+def init_library_comm(group=None) -> int:
+    """Give libhalva_dpa.so its own NCCL communicator over `group` (include/halva_dpa.h: dpa_comm_*): vocab-parallel
+    dpa_loss(..., vocab_group=group) then exchanges inside the two C calls instead of through torch.distributed.
+    The 128-byte NCCL id is created on the group's rank 0 and broadcast through the group.  Returns the world size."""
+    import ctypes as C
+
+    from . import _lib
+    lib = _lib.load()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if world == 1:
+        return 1
+    if lib.dpa_comm_world() == world:
+        return world
+    buf = (C.c_ubyte * 128)()
+    if rank == 0:
+        _lib.check(lib.dpa_comm_unique_id(buf), "dpa_comm_unique_id")
+    t = torch.tensor(list(buf), dtype=torch.uint8)
+    on_gpu = dist.get_backend(group) == "nccl"
+    if on_gpu:
+        t = t.cuda()
+    dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    raw = bytes(t.cpu().tolist())
+    _lib.check(lib.dpa_comm_init(rank, world, raw), "dpa_comm_init")
+    return world
+
+
+def destroy_library_comm() -> None:
+    from . import _lib
+    _lib.check(_lib.load().dpa_comm_destroy(), "dpa_comm_destroy")
+
+
 # ---- layout of the vocab-parallel exchange record (dpa_row_stats_view): [cap_pair x {m,s,z_y,0}] [cap_ref x {m_p,s_p,m_r,s_r}]
 #      [cap_ref x u] fp32.  merge_row_stats is the host restatement of merge_strided_kernel, used by the CPU protocol test.
 def row_stats_record_floats(cap_pair: int, cap_ref: int) -> int:

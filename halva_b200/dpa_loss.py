@@ -59,6 +59,7 @@ class _Call:
                 (_lib.FLAG_DENSE if dense else 0) | (_lib.FLAG_FUSED_GRAD if fused else 0) | \
                 (_lib.FLAG_FUSED_NORM if norm is not None else 0)
         self.fused = fused
+        self.lib_comm = False
         self.norm = None
         if norm is not None:                  # (weight, frozen model's weight, eps, weight needs grad)
             nw, nwr, eps, need = norm
@@ -111,7 +112,10 @@ class _Call:
                 self.args.scratch, self.args.scratch_bytes = None, 0
                 return
             scratch = self._with_scratch(self.ws.fwd_bytes)
-            if vocab_group is None:
+            # vocab-parallel with the library's own NCCL communicator (halva_b200.dist.init_library_comm): the exchange
+            # steps happen inside dpa_forward / dpa_backward
+            self.lib_comm = vocab_group is not None and self.lib.dpa_comm_world() > 1
+            if vocab_group is None or self.lib_comm:
                 _lib.check(self.lib.dpa_forward(C.byref(self.args), self._stream()), "dpa_forward")
             else:
                 import torch.distributed as dist
@@ -167,7 +171,7 @@ class DPALossFn(torch.autograd.Function):
     def backward(ctx, g_loss, g_align, g_div):
         call = ctx.call
         dH_pair, dH_ref, dW, dnw = call.backward(g_loss)
-        if ctx.vocab_group is not None:
+        if ctx.vocab_group is not None and not call.lib_comm:
             import torch.distributed as dist
             dist.all_reduce(dH_pair, group=ctx.vocab_group)      # partial sums over vocab shards
             dist.all_reduce(dH_ref, group=ctx.vocab_group)

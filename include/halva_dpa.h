@@ -135,6 +135,17 @@ int dpa_forward_finish(const dpa_args_t* args, const void* gathered_stats, int n
 /* byte size and device address of this rank's merged per-row statistics inside `state` */
 int dpa_row_stats_view(const dpa_args_t* args, void** ptr, size_t* bytes);
 
+/* Optional NCCL communicator for vocab-parallel lm_head (V_local < V).  Once initialised, dpa_forward (statistics path)
+ * all-gathers the per-row statistics record of every shard and merges them, and dpa_backward all-reduces the dH partial
+ * sums, both on the caller's stream -- one call each way, no caller-side exchange.  NCCL is bound at run time (the copy
+ * already loaded in the process, else libnccl.so.2).  Not thread-safe: call once per process at start-up, before
+ * dpa_query_workspace (the forward scratch grows by world * record bytes).
+ *   rank 0:    dpa_comm_unique_id(id)  -> broadcast the 128 bytes by any means ->  every rank: dpa_comm_init(rank, world, id) */
+int dpa_comm_unique_id(void* out_128_bytes);
+int dpa_comm_init(int rank, int world, const void* unique_id_128_bytes);
+int dpa_comm_destroy(void);
+int dpa_comm_world(void);          /* 1 when no communicator is initialised */
+
 /* Optional live timing of the kernels this library launches (bench.py): when enabled every launch group is
  * bracketed by CUDA events on the caller's stream; collect() synchronises on them and sums milliseconds and
  * kernel-launch counts per kernel class k (name via dpa_profile_kind_name(k)); returns the number of classes. */

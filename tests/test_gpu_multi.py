@@ -55,6 +55,14 @@ def _worker(rank, world, port, out):
         assert abs(part[1].item() - full[1].item()) <= 1e-4 * abs(full[1].item()) + 1e-7
         assert _rel(part[2], full[2]) <= 5e-3 and _rel(part[3], full[3]) <= 5e-3        # bf16 partial sums all-reduced
         assert _rel(part[4], full[4][v0:v1]) <= 1e-3                                    # dW stays sharded
+        # the same with the library's own NCCL communicator: both exchange steps inside the two C calls
+        from halva_b200 import _lib
+        from halva_b200.dist import destroy_library_comm, init_library_comm
+        assert init_library_comm(dist.group.WORLD) == world and _lib.load().dpa_comm_world() == world
+        own = run(t["W"][v0:v1].contiguous(), t["W_ref"][v0:v1].contiguous(), vocab_group=dist.group.WORLD, v_offset=v0, vocab_size=shape.V)
+        destroy_library_comm()
+        assert own[0].item() == part[0].item() and torch.equal(own[4], part[4])
+        assert _rel(own[2], part[2]) <= 1e-3 and _rel(own[3], part[3]) <= 1e-3
         # ---- data parallel: pairs split over ranks, lm_head gradient averaged
         B = shape.B
         mine = list(dp_shard(B, world, rank))
