@@ -1,15 +1,19 @@
 // Persistent, warp-specialised tcgen05 GEMM for sm_100a with pluggable fused epilogues.
 //
-//   D[128 x BN] (+)= A[128 x K] * B[BN x K]^T      bf16 operands, fp32 accumulators in TMEM
+//   D[128*CG x BN] (+)= A[128*CG x K] * B[BN x K]^T      bf16 operands, fp32 accumulators in TMEM
+//   CG = 2 (default): a cluster of two CTAs on one TPC shares the tile -- tcgen05.mma.cta_group::2, M = 256, each CTA
+//   stages its own 128 rows of A and half of B; CG = 1: one CTA per 128-row tile.
 //
 //   warps 0..3         epilogue: tcgen05.ld (thread == accumulator row) -> fused maths -> HBM
 //   warp 4 (one lane)  TMA producer: cp.async.bulk.tensor -> 128B-swizzled smem ring (mbarrier full/empty)
 //   warp 5 (one lane)  tcgen05.mma issuer; tcgen05.commit frees smem slots and publishes accumulators
 //   warp 6             TMEM allocator (all 512 columns: two accumulator stages)
 //
-// The DPA loss uses it six ways (see dpa_api.cu): forward row statistics for pair rows and for
-// reference-sample rows (DUAL: policy and frozen-model logits of the same tile side by side in TMEM),
-// the recompute pass that turns logits into dLogits, and the two backward GEMMs dH = dZ*W, dW = dZ^T*H.
+// The DPA loss uses it through seven epilogues (see dpa_api.cu, struct Plan): forward row statistics of pair rows
+// (optionally keeping their bf16 logits), statistics + kept logits of reference-sample rows (fused-gradient forward),
+// the DUAL variants that hold the policy and frozen-model logits of the same tile side by side in TMEM (statistics
+// incl. the KL numerator; recompute of dLogits), the recompute of pair-row dLogits, and the two gradient GEMMs
+// dH = dZ*W, dW = dZ^T*H.
 // A work "unit" is (row tile, group of consecutive column tiles); row counts live in device memory
 // (DpaMeta) so that nothing on the path needs a host synchronisation.
 #pragma once
