@@ -236,6 +236,9 @@ def run_ours(args):
         v0, v1 = vocab_shard_bounds(shape.V, world, rank)
         t["W"] = t["W"][v0:v1].contiguous()
         vp_kw = dict(vocab_group=dist.group.WORLD, v_offset=v0, vocab_size=shape.V)
+        if not args.vp_torch_exchange:      # the library's own NCCL communicator: both exchange steps inside the two C calls
+            from halva_b200.dist import init_library_comm
+            init_library_comm(dist.group.WORLD)
     W = t["W"].requires_grad_(need_dw)
     tensors = dict(h_pair=hp, h_ref_pol=hr, h_ref_frz=t["h_ref_frz"], labels_pair=t["labels_pair"], signs_pair=t["signs_pair"],
                    labels_ref=t["labels_ref"])
@@ -460,6 +463,8 @@ def main():
     ap.add_argument("--chunk-rows", type=int, default=0)
     ap.add_argument("--parallelism", default="dp", choices=["dp", "vp"],
                     help="dp: data parallel over sample pairs (default); vp: vocab-parallel lm_head (same rows on every rank)")
+    ap.add_argument("--vp-torch-exchange", action="store_true",
+                    help="vp: exchange through torch.distributed around the C calls instead of the library's own communicator")
     ap.add_argument("--no-dw", action="store_true", help="lm_head frozen (the shipped LoRA recipe): no dW")
     ap.add_argument("--dense", action="store_true", help="process every fed position (no row compaction)")
     ap.add_argument("--backward", default="auto", choices=["auto", "fused", "recompute"],

@@ -182,7 +182,7 @@ struct Layout {
   // forward scratch offsets
   size_t f_Hp, f_Hf, f_part_pair, f_part_ref, f_part_u, f_gather, fwd_total;
   // backward scratch offsets
-  size_t b_Hp, b_Hf, b_dz, b_dW32, bwd_total;
+  size_t b_Hp, b_Hf, b_dz, b_dW32, b_dHp, bwd_total;
   // fused-gradient forward scratch offsets (DPA_FLAG_FUSED_GRAD)
   size_t u_Hp, u_Hf, u_part_pair, u_part_ref, u_part_u, u_dz, u_zr, u_dW32, fused_total;
 };
@@ -249,6 +249,8 @@ int make_layout(const dpa_shape_t& s, Layout& L) {
   L.b_Hf = take((size_t)L.cap_ref * s.H * 2);
   L.b_dz = take((size_t)L.chunk_rows * L.ldz * 2);
   L.b_dW32 = (s.flags & DPA_FLAG_NEED_DW) ? take((size_t)s.V_local * s.H * 4) : o;
+  // library-side vocab-parallel exchange: dH partial sums stay packed (active rows only) for the all-reduce
+  L.b_dHp = (comm_world > 1 && s.V_local < s.V) ? take((size_t)cap_tot * s.H * 2) : o;
   L.bwd_total = o;
 
   o = 0;
@@ -520,6 +522,7 @@ struct Plan {
   const dpa_shape_t& s;
   const DpaMeta* meta;
   __nv_bfloat16* dz = nullptr; __nv_bfloat16* zr = nullptr; float* dW32 = nullptr;
+  __nv_bfloat16* dH_packed = nullptr;     // vocab-parallel with the library's communicator: dH rows stay packed until reduced
   float4* part_pair = nullptr; float4* part_ref = nullptr; float* part_u = nullptr;
   CUtensorMap tmHp, tmHf, tmW256, tmW128, tmW64, tmWr256, tmWr128, tmWr64, tmDzK, tmWmn, tmDzMN, tmHpMN;
 
@@ -609,7 +612,7 @@ struct Plan {
       using Epi = EpiStoreRows<256>;
       GemmWork w{meta, KIND_DH, ch, L.chunk_rows, 0, s.H, s.V_local, 1};
       typename Epi::Params ep{meta, at<int>(a->state, L.src_pair), at<int>(a->state, L.src_ref),
-                              static_cast<__nv_bfloat16*>(a->dH_pair), static_cast<__nv_bfloat16*>(a->dH_ref), s.H};
+                              static_cast<__nv_bfloat16*>(a->dH_pair), static_cast<__nv_bfloat16*>(a->dH_ref), s.H, dH_packed};
       ProfScope ps(PK_DH, 1, st);
       int rc = launch_single<Epi, KMAJOR, MNMAJOR>(st, d, tmDzK, tmWmn, tmWmn, w, ep, "dH");
       if (rc) return rc;
@@ -754,13 +757,37 @@ int run_backward(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, cuda
   Plan p(a, L, d, st);
   if ((rc = p.init(L.b_Hp, L.b_Hf, 0, 0, 0, false, at<__nv_bfloat16>(a->scratch, L.b_dz), nullptr,
                    (s.flags & DPA_FLAG_NEED_DW) ? at<float>(a->scratch, L.b_dW32) : nullptr))) return rc;
+  // Vocab-parallel with the library's own communicator: the dH partial sums of this rank's vocabulary shard stay packed
+  // (active rows only -- a quarter of the dense tensors at 10 % phrase density), are all-reduced chunk by chunk and
+  // scattered at the end.  The all-reduce count is a host value, so this (optional) mode reads the active row count
+  // back once; the forward that produced it has long finished by the time the backward is called.
+  const bool vp = comm_active(s);
+  int n_tot_host = 0;
+  if (vp) {
+    p.dH_packed = at<__nv_bfloat16>(a->scratch, L.b_dHp);
+    CUDA_TRY(cudaMemcpyAsync(&n_tot_host, &p.meta->n_tot, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
   if ((rc = p.coef(a->d_loss))) return rc;
   if ((rc = run_gather(a, L, d, a->scratch, L.b_Hp, L.b_Hf, st))) return rc;
   if ((rc = p.zero_grad_outputs())) return rc;
   for (int ch = 0; ch < L.n_chunks; ++ch) {
+    if (vp && (long long)ch * L.chunk_rows >= n_tot_host) break;
     if ((long long)ch * L.chunk_rows < L.cap_pair && (rc = p.dz_pair<ROUND>(ch))) return rc;
     if ((rc = p.dz_ref<ROUND>(ch))) return rc;
     if ((rc = p.grad_gemms(ch))) return rc;
+    if (vp) {
+      const size_t r0 = (size_t)ch * L.chunk_rows, r1 = std::min<size_t>(r0 + L.chunk_rows, (size_t)n_tot_host);
+      ProfScope ps(PK_MISC, 0, st);
+      NCCL_TRY(g_nccl.AllReduce(p.dH_packed + r0 * s.H, p.dH_packed + r0 * s.H, (r1 - r0) * s.H, kNcclBfloat16, kNcclSum, g_comm.comm, st));
+    }
+  }
+  if (vp) {
+    ScatterArgs sc{p.meta, at<int>(a->state, L.src_pair), at<int>(a->state, L.src_ref), p.dH_packed,
+                   static_cast<__nv_bfloat16*>(a->dH_pair), static_cast<__nv_bfloat16*>(a->dH_ref), s.H};
+    ProfScope ps(PK_MISC, 1, st);
+    scatter_rows_kernel<<<d->sms * 8, 256, 0, st>>>(sc);
+    LAUNCH_CHECK("scatter_rows");
   }
   if ((rc = run_norm_backward(a, L, d, st))) return rc;
   return p.finish_dW();
@@ -846,13 +873,7 @@ int dpa_backward(const dpa_args_t* a, void* stream) {
   if ((rc = check_grad_outputs(a))) return rc;
   rc = (a->shape.flags & DPA_FLAG_ROUND_LOGITS) ? run_backward<true>(a, L, d, st) : run_backward<false>(a, L, d, st);
   if (rc) return rc;
-  if (comm_active(a->shape)) {
-    // the one exchange step of the backward: dH partial sums over the vocab shards (dW stays sharded)
-    const dpa_shape_t& s = a->shape;
-    NCCL_TRY(g_nccl.AllReduce(a->dH_pair, a->dH_pair, (size_t)2 * s.B * s.T * s.H, kNcclBfloat16, kNcclSum, g_comm.comm, st));
-    NCCL_TRY(g_nccl.AllReduce(a->dH_ref, a->dH_ref, (size_t)s.B_ref * s.T_ref * s.H, kNcclBfloat16, kNcclSum, g_comm.comm, st));
-  }
-  return DPA_OK;
+  return DPA_OK;     // (vocab-parallel: the dH exchange already happened inside run_backward, on the packed rows)
 }
 
 int dpa_comm_unique_id(void* out128) {

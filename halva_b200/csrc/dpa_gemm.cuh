@@ -550,10 +550,12 @@ struct EpiStoreRows {
     const DpaMeta* meta;
     const int* src_pair; const int* src_ref;       // packed row -> flat (sequence*T + t) row of the dense tensors
     __nv_bfloat16* dH_pair; __nv_bfloat16* dH_ref; int H;
-  };
+    __nv_bfloat16* packed;                         // non-null: keep the rows packed ([n_tot][H]; vocab-parallel: the partial
+  };                                               // sums are all-reduced in this compact form and scattered afterwards)
   struct State { __nv_bfloat16* out; };
   __device__ static void unit_begin(const Params& p, State& s, int erow, int) {
     const int p0 = p.meta->p0;
+    if (p.packed) { s.out = p.packed + (size_t)erow * p.H; return; }
     s.out = nullptr;
     if (erow < p0) { if (erow < p.meta->n_pair) s.out = p.dH_pair + (size_t)p.src_pair[erow] * p.H; }
     else { const int j = erow - p0; if (j < p.meta->n_ref) s.out = p.dH_ref + (size_t)p.src_ref[j] * p.H; }

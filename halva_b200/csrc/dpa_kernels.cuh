@@ -277,6 +277,27 @@ __global__ void gather_rows_kernel(GatherArgs a) {
   }
 }
 
+// ---- vocab-parallel backward: scatter the all-reduced packed dH rows to their [s,t] positions (one warp per row)
+struct ScatterArgs {
+  const DpaMeta* meta;
+  const int* src_pair; const int* src_ref;
+  const __nv_bfloat16* packed; __nv_bfloat16* dH_pair; __nv_bfloat16* dH_ref; int H;
+};
+__global__ void scatter_rows_kernel(ScatterArgs a) {
+  const int p0 = a.meta->p0, n_pair = a.meta->n_pair, n_ref = a.meta->n_ref;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int vec = a.H / 8;
+  for (int q = wid; q < n_pair + n_ref; q += warps) {
+    const bool is_pair = q < n_pair;
+    const int r = is_pair ? q : p0 + (q - n_pair);
+    const int s = is_pair ? a.src_pair[q] : a.src_ref[q - n_pair];
+    const uint4* src = reinterpret_cast<const uint4*>(a.packed + (size_t)r * a.H);
+    uint4* dst = reinterpret_cast<uint4*>((is_pair ? a.dH_pair : a.dH_ref) + (size_t)s * a.H);
+    for (int i = lane; i < vec; i += 32) dst[i] = src[i];
+  }
+}
+
 // ---- backward of the folded final RMSNorm, in place over the dH rows of the active policy rows:
 //      dn = bf16(dy * w), dx = r dn - x r^3 mean(dn x), d_norm_w += dy * bf16(x r)   (autograd of modelling_llama.py:64-69)
 struct NormBwdArgs {
