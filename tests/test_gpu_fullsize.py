@@ -85,3 +85,31 @@ def test_cfg2_pair_permutation(cfg2):
     assert abs(a["loss"] - b["loss"]) <= 2e-6 * abs(a["loss"])
     assert _rel(b["dH_pair"], a["dH_pair"][perm]) <= 1e-3
     assert _rel(b["dW"], a["dW"]) <= 1e-3
+
+
+@pytest.mark.parametrize("cfg,pairs", [("cfg3", 4), ("cfg4", 2)])
+def test_13b_shapes_vs_reference_op_chain(cfg, pairs):
+    """BASELINE configs[2]/[3] shapes (H 5120; T 4096 with the 196-token VILA image prefix) at a reduced pair count:
+    loss and gradients against the reference's ATen sequence on the same GPU."""
+    from halva_b200 import dpa_loss, read_status
+    from halva_b200.synth import CONFIGS, make_inputs
+    from oracle import dpa_port
+    shape = dataclasses.replace(CONFIGS[cfg], B=pairs, B_ref=pairs)
+    t = make_inputs(shape, seed=99, device="cuda", plant=5.0)
+
+    def grads(fn):
+        hp = t["h_pair"].clone().requires_grad_(True)
+        hr = t["h_ref_pol"].clone().requires_grad_(True)
+        W = t["W"].clone().requires_grad_(True)
+        loss = fn(hp, hr, W)
+        loss.backward()
+        return loss, hp.grad, hr.grad, W.grad
+
+    ours = grads(lambda hp, hr, W: dpa_loss(hp, t["labels_pair"], t["signs_pair"], hr, t["labels_ref"], W, h_ref_frozen=t["h_ref_frz"],
+                                            alpha=shape.alpha)[0])
+    assert read_status(ours[0])["status"] == 0
+    ref = grads(lambda hp, hr, W: dpa_port.dpa_loss_torch(hp, t["labels_pair"], t["signs_pair"], hr, t["h_ref_frz"], t["labels_ref"], W,
+                                                          W.detach(), shape.alpha)[0])
+    assert np.isfinite(ref[0].item()) and abs(ours[0].item() - ref[0].item()) <= 1e-3 * abs(ref[0].item())
+    for a, b, name in zip(ours[1:], ref[1:], ("dH_pair", "dH_ref", "dW")):
+        assert _rel(a, b) <= 1e-2, (cfg, name, _rel(a, b))
