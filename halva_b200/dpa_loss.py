@@ -212,11 +212,12 @@ def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.
     backward                       "recompute": forward keeps only per-row statistics, backward recomputes the logits
                                    chunk-wise (BASELINE north star);  "fused": the forward pass also forms the gradients
                                    (for d_loss = 1) -- reference-sample logits of one row chunk are kept in bf16 and
-                                   turned into dLogits in place, which saves two of the six GEMMs per such row -- and
+                                   turned into dLogits in place (executed GEMMs = the algorithmic count: 4 per such row
+                                   instead of 6, 3 instead of 4 per pair row) -- and
                                    backward only scales by d_loss;  "auto" = "fused" when round_logits is on, a gradient
                                    is needed and there is no vocab_group, else "recompute".
     Ill-formed phrase ids (K_pos != K_neg, K == 0, id > 255) make the losses NaN and set bits in
-    `dpa_last_status()`; the reference raises / returns NaN there.
+    `read_status(loss)["status"]`; the reference raises / returns NaN there.
     """
     W_ref = W if W_ref is None else W_ref
     _check_inputs(h_pair, labels_pair, signs_pair, h_ref_pol, h_ref_frozen, labels_ref, W, W_ref)
