@@ -296,3 +296,31 @@ def test_shim_cuda_vs_port_bf16(vila):
         assert rel(g[n], g2[n]) <= 3e-2, (n, rel(g[n], g2[n]))      # bf16 autograd chain through the stand-in decoder
     if vila:
         assert len(tr.loss_holder["loss"]) == 1 and torch.is_tensor(tr.loss_holder["loss"][0])
+
+
+def test_zero3_partitioned_lm_head_is_gathered(monkeypatch):
+    """Under DeepSpeed ZeRO-3 lm_head.weight is partitioned (carries `ds_id`) and only lm_head.forward's hooks re-assemble
+    it; the shim reads the weight directly, so it must wrap the op in deepspeed.zero.GatheredParameters
+    (the reference's own pattern, llava/train/train_halva.py:102-113)."""
+    import contextlib
+    import sys
+    from halva_b200 import trainer as shim
+    seen = []
+
+    @contextlib.contextmanager
+    def gathered(params, modifier_rank=None):
+        seen.append([id(p) for p in params])
+        yield
+
+    fake = types.ModuleType("deepspeed")
+    fake.zero = types.SimpleNamespace(GatheredParameters=gathered)
+    monkeypatch.setitem(sys.modules, "deepspeed", fake)
+    monkeypatch.setattr(shim._dpa_loss_mod, "dpa_loss", _port_as_op)
+    pol, frz = _models(seed=3)
+    pol.lm_head.weight.ds_id = 7                       # what ZeRO-3 stamps on a partitioned parameter
+    loss = shim.fused_compute_loss(_trainer(pol, frz), pol, make_inputs(seed=3))
+    assert torch.isfinite(loss) and seen == [[id(pol.lm_head.weight)]]
+    seen.clear()
+    del pol.lm_head.weight.ds_id
+    shim.fused_compute_loss(_trainer(pol, frz), pol, make_inputs(seed=3))
+    assert seen == []                                  # nothing to gather outside ZeRO-3
