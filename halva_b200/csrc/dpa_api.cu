@@ -618,9 +618,9 @@ struct Plan {
       if (rc) return rc;
     }
     if (dW32) {
-      using Epi = EpiAccumF32<256>;
+      using Epi = EpiAccumDW<256>;
       GemmWork w{meta, KIND_DW, ch, L.chunk_rows, s.V_local, s.H, 0, 1};
-      typename Epi::Params ep{dW32, s.H, s.V_local, s.H, 1};
+      typename Epi::Params ep{meta, ch, L.chunk_rows, dW32, static_cast<__nv_bfloat16*>(a->dW), s.H, s.V_local, s.H};
       ProfScope ps(PK_DW, 1, st);
       return launch_single<Epi, MNMAJOR, MNMAJOR>(st, d, tmDzMN, tmHpMN, tmHpMN, w, ep, "dW");
     }
@@ -630,14 +630,13 @@ struct Plan {
     ProfScope ps(PK_MISC, 0, st);
     CUDA_TRY(cudaMemsetAsync(a->dH_pair, 0, (size_t)2 * s.B * s.T * s.H * 2, st));
     CUDA_TRY(cudaMemsetAsync(a->dH_ref, 0, (size_t)s.B_ref * s.T_ref * s.H * 2, st));
-    if (dW32) CUDA_TRY(cudaMemsetAsync(dW32, 0, (size_t)s.V_local * s.H * 4, st));
-    return DPA_OK;
+    return DPA_OK;      // (the dW accumulator needs no memset: the first chunk's epilogue overwrites it)
   }
   int finish_dW() {
     if (!dW32) return DPA_OK;
-    ProfScope ps(PK_MISC, 1, st);
-    f32_to_bf16_kernel<<<d->sms * 8, 256, 0, st>>>(dW32, static_cast<__nv_bfloat16*>(a->dW), (size_t)s.V_local * s.H);
-    LAUNCH_CHECK("dW convert");
+    ProfScope ps(PK_MISC, 1, st);      // the last chunk with rows wrote dW in bf16; only the no-rows-at-all case is left
+    zero_if_no_rows_kernel<<<d->sms * 2, 256, 0, st>>>(meta, static_cast<__nv_bfloat16*>(a->dW), (size_t)s.V_local * s.H);
+    LAUNCH_CHECK("dW zero-if-empty");
     return DPA_OK;
   }
   int coef(const float* d_loss) {

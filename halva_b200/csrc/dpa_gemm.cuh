@@ -581,6 +581,7 @@ struct EpiAccumF32 {
   __device__ static void unit_begin(const Params& p, State& s, int, int trow_global) {
     s.out = trow_global < p.m_extent ? p.out + (size_t)trow_global * p.ld : nullptr;
   }
+  // (the chunked dW accumulation of the DPA path uses EpiAccumDW below; this one serves the debug GEMM)
   __device__ static void tile(const Params& p, State& s, uint32_t taddr, int col0) {
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
@@ -601,6 +602,50 @@ struct EpiAccumF32 {
 #pragma unroll
           for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         }
+      }
+    }
+  }
+  __device__ static void unit_end(const Params&, State&, int) {}
+};
+
+// ---- dW += dZ^T * H over the row chunks: the first chunk overwrites the fp32 accumulator (no memset), middle chunks add,
+//      the last chunk that has rows adds and writes bf16 straight to dW (no conversion pass).  Which chunk is first / last
+//      is decided on the device from DpaMeta (the host does not know the active row count).
+template <int BN>
+struct EpiAccumDW {
+  struct Params {
+    const DpaMeta* meta; int chunk, chunk_rows;
+    float* acc32; __nv_bfloat16* out; int ld; int m_extent; int n_extent;
+  };
+  struct State { float* acc; __nv_bfloat16* out; int first, last; };
+  __device__ static void unit_begin(const Params& p, State& s, int, int trow_global) {
+    const bool ok = trow_global < p.m_extent;
+    s.acc = ok ? p.acc32 + (size_t)trow_global * p.ld : nullptr;
+    s.out = ok ? p.out + (size_t)trow_global * p.ld : nullptr;
+    s.first = p.chunk == 0;
+    s.last = (long long)(p.chunk + 1) * p.chunk_rows >= p.meta->n_tot;
+  }
+  __device__ static void tile(const Params& p, State& s, uint32_t taddr, int col0) {
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int cbase = col0 + c * 32;
+      if (cbase >= p.n_extent) break;
+      float v[32];
+      load_chunk(taddr + c * 32, v);
+      if (!s.acc) continue;
+      float4* a = reinterpret_cast<float4*>(s.acc + cbase);
+      if (!s.first) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 t = a[i];
+          v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+        }
+      }
+      if (s.last) {
+        store_bf16_chunk(s.out + cbase, v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
       }
     }
   }

@@ -635,6 +635,14 @@ __global__ void scale_bf16_kernel(__nv_bfloat16* x, size_t n, const float* __res
   }
 }
 
+// dW when no row at all contributed (no chunk ran): zero it; otherwise the last chunk's GEMM epilogue already wrote it
+__global__ void zero_if_no_rows_kernel(const DpaMeta* meta, __nv_bfloat16* out, size_t n) {
+  if (meta->n_tot != 0) return;
+  uint4* p = reinterpret_cast<uint4*>(out);
+  const size_t nv = n >> 3, stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) p[i] = make_uint4(0, 0, 0, 0);
+}
+
 __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
   const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
   for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
