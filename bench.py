@@ -358,6 +358,40 @@ def run_ours(args):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ms_frozen = tt.item()
 
+    # ---- variant: the frozen model's logits GIVEN (dpa_loss(ref_logits=...), e.g. cached from an earlier frozen pass) instead
+    #      of its hidden states: one lm_head GEMM less per reference-sample row, an HBM-bound copy + statistics pass instead
+    ms_given = None
+    if not args.no_variants and not vp and args.backward != "recompute":
+        with torch.no_grad():
+            zr = torch.empty(shape.B_ref, shape.T_ref, shape.V, dtype=torch.bfloat16, device=dev)
+            for b0 in range(shape.B_ref):
+                torch.matmul(t["h_ref_frz"][b0], t["W"].detach().t(), out=zr[b0])
+
+        def step_given():
+            hp.grad = None
+            hr.grad = None
+            W.grad = None
+            l, _, _ = dpa_loss(hp, t["labels_pair"], t["signs_pair"], hr, t["labels_ref"], W, ref_logits=zr,
+                               alpha=shape.alpha, dense=args.dense, chunk_rows=args.chunk_rows)
+            l.backward()
+            return l
+
+        for _ in range(3):
+            lg_ = step_given()
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step_given()
+        e1.record()
+        barrier()
+        ms_given = e0.elapsed_time(e1) / args.steps
+        loss_given = lg_.item()
+        del zr, lg_
+        if world > 1:
+            tt = torch.tensor([ms_given], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms_given = tt.item()
+
     # ---- end to end: host (pinned) buffers in, losses out, H2D double-buffered against the previous step's compute
     ms_e2e, h2d_bytes, loss_e2e = None, 0, None
     if not args.no_e2e:
@@ -442,6 +476,11 @@ def run_ours(args):
     if ms_frozen:
         line["variants"] = dict(lm_head_frozen=dict(ms_per_step=ms_frozen, value=tokens_step / (ms_frozen * 1e-3), unit=UNIT,
                                                     note="same batch, lm_head not trainable (LoRA recipe): no dW GEMM"))
+    if ms_given:
+        line.setdefault("variants", {})["ref_logits_given"] = dict(
+            ms_per_step=ms_given, value=tokens_step / (ms_given * 1e-3), unit=UNIT, loss=loss_given,
+            note="same batch, the frozen model's bf16 logits handed over as ref_logits [B_ref,T_ref,V] instead of its hidden "
+                 "states: 3 instead of 4 lm_head GEMMs per reference-sample row")
     if world == 1 and not args.no_cpu_baseline:
         r = time_cpu_port(2, 1)
         line["cpu_baseline"] = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="port", sample=r["sample"],

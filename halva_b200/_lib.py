@@ -7,12 +7,12 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HALVA_DPA_LIB") or os.path.join(HERE, "libhalva_dpa.so")   # override: A/B builds of the kernels
 
-DPA_BF16 = 0
+DPA_BF16, DPA_F32 = 0, 1
 DPA_I64, DPA_I32 = 0, 1
-FLAG_ROUND_LOGITS, FLAG_NEED_DW, FLAG_DENSE, FLAG_FUSED_GRAD, FLAG_FUSED_NORM = 1, 2, 4, 8, 16
-ABI_VERSION = 3
+FLAG_ROUND_LOGITS, FLAG_NEED_DW, FLAG_DENSE, FLAG_FUSED_GRAD, FLAG_FUSED_NORM, FLAG_LOSS_ONLY = 1, 2, 4, 8, 16, 32
+ABI_VERSION = 4
 STATUS_BAD_SIGN, STATUS_K_MISMATCH, STATUS_K_ZERO, STATUS_BAD_LABEL = 1, 2, 4, 8
-EXPORTS = ["dpa_version", "dpa_last_error", "dpa_query_workspace", "dpa_forward", "dpa_backward",
+EXPORTS = ["dpa_version", "dpa_last_error", "dpa_query_workspace", "dpa_struct_sizes", "dpa_forward", "dpa_backward",
            "dpa_forward_stats", "dpa_forward_finish", "dpa_row_stats_view", "dpa_debug_gemm",
            "dpa_profile_enable", "dpa_profile_collect", "dpa_profile_kind_name", "dpa_set_cta_group",
            "dpa_comm_unique_id", "dpa_comm_init", "dpa_comm_destroy", "dpa_comm_world"]
@@ -36,7 +36,8 @@ class Args(C.Structure):
                 ("scratch", C.c_void_p), ("scratch_bytes", C.c_size_t),
                 ("losses", C.c_void_p), ("status", C.c_void_p),
                 ("d_loss", C.c_void_p), ("dH_pair", C.c_void_p), ("dH_ref", C.c_void_p), ("dW", C.c_void_p),
-                ("norm_w", C.c_void_p), ("norm_w_ref", C.c_void_p), ("d_norm_w", C.c_void_p), ("norm_eps", C.c_float)]
+                ("norm_w", C.c_void_p), ("norm_w_ref", C.c_void_p), ("d_norm_w", C.c_void_p), ("norm_eps", C.c_float),
+                ("ref_logits", C.c_void_p), ("ref_logits_ld", C.c_int64), ("ref_logits_dtype", C.c_int32)]
 
 
 class DPAError(RuntimeError):
@@ -60,6 +61,10 @@ def load():
         raise DPAError(f"{LIB_PATH} has ABI version {lib.dpa_version()}, this package needs {ABI_VERSION}: rebuild it "
                        "(`python -m halva_b200.build --force`)")
     lib.dpa_last_error.restype = C.c_char_p
+    sz = [C.c_int(), C.c_int(), C.c_int()]
+    lib.dpa_struct_sizes(*[C.byref(x) for x in sz])
+    if [x.value for x in sz] != [C.sizeof(Shape), C.sizeof(Workspace), C.sizeof(Args)]:
+        raise DPAError(f"{LIB_PATH}: struct sizes {[x.value for x in sz]} differ from this package's ctypes mirror")
     lib.dpa_query_workspace.argtypes = [C.POINTER(Shape), C.POINTER(Workspace)]
     for name in ("dpa_forward", "dpa_backward", "dpa_forward_stats"):
         getattr(lib, name).argtypes = [C.POINTER(Args), C.c_void_p]

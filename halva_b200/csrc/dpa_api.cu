@@ -26,7 +26,7 @@ int fail(int code, const char* fmt, ...) {
 // bench.py asks for live CUDA-event timings of the individual kernels (they are launched inside this library,
 // so the caller cannot bracket them). Off by default; when on, every launch group is bracketed by two events.
 enum ProfKind { PK_META = 0, PK_GATHER, PK_FWD_PAIR, PK_FWD_REF, PK_REDUCE, PK_COEF, PK_DZ_PAIR, PK_DZ_REF, PK_DH, PK_DW, PK_MISC,
-                PK_STASH_REF, PK_DZ_ELEM, PK_SCALE, PK_COUNT };
+                PK_STASH_REF, PK_DZ_ELEM, PK_SCALE, PK_STASH_GIVEN, PK_COUNT };
 struct ProfSpan { int kind; int launches; cudaEvent_t a, b; };
 std::vector<ProfSpan> g_spans;
 std::mutex g_prof_mu;
@@ -277,12 +277,24 @@ int check_common(const dpa_args_t* a, Layout& L, DeviceInfo** dev) {
   if (rc) return rc;
   const void* ptrs[] = {a->h_pair, a->labels_pair, a->signs_pair, a->h_ref_pol, a->h_ref_frz, a->labels_ref, a->W, a->W_ref};
   const char* names[] = {"h_pair", "labels_pair", "signs_pair", "h_ref_pol", "h_ref_frz", "labels_ref", "W", "W_ref"};
+  const bool given = a->ref_logits != nullptr;       // frozen logits given: h_ref_frz / W_ref are not needed
   for (int i = 0; i < 8; ++i) {
+    if (given && (i == 4 || i == 7) && !ptrs[i]) continue;
     if (!ptrs[i]) return fail(DPA_ERR_ARG, "%s is NULL", names[i]);
     if (!aligned16(ptrs[i])) return fail(DPA_ERR_ALIGN, "%s must be 16-byte aligned", names[i]);
   }
   if (!a->state || a->state_bytes < L.state_total) return fail(DPA_ERR_WORKSPACE, "state workspace: need %zu bytes, got %zu", L.state_total, a->state_bytes);
   if (!aligned16(a->state) || (a->scratch && !aligned16(a->scratch))) return fail(DPA_ERR_ALIGN, "workspaces must be 16-byte aligned (256 recommended)");
+  if (given) {
+    if (!(a->shape.flags & DPA_FLAG_FUSED_GRAD))
+      return fail(DPA_ERR_ARG, "ref_logits needs DPA_FLAG_FUSED_GRAD (+ DPA_FLAG_LOSS_ONLY for evaluation): the chunked forward keeps bf16 logits");
+    if (a->ref_logits_dtype != DPA_BF16 && a->ref_logits_dtype != DPA_F32) return fail(DPA_ERR_DTYPE, "ref_logits must be bf16 or fp32");
+    const long long esz = a->ref_logits_dtype == DPA_F32 ? 4 : 2;
+    if (a->ref_logits_ld < a->shape.V_local) return fail(DPA_ERR_BAD_SHAPE, "ref_logits_ld=%lld < V_local=%d", (long long)a->ref_logits_ld, a->shape.V_local);
+    if (!aligned16(a->ref_logits) || (a->ref_logits_ld * esz) % 16) return fail(DPA_ERR_ALIGN, "ref_logits and its row stride must be 16-byte aligned");
+  }
+  if ((a->shape.flags & DPA_FLAG_LOSS_ONLY) && !(a->shape.flags & DPA_FLAG_FUSED_GRAD))
+    return fail(DPA_ERR_ARG, "DPA_FLAG_LOSS_ONLY modifies DPA_FLAG_FUSED_GRAD");
   if (a->shape.flags & DPA_FLAG_FUSED_NORM) {
     if (!a->norm_w || !a->norm_w_ref) return fail(DPA_ERR_ARG, "DPA_FLAG_FUSED_NORM set but norm_w / norm_w_ref is NULL");
     if (!aligned16(a->norm_w) || !aligned16(a->norm_w_ref) || (a->d_norm_w && !aligned16(a->d_norm_w)))
@@ -539,14 +551,17 @@ struct Plan {
     int rc;
     char* Hp = at<char>(a->scratch, oHp);
     if ((rc = make_operand_tmap(d, &tmHp, Hp, KMAJOR, cap_tot, s.H, s.H, BM))) return rc;
-    if ((rc = make_operand_tmap(d, &tmHf, at<char>(a->scratch, oHf), KMAJOR, L.cap_ref, s.H, s.H, BM))) return rc;
+    const bool frozen = a->h_ref_frz && a->W_ref;      // false: the frozen model's logits are given (ref_logits)
+    if (frozen && (rc = make_operand_tmap(d, &tmHf, at<char>(a->scratch, oHf), KMAJOR, L.cap_ref, s.H, s.H, BM))) return rc;
     // lm_head rows as the K-major B operand: boxes of 256 (single CTA), 128 (CTA pair / dual single CTA), 64 (dual pair)
     if ((rc = make_operand_tmap(d, &tmW256, a->W, KMAJOR, s.V_local, s.H, s.H, 256))) return rc;
     if ((rc = make_operand_tmap(d, &tmW128, a->W, KMAJOR, s.V_local, s.H, s.H, 128))) return rc;
     if ((rc = make_operand_tmap(d, &tmW64, a->W, KMAJOR, s.V_local, s.H, s.H, 64))) return rc;
-    if ((rc = make_operand_tmap(d, &tmWr256, a->W_ref, KMAJOR, s.V_local, s.H, s.H, 256))) return rc;
-    if ((rc = make_operand_tmap(d, &tmWr128, a->W_ref, KMAJOR, s.V_local, s.H, s.H, 128))) return rc;
-    if ((rc = make_operand_tmap(d, &tmWr64, a->W_ref, KMAJOR, s.V_local, s.H, s.H, 64))) return rc;
+    if (frozen) {
+      if ((rc = make_operand_tmap(d, &tmWr256, a->W_ref, KMAJOR, s.V_local, s.H, s.H, 256))) return rc;
+      if ((rc = make_operand_tmap(d, &tmWr128, a->W_ref, KMAJOR, s.V_local, s.H, s.H, 128))) return rc;
+      if ((rc = make_operand_tmap(d, &tmWr64, a->W_ref, KMAJOR, s.V_local, s.H, s.H, 64))) return rc;
+    }
     if (dz) {
       // dH = dZ[rows x V] * W[V x H]:      A = dz K-major (K = vocab),  B = W MN-major (N = hidden contiguous)
       // dW = dZ^T[V x rows] * H[rows x H]: A = dz MN-major (M = vocab), B = packed hidden rows MN-major
@@ -597,14 +612,30 @@ struct Plan {
   int stash_ref(int ch) {
     using Epi = EpiStatsStore<256>;
     float2* part2 = reinterpret_cast<float2*>(part_ref);
-    ProfScope ps(PK_STASH_REF, 2, st);
-    GemmWork wp{meta, KIND_STASH_POL, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair};
-    typename Epi::Params epp{meta, part2, dz, L.cap_ref, s.V_local, L.ldz, ch * L.chunk_rows, 0};
-    int rc = launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHp, tmW256, tmW128, wp, epp, "stash_pol");
-    if (rc) return rc;
-    GemmWork wf{meta, KIND_STASH_FRZ, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair};
-    typename Epi::Params epf{meta, part2, zr, L.cap_ref, s.V_local, L.ldz, ch * L.chunk_rows, 1};
-    return launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHf, tmWr256, tmWr128, wf, epf, "stash_frz");
+    const bool given = a->ref_logits != nullptr;
+    {
+      ProfScope ps(PK_STASH_REF, given ? 1 : 2, st);
+      GemmWork wp{meta, KIND_STASH_POL, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair};
+      typename Epi::Params epp{meta, part2, dz, L.cap_ref, s.V_local, L.ldz, ch * L.chunk_rows, 0};
+      int rc = launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHp, tmW256, tmW128, wp, epp, "stash_pol");
+      if (rc) return rc;
+      if (!given) {
+        GemmWork wf{meta, KIND_STASH_FRZ, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair};
+        typename Epi::Params epf{meta, part2, zr, L.cap_ref, s.V_local, L.ldz, ch * L.chunk_rows, 1};
+        return launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHf, tmWr256, tmWr128, wf, epf, "stash_frz");
+      }
+    }
+    return stash_given(ch, part2);
+  }
+  // the frozen model's logits are given (dpa_args_t::ref_logits): copy the chunk's rows + their statistics, no GEMM
+  int stash_given(int ch, float2* part2) {
+    StashGivenArgs g{meta, ch, L.chunk_rows, a->ref_logits, (long long)a->ref_logits_ld, at<int>(a->state, L.src_ref),
+                     at<int>(a->state, L.act_ref), zr, L.ldz, s.V_local, part2, L.cap_ref, L.ng_pair, kBnPair * kTpuPair};
+    ProfScope pg(PK_STASH_GIVEN, 1, st);
+    if (a->ref_logits_dtype == DPA_F32) stash_given_kernel<true><<<d->sms * 8, 256, 0, st>>>(g);
+    else stash_given_kernel<false><<<d->sms * 8, 256, 0, st>>>(g);
+    LAUNCH_CHECK("stash_given");
+    return DPA_OK;
   }
   // dH = dz W (rows scattered to their [s,t] positions) and, if lm_head is trainable, dW += dz^T H for chunk ch
   int grad_gemms(int ch) {
@@ -657,6 +688,7 @@ int forward_stats_impl(const dpa_args_t* a, cudaStream_t st, Layout& L, DeviceIn
   int rc = check_common(a, L, dev);
   if (rc) return rc;
   DeviceInfo* d = *dev;
+  if (a->ref_logits) return fail(DPA_ERR_ARG, "ref_logits is only available under DPA_FLAG_FUSED_GRAD");
   if (!a->scratch || a->scratch_bytes < L.fwd_total) return fail(DPA_ERR_WORKSPACE, "forward scratch: need %zu bytes, got %zu", L.fwd_total, a->scratch_bytes);
   if (!a->losses || !a->status) return fail(DPA_ERR_ARG, "losses/status is NULL");
   if ((rc = run_meta(a, L, d, st))) return rc;
@@ -683,17 +715,19 @@ int forward_fused_impl(const dpa_args_t* a, cudaStream_t st) {
   if (!(s.flags & DPA_FLAG_ROUND_LOGITS)) return fail(DPA_ERR_ARG, "DPA_FLAG_FUSED_GRAD needs DPA_FLAG_ROUND_LOGITS (the kept logits are bf16)");
   if (!a->scratch || a->scratch_bytes < L.fused_total) return fail(DPA_ERR_WORKSPACE, "fused scratch: need %zu bytes, got %zu", L.fused_total, a->scratch_bytes);
   if (!a->losses || !a->status) return fail(DPA_ERR_ARG, "losses/status is NULL");
-  if ((rc = check_grad_outputs(a))) return rc;
+  const bool loss_only = (s.flags & DPA_FLAG_LOSS_ONLY) != 0;      // evaluation: same chunked pass, no gradient GEMMs
+  if (!loss_only && (rc = check_grad_outputs(a))) return rc;
   Plan p(a, L, d, st);
   if ((rc = p.init(L.u_Hp, L.u_Hf, L.u_part_pair, L.u_part_ref, L.u_part_u, true, at<__nv_bfloat16>(a->scratch, L.u_dz),
-                   at<__nv_bfloat16>(a->scratch, L.u_zr), (s.flags & DPA_FLAG_NEED_DW) ? at<float>(a->scratch, L.u_dW32) : nullptr))) return rc;
+                   at<__nv_bfloat16>(a->scratch, L.u_zr),
+                   ((s.flags & DPA_FLAG_NEED_DW) && !loss_only) ? at<float>(a->scratch, L.u_dW32) : nullptr))) return rc;
 
   if ((rc = run_meta(a, L, d, st))) return rc;
   if ((rc = run_gather(a, L, d, a->scratch, L.u_Hp, L.u_Hf, st))) return rc;
-  if ((rc = p.zero_grad_outputs())) return rc;
+  if (!loss_only && (rc = p.zero_grad_outputs())) return rc;
 
   // ---- alignment half: statistics of every pair row -> P, N -> sigma, alignment loss -> row coefficients
-  if ((rc = p.fwd_pair<true>(L.chunk_rows))) return rc;       // nothing else touches chunk 0's dz buffer until its turn
+  if ((rc = p.fwd_pair<true>(loss_only ? 0 : L.chunk_rows))) return rc;   // nothing else touches chunk 0's dz buffer until its turn
   if ((rc = p.merge(RowRange{SEG_PAIR, 0, 0}, true))) return rc;
   if ((rc = run_finish_rows(a, L, d, st, RowRange{SEG_PAIR, 0, 0}))) return rc;
   if ((rc = run_losses(a, L, st, LOSS_ALIGN))) return rc;
@@ -701,7 +735,9 @@ int forward_fused_impl(const dpa_args_t* a, cudaStream_t st) {
 
   // ---- row chunks of the packed space [pair rows | reference-sample rows]
   for (int ch = 0; ch < L.n_chunks; ++ch) {
-    if (ch == 0) {
+    if (loss_only) {
+      // no dz of the pair rows is needed
+    } else if (ch == 0) {
       DzPairElemArgs e{p.meta, L.chunk_rows, p.dz, L.ldz, s.V_local, s.v_offset, at<int>(a->state, L.lab_pair),
                        at<float>(a->state, L.lse_pair), at<float>(a->state, L.coef_pair)};
       ProfScope ps(PK_DZ_ELEM, 1, st);
@@ -721,9 +757,10 @@ int forward_fused_impl(const dpa_args_t* a, cudaStream_t st) {
       dz_kl_elem_kernel<<<d->sms * 8, 256, 0, st>>>(e);
       LAUNCH_CHECK("dz_kl_elem");
     }
-    if ((rc = p.grad_gemms(ch))) return rc;
+    if (!loss_only && (rc = p.grad_gemms(ch))) return rc;
   }
   if ((rc = run_losses(a, L, st, LOSS_TOTAL))) return rc;
+  if (loss_only) return DPA_OK;
   if ((rc = run_norm_backward(a, L, d, st))) return rc;
   return p.finish_dW();
 }
@@ -733,6 +770,7 @@ int backward_scale_impl(const dpa_args_t* a, cudaStream_t st) {
   Layout L; DeviceInfo* d;
   int rc = check_common(a, L, &d);
   if (rc) return rc;
+  if (a->shape.flags & DPA_FLAG_LOSS_ONLY) return fail(DPA_ERR_ARG, "DPA_FLAG_LOSS_ONLY: the forward formed no gradients");
   if ((rc = check_grad_outputs(a))) return rc;
   if (!a->d_loss) return DPA_OK;                                 // NULL = 1
   const dpa_shape_t& s = a->shape;
@@ -805,6 +843,13 @@ int dpa_query_workspace(const dpa_shape_t* shape, dpa_workspace_t* out) {
   int rc = make_layout(*shape, L);
   if (rc) return rc;
   out->state_bytes = L.state_total; out->fwd_bytes = L.fwd_total; out->bwd_bytes = L.bwd_total; out->fused_bytes = L.fused_total;
+  return DPA_OK;
+}
+
+int dpa_struct_sizes(int* shape_bytes, int* workspace_bytes, int* args_bytes) {
+  if (shape_bytes) *shape_bytes = (int)sizeof(dpa_shape_t);
+  if (workspace_bytes) *workspace_bytes = (int)sizeof(dpa_workspace_t);
+  if (args_bytes) *args_bytes = (int)sizeof(dpa_args_t);
   return DPA_OK;
 }
 
@@ -937,7 +982,7 @@ int dpa_profile_collect(double* ms, int* launches, int n) {
 
 const char* dpa_profile_kind_name(int k) {
   static const char* names[PK_COUNT] = {"meta", "gather", "fwd_pair", "fwd_ref", "reduce", "coef", "dz_pair", "dz_ref", "dH", "dW", "misc",
-                                        "stash_ref", "dz_elem", "scale"};
+                                        "stash_ref", "dz_elem", "scale", "stash_given"};
   return (k >= 0 && k < PK_COUNT) ? names[k] : "";
 }
 

@@ -225,7 +225,8 @@ __global__ void gather_rows_kernel(GatherArgs a) {
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int vec = a.H / 8;                                 // uint4 per row
-  for (int r = wid; r < n_tot + nr_pad; r += warps) {
+  const int r_end = a.h_ref_frz ? n_tot + nr_pad : n_tot;    // (ref_logits given: no frozen hidden rows)
+  for (int r = wid; r < r_end; r += warps) {
     const uint4* src = nullptr; uint4* dst;
     const __nv_bfloat16* w = a.norm_w;
     if (r < p0) {
@@ -569,6 +570,83 @@ __global__ void __launch_bounds__(256) dz_kl_elem_kernel(DzElemArgs a) {
     }
     const float tot = block_sum(t, sh);
     if (threadIdx.x == 0) a.kl_row[j] = tot - a.kl_row[j];                 // sum_v q (z_r - z_p) - (LSE_r - LSE_p)
+  }
+}
+
+// ---- fused-gradient forward with the frozen model's logits GIVEN (dpa_args_t::ref_logits) instead of computed: what the
+//      stash_frz GEMM would have left for the chunk's reference-sample rows -- bf16 logits in zr and the per (row, column
+//      group) {max, sum-exp} partials -- read from the caller's [rows, V] tensor.  HBM-bound: 4 (fp32) or 2 (bf16) bytes
+//      read + 2 written per logit of an ACTIVE row; one block per row, one warp per column group (8 columns per lane and
+//      step, 256 contiguous columns per warp and step).
+struct StashGivenArgs {
+  const DpaMeta* meta; int chunk, chunk_rows;
+  const void* logits; long long ld;                 // [B_ref * T_ref][ld], column c = vocabulary id v_offset + c
+  const int* src_ref; const int* act_ref;           // indexed by reference row j
+  __nv_bfloat16* zr; int ldz, v_local;
+  float2* part; int row_cap, n_groups, group_cols;  // [n_groups][row_cap][2]: slot 1 = frozen model
+};
+template <bool F32>
+__global__ void __launch_bounds__(256) stash_given_kernel(StashGivenArgs a) {
+  const int p0 = a.meta->p0, n_tot = a.meta->n_tot;
+  const int c_lo = a.chunk * a.chunk_rows;
+  const int lo = max(c_lo, p0), hi = min(c_lo + a.chunk_rows, n_tot);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  constexpr int kSteps = 5;                          // 5 x 256 columns = one 1280-column group
+  for (int r = lo + blockIdx.x; r < hi; r += gridDim.x) {
+    const int j = r - p0;
+    if (!a.act_ref[j]) {                             // padding / ignored rows: finite dummies, never used (coef == 0)
+      for (int g = threadIdx.x; g < a.n_groups; g += blockDim.x) a.part[((size_t)g * a.row_cap + j) * 2 + 1] = make_float2(0.f, 1.f);
+      continue;
+    }
+    const size_t src = (size_t)a.src_ref[j] * (size_t)a.ld;
+    __nv_bfloat16* out = a.zr + (size_t)(r - c_lo) * a.ldz;
+    for (int g = warp; g < a.n_groups; g += nw) {
+      float v[kSteps * 8];
+      float m = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < kSteps; ++i) {
+        const int col = g * a.group_cols + i * 256 + lane * 8;
+        float* x = v + i * 8;
+        if (col + 8 <= a.v_local) {
+          if constexpr (F32) {
+            const float4* q = reinterpret_cast<const float4*>(static_cast<const float*>(a.logits) + src + col);
+            const float4 q0 = __ldg(q), q1 = __ldg(q + 1);
+            x[0] = q0.x; x[1] = q0.y; x[2] = q0.z; x[3] = q0.w; x[4] = q1.x; x[5] = q1.y; x[6] = q1.z; x[7] = q1.w;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x[k] = bf16_round_f32(x[k]);
+          } else {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(a.logits) + src + col));
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const float2 f = bf2_to_f2(w[k]); x[2 * k] = f.x; x[2 * k + 1] = f.y; }
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            float t = -INFINITY;
+            if (col + k < a.v_local) {
+              if constexpr (F32) t = bf16_round_f32(static_cast<const float*>(a.logits)[src + col + k]);
+              else t = __bfloat162float(static_cast<const __nv_bfloat16*>(a.logits)[src + col + k]);
+            }
+            x[k] = t;
+          }
+        }
+        if (col < a.v_local) {
+          float z[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { z[k] = (col + k < a.v_local) ? x[k] : 0.f; m = fmaxf(m, x[k]); }
+          *reinterpret_cast<uint4*>(out + col) = make_uint4(pack_bf16x2(z[0], z[1]), pack_bf16x2(z[2], z[3]),
+                                                           pack_bf16x2(z[4], z[5]), pack_bf16x2(z[6], z[7]));
+        }
+      }
+      for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      const float mb = m * kLog2e;
+      float ssum = 0.f;
+#pragma unroll
+      for (int i = 0; i < kSteps * 8; ++i) ssum += fast_exp2(fmaf(v[i], kLog2e, -mb));    // -inf (past v_local) -> 0
+      for (int o = 16; o; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+      if (lane == 0) a.part[((size_t)g * a.row_cap + j) * 2 + 1] = make_float2(m, ssum);
+    }
   }
 }
 

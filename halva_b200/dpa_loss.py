@@ -21,17 +21,31 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
-def _check_inputs(h_pair, labels_pair, signs_pair, h_ref_pol, h_ref_frozen, labels_ref, W, W_ref):
+def _check_inputs(h_pair, labels_pair, signs_pair, h_ref_pol, h_ref_frozen, labels_ref, W, W_ref, ref_logits=None):
     if h_pair.dim() != 3 or h_pair.shape[0] % 2:
         raise ValueError("h_pair must be [2B, T, H] (first B correct, last B hallucinated sequences)")
     if tuple(h_pair.shape[:2]) != tuple(labels_pair.shape) or tuple(labels_pair.shape) != tuple(signs_pair.shape):
         # same check and message as the reference raises at halva_trainer.py:398-399
         raise ValueError("Logits (batch and sequence length dim) and labels must have the same shape.")
-    if h_ref_pol.shape != h_ref_frozen.shape or tuple(h_ref_pol.shape[:2]) != tuple(labels_ref.shape):
+    if tuple(h_ref_pol.shape[:2]) != tuple(labels_ref.shape):
         raise ValueError("Logits (batch and sequence length dim) and labels must have the same shape.")
-    if W.dim() != 2 or W.shape != W_ref.shape or W.shape[1] != h_pair.shape[2] or h_ref_pol.shape[2] != h_pair.shape[2]:
-        raise ValueError("W / W_ref must be [V, H] with H matching the hidden states")
-    for name, t in (("h_pair", h_pair), ("h_ref_pol", h_ref_pol), ("h_ref_frozen", h_ref_frozen), ("W", W), ("W_ref", W_ref)):
+    if W.dim() != 2 or W.shape[1] != h_pair.shape[2] or h_ref_pol.shape[2] != h_pair.shape[2]:
+        raise ValueError("W must be [V, H] with H matching the hidden states")
+    frozen = ()
+    if ref_logits is not None:
+        if ref_logits.dim() != 3 or tuple(ref_logits.shape[:2]) != tuple(labels_ref.shape) or ref_logits.shape[2] != W.shape[0]:
+            raise ValueError("ref_logits must be [B_ref, T_ref, V] (the frozen reference model's logits on the reference sample)")
+        if not ref_logits.is_cuda:
+            raise DPAError(f"ref_logits is on {ref_logits.device}: the DPA-loss path is CUDA (sm_100a) only, there is no CPU fallback")
+        if ref_logits.dtype not in (torch.bfloat16, torch.float32):
+            raise TypeError("ref_logits must be bf16 or fp32")
+    else:
+        if h_ref_pol.shape != h_ref_frozen.shape:
+            raise ValueError("Logits (batch and sequence length dim) and labels must have the same shape.")
+        if W.shape != W_ref.shape:
+            raise ValueError("W / W_ref must be [V, H] with H matching the hidden states")
+        frozen = (("h_ref_frozen", h_ref_frozen), ("W_ref", W_ref))
+    for name, t in (("h_pair", h_pair), ("h_ref_pol", h_ref_pol), ("W", W)) + frozen:
         if not t.is_cuda:
             raise DPAError(f"{name} is on {t.device}: the DPA-loss path is CUDA (sm_100a) only, there is no CPU fallback")
         if t.dtype != torch.bfloat16:
@@ -47,17 +61,29 @@ class _Call:
     """Owns the ctypes argument block and the tensors it points to for one forward/backward pair."""
 
     def __init__(self, h_pair, labels_pair, signs_pair, h_ref_pol, h_ref_frozen, labels_ref, W, W_ref, alpha,
-                 round_logits, need_dW, dense, chunk_rows, v_offset, V_global, fused, norm=None):
+                 round_logits, need_dW, dense, chunk_rows, v_offset, V_global, fused, norm=None, ref_logits=None,
+                 loss_only=False):
         lib = _lib.load()
         self.lib = lib
         dev = h_pair.device
-        self.keep = [t.contiguous() for t in (h_pair, labels_pair, signs_pair, h_ref_pol, h_ref_frozen, labels_ref, W, W_ref)]
+        self.keep = [None if t is None else t.contiguous()
+                     for t in (h_pair, labels_pair, signs_pair, h_ref_pol, h_ref_frozen, labels_ref, W, W_ref)]
+        if ref_logits is not None:             # given instead of h_ref_frozen / W_ref; any row stride whose bytes % 16 == 0
+            esz = ref_logits.element_size()
+            if ref_logits.stride(2) != 1 or ref_logits.stride(0) != ref_logits.shape[1] * ref_logits.stride(1) or \
+                    (ref_logits.stride(1) * esz) % 16 or ref_logits.data_ptr() % 16:
+                Vg = ref_logits.shape[2]                               # odd vocabulary sizes: pad the row stride to 16 bytes
+                buf = torch.empty(*ref_logits.shape[:2], -(-Vg * esz // 16) * 16 // esz, dtype=ref_logits.dtype, device=dev)
+                buf[..., :Vg].copy_(ref_logits)
+                ref_logits = buf[..., :Vg]
+            self.keep.append(ref_logits)
         hp, lp, sp, hr, hf, lr, w, wr = self.keep[:8]
         B2, T, H = hp.shape
         Br, Tr, _ = hr.shape
         flags = (_lib.FLAG_ROUND_LOGITS if round_logits else 0) | (_lib.FLAG_NEED_DW if need_dW else 0) | \
                 (_lib.FLAG_DENSE if dense else 0) | (_lib.FLAG_FUSED_GRAD if fused else 0) | \
-                (_lib.FLAG_FUSED_NORM if norm is not None else 0)
+                (_lib.FLAG_FUSED_NORM if norm is not None else 0) | (_lib.FLAG_LOSS_ONLY if loss_only else 0)
+        self.loss_only = loss_only
         self.fused = fused
         self.lib_comm = False
         self.norm = None
@@ -82,7 +108,9 @@ class _Call:
                          state=_ptr(self.state), state_bytes=ws.state_bytes, scratch=None, scratch_bytes=0,
                          losses=_ptr(self.losses), status=_ptr(self.status), d_loss=None, dH_pair=None, dH_ref=None, dW=None,
                          norm_w=_ptr(self.norm[0]) if self.norm else None, norm_w_ref=_ptr(self.norm[1]) if self.norm else None,
-                         d_norm_w=None, norm_eps=self.norm[2] if self.norm else 0.0)
+                         d_norm_w=None, norm_eps=self.norm[2] if self.norm else 0.0,
+                         ref_logits=_ptr(ref_logits), ref_logits_ld=0 if ref_logits is None else ref_logits.stride(1),
+                         ref_logits_dtype=_lib.DPA_F32 if ref_logits is not None and ref_logits.dtype == torch.float32 else _lib.DPA_BF16)
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.state.device).cuda_stream)
@@ -105,7 +133,7 @@ class _Call:
         with torch.cuda.device(self.state.device):
             if self.fused:
                 # loss and (d_loss = 1) gradients in one pass; backward() only scales
-                self.grads = self._alloc_grads()
+                self.grads = None if self.loss_only else self._alloc_grads()
                 scratch = self._with_scratch(self.ws.fused_bytes)
                 _lib.check(self.lib.dpa_forward(C.byref(self.args), self._stream()), "dpa_forward[fused]")
                 del scratch
@@ -154,11 +182,15 @@ class DPALossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, h_pair, h_ref_pol, W, norm_w, labels_pair, signs_pair, labels_ref, h_ref_frozen, W_ref, alpha, round_logits,
-                need_dW, dense, chunk_rows, vocab_group, v_offset, V_global, fused, norm_w_ref, norm_eps):
-        fused = bool(fused and any(ctx.needs_input_grad[:4]))      # no gradient wanted (eval): statistics only
+                need_dW, dense, chunk_rows, vocab_group, v_offset, V_global, fused, norm_w_ref, norm_eps, ref_logits):
+        want_grad = any(ctx.needs_input_grad[:4])
+        loss_only = ref_logits is not None and not want_grad        # given logits live on the chunked (fused) forward only
+        fused = bool(fused and (want_grad or loss_only))            # no gradient wanted (eval): statistics only
         norm = None if norm_w is None else (norm_w.detach(), norm_w_ref.detach(), norm_eps, ctx.needs_input_grad[3])
-        call = _Call(h_pair.detach(), labels_pair, signs_pair, h_ref_pol.detach(), h_ref_frozen.detach(), labels_ref,
-                     W.detach(), W_ref.detach(), alpha, round_logits, need_dW, dense, chunk_rows, v_offset, V_global, fused, norm)
+        det = lambda t: None if t is None else t.detach()
+        call = _Call(h_pair.detach(), labels_pair, signs_pair, h_ref_pol.detach(), det(h_ref_frozen), labels_ref,
+                     W.detach(), det(W_ref), alpha, round_logits, need_dW and not loss_only, dense, chunk_rows, v_offset, V_global,
+                     fused, norm, det(ref_logits), loss_only)
         call.forward(vocab_group)
         ctx.call = call
         ctx.status_t = call.status
@@ -176,12 +208,13 @@ class DPALossFn(torch.autograd.Function):
             dist.all_reduce(dH_pair, group=ctx.vocab_group)      # partial sums over vocab shards
             dist.all_reduce(dH_ref, group=ctx.vocab_group)
         ctx.call = None
-        return (dH_pair, dH_ref, dW, dnw) + (None,) * 16
+        return (dH_pair, dH_ref, dW, dnw) + (None,) * 17
 
 
 def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.Tensor,
              h_ref_pol: torch.Tensor, labels_ref: torch.Tensor, W: torch.Tensor, *,
-             h_ref_frozen: torch.Tensor, W_ref: Optional[torch.Tensor] = None, alpha: float,
+             h_ref_frozen: Optional[torch.Tensor] = None, W_ref: Optional[torch.Tensor] = None,
+             ref_logits: Optional[torch.Tensor] = None, alpha: float,
              round_logits: bool = True, need_dW: Optional[bool] = None, dense: bool = False, chunk_rows: int = 0,
              vocab_group=None, v_offset: Optional[int] = None, vocab_size: Optional[int] = None,
              backward: str = "auto", norm_weight: Optional[torch.Tensor] = None,
@@ -198,6 +231,11 @@ def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.
     W            [V, H]   bf16     lm_head weight (or this rank's vocab shard with `vocab_group`)
     h_ref_frozen [Br,Tr,H] bf16    frozen reference model's hidden states on the reference sample
     W_ref        [V, H]            frozen lm_head (default: W itself, the LoRA recipe)
+    ref_logits   [Br,Tr,V] bf16/fp32  the frozen model's logits on the reference sample, given INSTEAD of h_ref_frozen /
+                                   W_ref (e.g. cached: the frozen pass of halva_trainer.py:576-578 does not depend on the
+                                   policy).  fp32 values are expected to be bf16-representable (`.float()` of a bf16
+                                   model's logits, :520) and are otherwise rounded to bf16.  Needs round_logits=True and
+                                   no vocab_group (served by the chunked "fused" pass; one lm_head GEMM less per row).
     alpha                          loss = align + alpha * div            (halva_trainer.py:590)
     round_logits                   True: round logits to bf16 before the fp32 softmax, exactly as the reference's
                                    bf16 nn.Linear does (modeling_llama.py:1028-1029); False: keep fp32 accumulators
@@ -219,8 +257,18 @@ def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.
     Ill-formed phrase ids (K_pos != K_neg, K == 0, id > 255) make the losses NaN and set bits in
     `read_status(loss)["status"]`; the reference raises / returns NaN there.
     """
-    W_ref = W if W_ref is None else W_ref
-    _check_inputs(h_pair, labels_pair, signs_pair, h_ref_pol, h_ref_frozen, labels_ref, W, W_ref)
+    if (ref_logits is None) == (h_ref_frozen is None):
+        raise ValueError("give exactly one of h_ref_frozen (+ W_ref) and ref_logits")
+    if ref_logits is not None:
+        if W_ref is not None:
+            raise ValueError("W_ref has no meaning together with ref_logits")
+        if not round_logits or vocab_group is not None or backward == "recompute":
+            raise ValueError("ref_logits needs round_logits=True, no vocab_group and the 'fused' (chunked) pass")
+        if norm_weight is not None and norm_weight_ref is None:
+            norm_weight_ref = norm_weight
+    else:
+        W_ref = W if W_ref is None else W_ref
+    _check_inputs(h_pair, labels_pair, signs_pair, h_ref_pol, h_ref_frozen, labels_ref, W, W_ref, ref_logits)
     if need_dW is None:
         need_dW = bool(W.requires_grad)
     if vocab_group is not None:
@@ -244,7 +292,7 @@ def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.
     fused = backward == "fused" or (backward == "auto" and round_logits and vocab_group is None)
     out = DPALossFn.apply(h_pair, h_ref_pol, W, norm_weight, labels_pair, signs_pair, labels_ref, h_ref_frozen, W_ref, float(alpha),
                           bool(round_logits), bool(need_dW), bool(dense), int(chunk_rows), vocab_group, int(v_offset),
-                          int(vocab_size), fused, norm_weight_ref, float(norm_eps))
+                          int(vocab_size), fused, norm_weight_ref, float(norm_eps), ref_logits)
     return out
 
 

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DPA_ABI_VERSION 3
+#define DPA_ABI_VERSION 4
 
 typedef enum {
   DPA_OK = 0,
@@ -51,7 +51,7 @@ typedef enum {
 #define DPA_STATUS_K_ZERO     4   /* no phrase at all: the reference returns NaN */
 #define DPA_STATUS_BAD_LABEL  8   /* an active label outside [0, V) */
 
-typedef enum { DPA_BF16 = 0 } dpa_dtype_t;
+typedef enum { DPA_BF16 = 0, DPA_F32 = 1 } dpa_dtype_t;   /* DPA_F32: ref_logits only */
 typedef enum { DPA_I64 = 0, DPA_I32 = 1 } dpa_index_t;
 
 #define DPA_FLAG_ROUND_LOGITS 1   /* round logits to bf16 before the fp32 softmax, as nn.Linear does in bf16 */
@@ -66,6 +66,8 @@ typedef enum { DPA_I64 = 0, DPA_I32 = 1 } dpa_index_t;
                                      RMSNorm (llava/model/language_model/modelling_llama.py:55-70: fp32 variance, cast back,
                                      weight multiply) is applied while the active rows are gathered, and its backward to
                                      the dH rows.  Needs norm_w / norm_w_ref / norm_eps. */
+#define DPA_FLAG_LOSS_ONLY    32  /* with DPA_FLAG_FUSED_GRAD: run the chunked forward for the losses only (evaluation,
+                                     torch.no_grad()): no gradient buffers needed, no gradient GEMMs */
 
 typedef struct {
   int32_t B;          /* sample pairs; h_pair holds 2B sequences, first B "pos"(correct), last B "neg"(hallucinated) */
@@ -117,11 +119,23 @@ typedef struct {
   const void* norm_w_ref;      /* [H] final-norm weight of the frozen reference model (may alias norm_w) */
   void* d_norm_w;              /* [H] gradient of norm_w, or NULL (frozen under the LoRA recipe) */
   float norm_eps;
+  /* Optional: the frozen reference model's logits on the reference sample, given instead of h_ref_frz / W_ref (both may
+   * then be NULL) -- e.g. logits cached from a previous pass of the frozen model (halva_trainer.py:576-578 runs it under
+   * no_grad every step).  Row (s, t) of the [B_ref * T_ref] rows starts at ref_logits + (s * T_ref + t) * ref_logits_ld
+   * elements; column c is vocabulary id v_offset + c, V_local columns are read.  bf16, or fp32 values that are
+   * bf16-representable (what `.float()` of a bf16 model's logits gives, halva_trainer.py:520; other fp32 values are
+   * rounded to bf16).  Only with DPA_FLAG_FUSED_GRAD (the chunked forward keeps bf16 logits anyway). */
+  const void* ref_logits;
+  int64_t ref_logits_ld;       /* row stride in elements; (ref_logits_ld * element size) % 16 == 0 */
+  int32_t ref_logits_dtype;    /* DPA_BF16 or DPA_F32 */
 } dpa_args_t;
 
 int dpa_version(void);
 const char* dpa_last_error(void);
 int dpa_query_workspace(const dpa_shape_t* shape, dpa_workspace_t* out);
+/* sizeof(dpa_shape_t), sizeof(dpa_workspace_t), sizeof(dpa_args_t) as this library was compiled: lets a binding written in
+ * another language (ctypes, cgo, JNI) check its mirror of the structs before the first real call */
+int dpa_struct_sizes(int* shape_bytes, int* workspace_bytes, int* args_bytes);
 
 /* forward: metadata + compaction + fused lm_head/log-softmax/gather/KL row statistics + loss assembly */
 int dpa_forward(const dpa_args_t* args, void* cuda_stream);

@@ -87,7 +87,8 @@ def rmsnorm_bwd(dy, x, w, n, r, mode):
 
 
 def dpa_loss(h_pair, labels_pair, signs_pair, h_ref_pol, h_ref_frz, labels_ref, W, W_ref, alpha,
-             mode="fp64", need_dW=True, grad_output=1.0, norm_w=None, norm_w_ref=None, norm_eps=1e-6, norm_mode=None):
+             mode="fp64", need_dW=True, grad_output=1.0, norm_w=None, norm_w_ref=None, norm_eps=1e-6, norm_mode=None,
+             ref_logits=None):
     """Forward + closed-form backward of compute_loss.
 
     h_pair [2B,T,H]: first B sequences "pos"(correct), last B "neg"(hallucinated)  (:485-487)
@@ -95,10 +96,14 @@ def dpa_loss(h_pair, labels_pair, signs_pair, h_ref_pol, h_ref_frz, labels_ref, 
     labels_ref [Br,Tr]; W/W_ref [V,H].
     mode: "fp64" exact maths on the given values; "bf16" additionally applies the reference's
     bf16 rounding points (inputs are expected to be bf16-representable already).
+    ref_logits [Br,Tr,V]: the frozen model's logits given directly (what reference_forward(self.ref_model, ...) returns
+    before its shift, :516-520) instead of h_ref_frz / W_ref, which may then be None.
     Returns dict(loss, align, div, P, N, dH_pair, dH_ref, dW, logp_pair, kl_rows).
     """
     rz = bf16_round if mode == "bf16" else (lambda a: a)
     f64 = lambda a: np.asarray(a, dtype=np.float64)
+    if ref_logits is not None:
+        h_ref_frz, W_ref = np.zeros_like(h_ref_pol), np.zeros_like(W)       # unused
     h_pair, h_ref_pol, h_ref_frz, W, W_ref = map(f64, (h_pair, h_ref_pol, h_ref_frz, W, W_ref))
     fused_norm = norm_w is not None
     norm_mode = mode if norm_mode is None else norm_mode    # "bf16": the norm's own rounding points even when the
@@ -143,7 +148,7 @@ def dpa_loss(h_pair, labels_pair, signs_pair, h_ref_pol, h_ref_frz, labels_ref, 
 
     # ---- divergence half (:571-588)
     zp = rz(h_ref_pol[:, :-1] @ W.T)
-    zr = rz(h_ref_frz[:, :-1] @ W_ref.T)
+    zr = rz(h_ref_frz[:, :-1] @ W_ref.T) if ref_logits is None else rz(f64(ref_logits)[:, :-1])
     vr = (labels_ref[:, 1:] != IGNORE)
     lp, lr = _lse(zp), _lse(zr)
     logq = zr - lr[..., None]

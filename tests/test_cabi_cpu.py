@@ -25,7 +25,15 @@ def test_exports_match_header():
     for name in declared:
         assert hasattr(lib, name), name
     from halva_b200._lib import ABI_VERSION
-    assert lib.dpa_version() == ABI_VERSION == 3
+    assert lib.dpa_version() == ABI_VERSION == 4
+
+
+def test_ctypes_structs_mirror_the_header():
+    from halva_b200._lib import Args, Shape, Workspace
+    lib = _lib()
+    a, b, c = C.c_int(), C.c_int(), C.c_int()
+    assert lib.dpa_struct_sizes(C.byref(a), C.byref(b), C.byref(c)) == 0
+    assert (a.value, b.value, c.value) == (C.sizeof(Shape), C.sizeof(Workspace), C.sizeof(Args))
 
 
 def test_workspace_query_and_shape_validation():
