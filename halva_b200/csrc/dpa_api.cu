@@ -101,10 +101,15 @@ int make_operand_tmap(const DeviceInfo* d, CUtensorMap* tm, const void* ptr, int
   return make_tmap(d, tm, ptr, mn_extent, k_extent, ld_elems * 2, 64, BK);
 }
 
+template <class Cfg, class Epi> constexpr auto gemm_kernel_of() {
+  if constexpr (Cfg::NSEG == 1) return dpa_gemm_kernel<Cfg, Epi>; else return dpa_gemm_split_kernel<Cfg, Epi>;
+}
+// sm: tensor maps of the mid / lo operand parts, only for Cfg::NSEG == 6 (split-bf16 operands of the fp32 path)
 template <class Cfg, class Epi>
 int launch_gemm(cudaStream_t st, int sms, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA2,
-                const CUtensorMap& tmB2, const GemmWork& work, const typename Epi::Params& ep, const char* what) {
-  auto kern = dpa_gemm_kernel<Cfg, Epi>;
+                const CUtensorMap& tmB2, const GemmWork& work, const typename Epi::Params& ep, const char* what,
+                const SplitMaps* sm = nullptr) {
+  auto kern = gemm_kernel_of<Cfg, Epi>();
   static std::once_flag once[16];
   int dev = 0; cudaGetDevice(&dev);
   cudaError_t attr_err = cudaSuccess;
@@ -132,7 +137,9 @@ int launch_gemm(cudaStream_t st, int sms, const CUtensorMap& tmA, const CUtensor
     }
     cfg.gridDim = dim3((unsigned)(std::min(sms / Cfg::CG, max_clusters[dev & 15]) * Cfg::CG));
   }
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmA2, tmB2, work, ep);
+  cudaError_t e;
+  if constexpr (Cfg::NSEG == 1) e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmA2, tmB2, work, ep);
+  else e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmA2, tmB2, *sm, work, ep);
   if (e != cudaSuccess) return fail(DPA_ERR_CUDA, "launch %s: %s", what, cudaGetErrorString(e));
   return DPA_OK;
 }
@@ -183,6 +190,10 @@ struct Layout {
   size_t f_Hp, f_Hf, f_part_pair, f_part_ref, f_part_u, f_gather, fwd_total;
   // backward scratch offsets
   size_t b_Hp, b_Hf, b_dz, b_dW32, b_dHp, bwd_total;
+  // fp32 inputs (split-bf16 operands): Hp / Hf / dz hold three parts (hi, mid, lo) one after the other, and the lm_head
+  // weights are split into scratch as well (three parts each)
+  struct Split { size_t W3, Wr3; } f_split, b_split;
+  bool split;
   // fused-gradient forward scratch offsets (DPA_FLAG_FUSED_GRAD)
   size_t u_Hp, u_Hf, u_part_pair, u_part_ref, u_part_u, u_dz, u_zr, u_dW32, fused_total;
 };
@@ -194,7 +205,11 @@ int make_layout(const dpa_shape_t& s, Layout& L) {
   if (s.H < 64 || s.H % 64) return fail(DPA_ERR_BAD_SHAPE, "H=%d must be a positive multiple of 64", s.H);
   if (s.V_local < 1) return fail(DPA_ERR_BAD_SHAPE, "V_local=%d must be positive", s.V_local);
   if (s.v_offset < 0 || s.v_offset + s.V_local > s.V) return fail(DPA_ERR_BAD_SHAPE, "vocab shard [%d,%d) outside V=%d", s.v_offset, s.v_offset + s.V_local, s.V);
-  if (s.dtype != DPA_BF16) return fail(DPA_ERR_DTYPE, "only bf16 hidden states / weights are supported by the tensor-core path");
+  if (s.dtype != DPA_BF16 && s.dtype != DPA_F32) return fail(DPA_ERR_DTYPE, "hidden states / weights must be bf16 or fp32");
+  L.split = s.dtype == DPA_F32;
+  if (L.split && (s.flags & (DPA_FLAG_ROUND_LOGITS | DPA_FLAG_FUSED_GRAD | DPA_FLAG_FUSED_NORM)))
+    return fail(DPA_ERR_ARG, "fp32 inputs: DPA_FLAG_ROUND_LOGITS / FUSED_GRAD / FUSED_NORM describe the bf16 execution and are not available");
+  if (L.split && comm_world > 1 && s.V_local < s.V) return fail(DPA_ERR_ARG, "fp32 inputs are not available with the library-side vocab-parallel exchange");
   if (s.index_dtype != DPA_I64 && s.index_dtype != DPA_I32) return fail(DPA_ERR_DTYPE, "labels/signs must be int64 or int32");
   if ((long long)2 * s.B * s.T >= (1ll << 31) / 2 || 2 * s.B >= 32768) return fail(DPA_ERR_BAD_SHAPE, "batch too large for 32-bit row ids");
   L.n_pos_pair = 2 * s.B * (s.T - 1);
@@ -234,21 +249,29 @@ int make_layout(const dpa_shape_t& s, Layout& L) {
   L.dnw32 = take((size_t)s.H * 4);                //                      fp32 accumulator of d_norm_w
   L.state_total = o;
 
+  const size_t parts = L.split ? 3 : 1;
   o = 0;
-  L.f_Hp = take((size_t)cap_tot * s.H * 2);
-  L.f_Hf = take((size_t)L.cap_ref * s.H * 2);
+  L.f_Hp = take(parts * cap_tot * s.H * 2);
+  L.f_Hf = take(parts * L.cap_ref * s.H * 2);
   L.f_part_pair = take((size_t)L.ng_pair * L.cap_pair * 16);
   L.f_part_ref = take((size_t)L.ng_ref * L.cap_ref * 16);
   L.f_part_u = take((size_t)L.ng_ref * L.cap_ref * 4);
+  auto take_split = [&](Layout::Split& sp) {
+    sp = Layout::Split{};
+    if (!L.split) return;
+    sp.W3 = take((size_t)3 * s.V_local * s.H * 2); sp.Wr3 = take((size_t)3 * s.V_local * s.H * 2);
+  };
+  take_split(L.f_split);
   L.f_gather = o;                       // records of all vocab shards when the library's own communicator exchanges them
   if (comm_world > 1 && s.V_local < s.V) take((size_t)comm_world * L.row_stats_bytes);
   L.fwd_total = o;
 
   o = 0;
-  L.b_Hp = take((size_t)cap_tot * s.H * 2);
-  L.b_Hf = take((size_t)L.cap_ref * s.H * 2);
-  L.b_dz = take((size_t)L.chunk_rows * L.ldz * 2);
-  L.b_dW32 = (s.flags & DPA_FLAG_NEED_DW) ? take((size_t)s.V_local * s.H * 4) : o;
+  L.b_Hp = take(parts * cap_tot * s.H * 2);
+  L.b_Hf = take(parts * L.cap_ref * s.H * 2);
+  L.b_dz = take(parts * L.chunk_rows * L.ldz * 2);
+  L.b_dW32 = ((s.flags & DPA_FLAG_NEED_DW) && !L.split) ? take((size_t)s.V_local * s.H * 4) : o;   // fp32: dW itself accumulates
+  take_split(L.b_split);
   // library-side vocab-parallel exchange: dH partial sums stay packed (active rows only) for the all-reduce
   L.b_dHp = (comm_world > 1 && s.V_local < s.V) ? take((size_t)cap_tot * s.H * 2) : o;
   L.bwd_total = o;
@@ -320,6 +343,16 @@ MetaArgs meta_args(const dpa_args_t* a, const Layout& L) {
 }
 
 int run_gather(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, void* scratch, size_t oHp, size_t oHf, cudaStream_t st) {
+  if (L.split) {            // fp32 inputs: packed rows as split-bf16 pairs
+    GatherSplitArgs g{at<DpaMeta>(a->state, L.meta), at<int>(a->state, L.src_pair), at<int>(a->state, L.src_ref),
+                      static_cast<const float*>(a->h_pair), static_cast<const float*>(a->h_ref_pol), static_cast<const float*>(a->h_ref_frz),
+                      at<__nv_bfloat16>(scratch, oHp), (size_t)(L.cap_pair + L.cap_ref) * a->shape.H,
+                      at<__nv_bfloat16>(scratch, oHf), (size_t)L.cap_ref * a->shape.H, a->shape.H};
+    ProfScope ps(PK_GATHER, 1, st);
+    gather_rows_split_kernel<<<d->sms * 8, 256, 0, st>>>(g);
+    LAUNCH_CHECK("gather_rows_split");
+    return DPA_OK;
+  }
   GatherArgs g{};
   g.meta = at<DpaMeta>(a->state, L.meta);
   g.src_pair = at<int>(a->state, L.src_pair); g.src_ref = at<int>(a->state, L.src_ref);
@@ -333,6 +366,17 @@ int run_gather(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, void* 
   if (a->shape.flags & DPA_FLAG_FUSED_NORM) gather_rows_kernel<true><<<d->sms * 8, 256, 0, st>>>(g);
   else gather_rows_kernel<false><<<d->sms * 8, 256, 0, st>>>(g);
   LAUNCH_CHECK("gather_rows");
+  return DPA_OK;
+}
+
+// fp32 inputs: lm_head weights -> split-bf16 triples in scratch (W_ref shares W's when it aliases W)
+int run_split_weights(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, const Layout::Split& sp, cudaStream_t st) {
+  const size_t n = (size_t)a->shape.V_local * a->shape.H;
+  const bool alias = a->W_ref == a->W;
+  ProfScope ps(PK_GATHER, alias ? 1 : 2, st);
+  split_f32_kernel<<<d->sms * 8, 256, 0, st>>>(static_cast<const float*>(a->W), at<__nv_bfloat16>(a->scratch, sp.W3), n);
+  if (!alias) split_f32_kernel<<<d->sms * 8, 256, 0, st>>>(static_cast<const float*>(a->W_ref), at<__nv_bfloat16>(a->scratch, sp.Wr3), n);
+  LAUNCH_CHECK("split_weights");
   return DPA_OK;
 }
 
@@ -537,14 +581,18 @@ struct Plan {
   __nv_bfloat16* dH_packed = nullptr;     // vocab-parallel with the library's communicator: dH rows stay packed until reduced
   float4* part_pair = nullptr; float4* part_ref = nullptr; float* part_u = nullptr;
   CUtensorMap tmHp, tmHf, tmW256, tmW128, tmW64, tmWr256, tmWr128, tmWr64, tmDzK, tmWmn, tmDzMN, tmHpMN;
+  // fp32 inputs: the maps above cover the high-order bf16 parts (in scratch), these the mid ([0]) and low-order ([1]) parts
+  const Layout::Split* split = nullptr;
+  size_t dz_part = 0;                      // elements between the hi / mid / lo copies of dz
+  CUtensorMap tmHpS[2], tmHfS[2], tmW128S[2], tmW64S[2], tmWr64S[2], tmDzKS[2], tmWmnS[2], tmDzMNS[2], tmHpMNS[2];
 
   Plan(const dpa_args_t* a_, const Layout& L_, const DeviceInfo* d_, cudaStream_t st_)
       : a(a_), L(L_), d(d_), st(st_), s(a_->shape), meta(at<DpaMeta>(a_->state, L_.meta)) {}
 
   int init(size_t oHp, size_t oHf, size_t oPartPair, size_t oPartRef, size_t oPartU, bool has_parts, __nv_bfloat16* dz_, __nv_bfloat16* zr_,
-           float* dW32_) {
+           float* dW32_, const Layout::Split* split_ = nullptr) {
     const int cap_tot = L.cap_pair + L.cap_ref;
-    dz = dz_; zr = zr_; dW32 = dW32_;
+    dz = dz_; zr = zr_; dW32 = dW32_; split = split_;
     if (has_parts) {
       part_pair = at<float4>(a->scratch, oPartPair); part_ref = at<float4>(a->scratch, oPartRef); part_u = at<float>(a->scratch, oPartU);
     }
@@ -553,25 +601,60 @@ struct Plan {
     if ((rc = make_operand_tmap(d, &tmHp, Hp, KMAJOR, cap_tot, s.H, s.H, BM))) return rc;
     const bool frozen = a->h_ref_frz && a->W_ref;      // false: the frozen model's logits are given (ref_logits)
     if (frozen && (rc = make_operand_tmap(d, &tmHf, at<char>(a->scratch, oHf), KMAJOR, L.cap_ref, s.H, s.H, BM))) return rc;
+    // the bf16 lm_head operands: the caller's tensors, or (fp32 inputs) the high-order halves split into scratch
+    const bool alias = a->W_ref == a->W;
+    const size_t w_part = (size_t)s.V_local * s.H * 2;                     // bytes between the parts of a split weight
+    const char* W3 = split ? at<char>(a->scratch, split->W3) : nullptr;
+    const char* Wr3 = split ? at<char>(a->scratch, alias ? split->W3 : split->Wr3) : nullptr;
+    const void* Wb = split ? W3 : a->W;
+    const void* Wrb = split ? Wr3 : a->W_ref;
     // lm_head rows as the K-major B operand: boxes of 256 (single CTA), 128 (CTA pair / dual single CTA), 64 (dual pair)
-    if ((rc = make_operand_tmap(d, &tmW256, a->W, KMAJOR, s.V_local, s.H, s.H, 256))) return rc;
-    if ((rc = make_operand_tmap(d, &tmW128, a->W, KMAJOR, s.V_local, s.H, s.H, 128))) return rc;
-    if ((rc = make_operand_tmap(d, &tmW64, a->W, KMAJOR, s.V_local, s.H, s.H, 64))) return rc;
+    if ((rc = make_operand_tmap(d, &tmW256, Wb, KMAJOR, s.V_local, s.H, s.H, 256))) return rc;
+    if ((rc = make_operand_tmap(d, &tmW128, Wb, KMAJOR, s.V_local, s.H, s.H, 128))) return rc;
+    if ((rc = make_operand_tmap(d, &tmW64, Wb, KMAJOR, s.V_local, s.H, s.H, 64))) return rc;
     if (frozen) {
-      if ((rc = make_operand_tmap(d, &tmWr256, a->W_ref, KMAJOR, s.V_local, s.H, s.H, 256))) return rc;
-      if ((rc = make_operand_tmap(d, &tmWr128, a->W_ref, KMAJOR, s.V_local, s.H, s.H, 128))) return rc;
-      if ((rc = make_operand_tmap(d, &tmWr64, a->W_ref, KMAJOR, s.V_local, s.H, s.H, 64))) return rc;
+      if ((rc = make_operand_tmap(d, &tmWr256, Wrb, KMAJOR, s.V_local, s.H, s.H, 256))) return rc;
+      if ((rc = make_operand_tmap(d, &tmWr128, Wrb, KMAJOR, s.V_local, s.H, s.H, 128))) return rc;
+      if ((rc = make_operand_tmap(d, &tmWr64, Wrb, KMAJOR, s.V_local, s.H, s.H, 64))) return rc;
     }
     if (dz) {
       // dH = dZ[rows x V] * W[V x H]:      A = dz K-major (K = vocab),  B = W MN-major (N = hidden contiguous)
       // dW = dZ^T[V x rows] * H[rows x H]: A = dz MN-major (M = vocab), B = packed hidden rows MN-major
       if ((rc = make_operand_tmap(d, &tmDzK, dz, KMAJOR, L.chunk_rows, s.V_local, L.ldz, BM))) return rc;
-      if ((rc = make_operand_tmap(d, &tmWmn, a->W, MNMAJOR, s.H, s.V_local, s.H, 0))) return rc;
+      if ((rc = make_operand_tmap(d, &tmWmn, Wb, MNMAJOR, s.H, s.V_local, s.H, 0))) return rc;
       if ((rc = make_operand_tmap(d, &tmDzMN, dz, MNMAJOR, s.V_local, L.chunk_rows, L.ldz, 0))) return rc;
       if ((rc = make_operand_tmap(d, &tmHpMN, Hp, MNMAJOR, s.H, cap_tot, s.H, 0))) return rc;
     }
+    if (split) {
+      const size_t hp_part = (size_t)cap_tot * s.H * 2, hf_part = (size_t)L.cap_ref * s.H * 2;
+      dz_part = (size_t)L.chunk_rows * L.ldz;
+      for (int p = 0; p < 2; ++p) {
+        char* HpP = Hp + (p + 1) * hp_part;
+        const char* WP = W3 + (p + 1) * w_part;
+        if ((rc = make_operand_tmap(d, &tmHpS[p], HpP, KMAJOR, cap_tot, s.H, s.H, BM))) return rc;
+        if ((rc = make_operand_tmap(d, &tmHfS[p], at<char>(a->scratch, oHf) + (p + 1) * hf_part, KMAJOR, L.cap_ref, s.H, s.H, BM))) return rc;
+        if ((rc = make_operand_tmap(d, &tmW128S[p], WP, KMAJOR, s.V_local, s.H, s.H, 128))) return rc;
+        if ((rc = make_operand_tmap(d, &tmW64S[p], WP, KMAJOR, s.V_local, s.H, s.H, 64))) return rc;
+        if ((rc = make_operand_tmap(d, &tmWr64S[p], Wr3 + (p + 1) * w_part, KMAJOR, s.V_local, s.H, s.H, 64))) return rc;
+        if (dz) {
+          __nv_bfloat16* dzP = dz + (p + 1) * dz_part;
+          if ((rc = make_operand_tmap(d, &tmDzKS[p], dzP, KMAJOR, L.chunk_rows, s.V_local, L.ldz, BM))) return rc;
+          if ((rc = make_operand_tmap(d, &tmWmnS[p], WP, MNMAJOR, s.H, s.V_local, s.H, 0))) return rc;
+          if ((rc = make_operand_tmap(d, &tmDzMNS[p], dzP, MNMAJOR, s.V_local, L.chunk_rows, L.ldz, 0))) return rc;
+          if ((rc = make_operand_tmap(d, &tmHpMNS[p], HpP, MNMAJOR, s.H, cap_tot, s.H, 0))) return rc;
+        }
+      }
+    }
     return DPA_OK;
   }
+  static SplitMaps split_maps(const CUtensorMap (&A)[2], const CUtensorMap (&B)[2], const CUtensorMap (&A2)[2], const CUtensorMap (&B2)[2]) {
+    SplitMaps m;
+    for (int p = 0; p < 2; ++p) { m.A[p] = A[p]; m.B[p] = B[p]; m.A2[p] = A2[p]; m.B2[p] = B2[p]; }
+    return m;
+  }
+  // split-bf16 GEMM configurations (fp32 inputs): always CTA pairs
+  template <int AMAJ, int BMAJ> using SplitCfg = GemmCfg<256, false, AMAJ, BMAJ, 2, 6>;
+  using SplitDualCfg = GemmCfg<128, true, KMAJOR, KMAJOR, 2, 6>;
 
   // statistics of every pair row; store_rows > 0 also keeps the bf16 logits of the first store_rows packed rows in dz
   template <bool ROUND> int fwd_pair(int store_rows) {
@@ -580,6 +663,10 @@ struct Plan {
     typename Epi::Params ep{at<int>(a->state, L.lab_pair), part_pair, L.cap_pair, s.V_local, s.v_offset,
                             store_rows > 0 ? dz : nullptr, L.ldz, store_rows};
     ProfScope ps(PK_FWD_PAIR, 1, st);
+    if (split) {
+      const SplitMaps sm = split_maps(tmHpS, tmW128S, tmHpS, tmW128S);
+      return launch_gemm<SplitCfg<KMAJOR, KMAJOR>, Epi>(st, d->sms, tmHp, tmW128, tmHp, tmW128, w, ep, "fwd_pair[split]", &sm);
+    }
     return launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHp, tmW256, tmW128, w, ep, "fwd_pair");
   }
   // policy + frozen logits of every reference-sample row side by side: statistics incl. the KL numerator
@@ -588,6 +675,10 @@ struct Plan {
     GemmWork w{meta, KIND_FWD_REF, 0, 0, 0, s.V_local, s.H, kTpuRef};
     typename Epi::Params ep{part_ref, part_u, L.cap_ref, s.V_local};
     ProfScope ps(PK_FWD_REF, 1, st);
+    if (split) {
+      const SplitMaps sm = split_maps(tmHpS, tmW64S, tmHfS, tmWr64S);
+      return launch_gemm<SplitDualCfg, Epi>(st, d->sms, tmHp, tmW64, tmHf, tmWr64, w, ep, "fwd_ref[split]", &sm);
+    }
     return launch_dual<Epi>(st, d, tmHp, tmHf, tmW128, tmWr128, tmW64, tmWr64, w, ep, "fwd_ref");
   }
   // recompute the pair rows of chunk ch -> dz
@@ -595,8 +686,16 @@ struct Plan {
     using Epi = EpiDzPair<kBnPair, ROUND>;
     GemmWork w{meta, KIND_DZ_PAIR, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair};
     typename Epi::Params ep{at<int>(a->state, L.lab_pair), at<float>(a->state, L.lse_pair), at<float>(a->state, L.coef_pair),
-                            dz, L.ldz, ch * L.chunk_rows, s.V_local, s.v_offset};
+                            dz, L.ldz, ch * L.chunk_rows, s.V_local, s.v_offset, 0};
     ProfScope ps(PK_DZ_PAIR, 1, st);
+    if constexpr (!ROUND) {
+      if (split) {
+        using EpiS = EpiDzPair<kBnPair, false, true>;
+        typename EpiS::Params eps{ep.labels, ep.lse, ep.coef, dz, L.ldz, ch * L.chunk_rows, s.V_local, s.v_offset, dz_part};
+        const SplitMaps sm = split_maps(tmHpS, tmW128S, tmHpS, tmW128S);
+        return launch_gemm<SplitCfg<KMAJOR, KMAJOR>, EpiS>(st, d->sms, tmHp, tmW128, tmHp, tmW128, w, eps, "dz_pair[split]", &sm);
+      }
+    }
     return launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHp, tmW256, tmW128, w, ep, "dz_pair");
   }
   // recompute the reference-sample rows of chunk ch (both models) -> dz
@@ -604,8 +703,16 @@ struct Plan {
     using Epi = EpiDzRef<kBnRef, ROUND>;
     GemmWork w{meta, KIND_DZ_REF, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuRef};
     typename Epi::Params ep{meta, at<float>(a->state, L.lse_ref_p), at<float>(a->state, L.lse_ref_r), at<float>(a->state, L.coef_ref),
-                            dz, L.ldz, ch * L.chunk_rows, s.V_local};
+                            dz, L.ldz, ch * L.chunk_rows, s.V_local, 0};
     ProfScope ps(PK_DZ_REF, 1, st);
+    if constexpr (!ROUND) {
+      if (split) {
+        using EpiS = EpiDzRef<kBnRef, false, true>;
+        typename EpiS::Params eps{meta, ep.lse_p, ep.lse_r, ep.coef, dz, L.ldz, ch * L.chunk_rows, s.V_local, dz_part};
+        const SplitMaps sm = split_maps(tmHpS, tmW64S, tmHfS, tmWr64S);
+        return launch_gemm<SplitDualCfg, EpiS>(st, d->sms, tmHp, tmW64, tmHf, tmWr64, w, eps, "dz_ref[split]", &sm);
+      }
+    }
     return launch_dual<Epi>(st, d, tmHp, tmHf, tmW128, tmWr128, tmW64, tmWr64, w, ep, "dz_ref");
   }
   // fused-gradient forward: policy and frozen logits of chunk ch's reference-sample rows: statistics + the bf16 logits
@@ -639,6 +746,27 @@ struct Plan {
   }
   // dH = dz W (rows scattered to their [s,t] positions) and, if lm_head is trainable, dW += dz^T H for chunk ch
   int grad_gemms(int ch) {
+    if (split) {              // fp32 inputs: split-bf16 dz and operands, fp32 gradients; dW accumulates in place
+      {
+        using Epi = EpiStoreRows<256, float>;
+        GemmWork w{meta, KIND_DH, ch, L.chunk_rows, 0, s.H, s.V_local, 1};
+        typename Epi::Params ep{meta, at<int>(a->state, L.src_pair), at<int>(a->state, L.src_ref),
+                                static_cast<float*>(a->dH_pair), static_cast<float*>(a->dH_ref), s.H, nullptr};
+        const SplitMaps sm = split_maps(tmDzKS, tmWmnS, tmDzKS, tmWmnS);
+        ProfScope ps(PK_DH, 1, st);
+        int rc = launch_gemm<SplitCfg<KMAJOR, MNMAJOR>, Epi>(st, d->sms, tmDzK, tmWmn, tmDzK, tmWmn, w, ep, "dH[split]", &sm);
+        if (rc) return rc;
+      }
+      if (s.flags & DPA_FLAG_NEED_DW) {
+        using Epi = EpiAccumF32<256>;
+        GemmWork w{meta, KIND_DW, ch, L.chunk_rows, s.V_local, s.H, 0, 1};
+        typename Epi::Params ep{static_cast<float*>(a->dW), s.H, s.V_local, s.H, ch > 0};
+        const SplitMaps sm = split_maps(tmDzMNS, tmHpMNS, tmDzMNS, tmHpMNS);
+        ProfScope ps(PK_DW, 1, st);
+        return launch_gemm<SplitCfg<MNMAJOR, MNMAJOR>, Epi>(st, d->sms, tmDzMN, tmHpMN, tmDzMN, tmHpMN, w, ep, "dW[split]", &sm);
+      }
+      return DPA_OK;
+    }
     {
       using Epi = EpiStoreRows<256>;
       GemmWork w{meta, KIND_DH, ch, L.chunk_rows, 0, s.H, s.V_local, 1};
@@ -659,14 +787,15 @@ struct Plan {
   }
   int zero_grad_outputs() {
     ProfScope ps(PK_MISC, 0, st);
-    CUDA_TRY(cudaMemsetAsync(a->dH_pair, 0, (size_t)2 * s.B * s.T * s.H * 2, st));
-    CUDA_TRY(cudaMemsetAsync(a->dH_ref, 0, (size_t)s.B_ref * s.T_ref * s.H * 2, st));
+    const size_t es = split ? 4 : 2;
+    CUDA_TRY(cudaMemsetAsync(a->dH_pair, 0, (size_t)2 * s.B * s.T * s.H * es, st));
+    CUDA_TRY(cudaMemsetAsync(a->dH_ref, 0, (size_t)s.B_ref * s.T_ref * s.H * es, st));
     return DPA_OK;      // (the dW accumulator needs no memset: the first chunk's epilogue overwrites it)
   }
   int finish_dW() {
-    if (!dW32) return DPA_OK;
-    ProfScope ps(PK_MISC, 1, st);      // the last chunk with rows wrote dW in bf16; only the no-rows-at-all case is left
-    zero_if_no_rows_kernel<<<d->sms * 2, 256, 0, st>>>(meta, static_cast<__nv_bfloat16*>(a->dW), (size_t)s.V_local * s.H);
+    if (!(s.flags & DPA_FLAG_NEED_DW) || !a->dW) return DPA_OK;
+    ProfScope ps(PK_MISC, 1, st);      // the last chunk with rows wrote dW; only the no-rows-at-all case is left
+    zero_if_no_rows_kernel<<<d->sms * 2, 256, 0, st>>>(meta, a->dW, (size_t)s.V_local * s.H * (split ? 4 : 2));
     LAUNCH_CHECK("dW zero-if-empty");
     return DPA_OK;
   }
@@ -692,9 +821,11 @@ int forward_stats_impl(const dpa_args_t* a, cudaStream_t st, Layout& L, DeviceIn
   if (!a->scratch || a->scratch_bytes < L.fwd_total) return fail(DPA_ERR_WORKSPACE, "forward scratch: need %zu bytes, got %zu", L.fwd_total, a->scratch_bytes);
   if (!a->losses || !a->status) return fail(DPA_ERR_ARG, "losses/status is NULL");
   if ((rc = run_meta(a, L, d, st))) return rc;
+  const Layout::Split* sp = L.split ? &L.f_split : nullptr;
   if ((rc = run_gather(a, L, d, a->scratch, L.f_Hp, L.f_Hf, st))) return rc;
+  if (sp && (rc = run_split_weights(a, L, d, *sp, st))) return rc;
   Plan p(a, L, d, st);
-  if ((rc = p.init(L.f_Hp, L.f_Hf, L.f_part_pair, L.f_part_ref, L.f_part_u, true, nullptr, nullptr, nullptr))) return rc;
+  if ((rc = p.init(L.f_Hp, L.f_Hf, L.f_part_pair, L.f_part_ref, L.f_part_u, true, nullptr, nullptr, nullptr, sp))) return rc;
   const bool round = (a->shape.flags & DPA_FLAG_ROUND_LOGITS) != 0;
   if ((rc = round ? p.fwd_pair<true>(0) : p.fwd_pair<false>(0))) return rc;
   if ((rc = round ? p.fwd_ref<true>() : p.fwd_ref<false>())) return rc;
@@ -792,8 +923,9 @@ int run_backward(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, cuda
   const dpa_shape_t& s = a->shape;
   int rc;
   Plan p(a, L, d, st);
+  const Layout::Split* sp = L.split ? &L.b_split : nullptr;
   if ((rc = p.init(L.b_Hp, L.b_Hf, 0, 0, 0, false, at<__nv_bfloat16>(a->scratch, L.b_dz), nullptr,
-                   (s.flags & DPA_FLAG_NEED_DW) ? at<float>(a->scratch, L.b_dW32) : nullptr))) return rc;
+                   ((s.flags & DPA_FLAG_NEED_DW) && !sp) ? at<float>(a->scratch, L.b_dW32) : nullptr, sp))) return rc;
   // Vocab-parallel with the library's own communicator: the dH partial sums of this rank's vocabulary shard stay packed
   // (active rows only -- a quarter of the dense tensors at 10 % phrase density), are all-reduced chunk by chunk and
   // scattered at the end.  The all-reduce count is a host value, so this (optional) mode reads the active row count
@@ -807,6 +939,7 @@ int run_backward(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, cuda
   }
   if ((rc = p.coef(a->d_loss))) return rc;
   if ((rc = run_gather(a, L, d, a->scratch, L.b_Hp, L.b_Hf, st))) return rc;
+  if (sp && (rc = run_split_weights(a, L, d, *sp, st))) return rc;
   if ((rc = p.zero_grad_outputs())) return rc;
   for (int ch = 0; ch < L.n_chunks; ++ch) {
     if (vp && (long long)ch * L.chunk_rows >= n_tot_host) break;

@@ -116,8 +116,22 @@ __device__ __forceinline__ TileRange compute_range(const GemmWork& w) {
   return r;
 }
 
-template <int BN_, bool DUAL_, int AMAJ_, int BMAJ_, int CG_ = 1>
+// NSEG = 6: split-bf16 operands for fp32 inputs ("bf16x6").  x = hi + mid + lo, each part the bf16 rounding of what the
+// previous parts left (the residuals are exact in fp32; three parts carry 24 mantissa bits).  The product keeps the six
+// terms down to 2^-16 of the leading one,  hi*hi + hi*mid + mid*hi + hi*lo + lo*hi + mid*mid  (the dropped ones are
+// <= 2^-24 relative, the fp32 rounding level), accumulated in the same TMEM accumulator as six K segments.
+struct SplitMaps { CUtensorMap A[2], B[2], A2[2], B2[2]; };   // tensor maps of the (mid, lo) parts; A2/B2: DUAL's second pair
+// Segment order: smallest terms first, hi*hi last.  The tensor core adds each K=16 step into the fp32 accumulator with
+// truncation, an error proportional to the accumulator's magnitude at that step: with the large term last, only its own
+// K/16 steps run on a large accumulator (measured: the error of an H=4096 logit against fp64 halves vs hi*hi first).
+//   segment:       0       1      2      3       4      5
+//   (A, B) part: (mid,mid) (hi,lo) (lo,hi) (hi,mid) (mid,hi) (hi,hi)
+constexpr uint32_t kSegPartA = 0x010201u, kSegPartB = 0x001021u;   // nibble s = part (0 hi, 1 mid, 2 lo) of A / B in segment s
+
+template <int BN_, bool DUAL_, int AMAJ_, int BMAJ_, int CG_ = 1, int NSEG_ = 1>
 struct GemmCfg {
+  static constexpr int NSEG = NSEG_;
+  static_assert(NSEG == 1 || NSEG == 6, "NSEG");
   static constexpr int BN = BN_;                 // N of one tcgen05.mma / columns of one accumulator
   static constexpr bool DUAL = DUAL_;
   static constexpr int AMAJ = AMAJ_, BMAJ = BMAJ_;
@@ -156,11 +170,10 @@ template <int MAJ> struct OperandDesc {
 };
 
 template <class Cfg, class Epi>
-__global__ void __launch_bounds__(kNumThreads, 1)
-dpa_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
-                const GemmWork work, const typename Epi::Params ep) {
-  constexpr int BN = Cfg::BN, STAGES = Cfg::STAGES, CG = Cfg::CG;
+__device__ __forceinline__ void dpa_gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA2,
+                                              const CUtensorMap& tmB2, const SplitMaps* sm, const GemmWork& work,
+                                              const typename Epi::Params& ep) {
+  constexpr int BN = Cfg::BN, STAGES = Cfg::STAGES, CG = Cfg::CG, NSEG = Cfg::NSEG;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -221,16 +234,24 @@ dpa_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int mt = mu * CG + cta_rank;
       const int nt_end = min((ng + 1) * tpu, n_tiles);
       for (int nt = ng * tpu; nt < nt_end; ++nt) {
+#pragma unroll 1
+       for (int seg = 0; seg < NSEG; ++seg) {
+        const CUtensorMap* mA = &tmA; const CUtensorMap* mB = &tmB; const CUtensorMap* mA2 = &tmA2; const CUtensorMap* mB2 = &tmB2;
+        if constexpr (NSEG > 1) {                     // split-bf16: which part of A and of B this K segment streams
+          const int pa = (kSegPartA >> (4 * seg)) & 15, pb = (kSegPartB >> (4 * seg)) & 15;
+          if (pa) { mA = &sm->A[pa - 1]; mA2 = &sm->A2[pa - 1]; }
+          if (pb) { mB = &sm->B[pb - 1]; mB2 = &sm->B2[pb - 1]; }
+        }
         for (int kb = 0; kb < tr.k_blocks; ++kb) {
           mbar_wait(&empty[st], ph ^ 1);
           if (elect_one()) {
             if constexpr (CG == 1) mbar_arrive_expect_tx(&full[st], Cfg::STAGE_BYTES);
-            load_operand<Cfg::AMAJ, BM, CG>(sA + st * Cfg::A_BYTES, &tmA, &full[st], tr.a_row0 + mt * BM, tr.a_k0 + kb * BK);
-            load_operand<Cfg::BMAJ, Cfg::BN_CTA, CG>(sB + st * Cfg::B_BYTES, &tmB, &full[st], nt * BN + cta_rank * Cfg::BN_CTA,
+            load_operand<Cfg::AMAJ, BM, CG>(sA + st * Cfg::A_BYTES, mA, &full[st], tr.a_row0 + mt * BM, tr.a_k0 + kb * BK);
+            load_operand<Cfg::BMAJ, Cfg::BN_CTA, CG>(sB + st * Cfg::B_BYTES, mB, &full[st], nt * BN + cta_rank * Cfg::BN_CTA,
                                                      tr.b_k0 + kb * BK);
             if constexpr (Cfg::DUAL) {
-              load_operand<Cfg::AMAJ, BM, CG>(sA2 + st * Cfg::A_BYTES, &tmA2, &full[st], tr.a2_row0 + mt * BM, tr.a_k0 + kb * BK);
-              load_operand<Cfg::BMAJ, Cfg::BN_CTA, CG>(sB2 + st * Cfg::B_BYTES, &tmB2, &full[st], nt * BN + cta_rank * Cfg::BN_CTA,
+              load_operand<Cfg::AMAJ, BM, CG>(sA2 + st * Cfg::A_BYTES, mA2, &full[st], tr.a2_row0 + mt * BM, tr.a_k0 + kb * BK);
+              load_operand<Cfg::BMAJ, Cfg::BN_CTA, CG>(sB2 + st * Cfg::B_BYTES, mB2, &full[st], nt * BN + cta_rank * Cfg::BN_CTA,
                                                        tr.b_k0 + kb * BK);
             }
             if constexpr (CG == 2) {
@@ -242,6 +263,7 @@ dpa_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           __syncwarp();
           if (++st == STAGES) { st = 0; ph ^= 1; }
         }
+       }
       }
     }
   } else if (warp == kMmaWarp && leader) {
@@ -260,7 +282,8 @@ dpa_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_wait(&tempty[as], aph ^ 1);
         tc_fence_after();
         const uint32_t acc = tmem_base + as * Cfg::ACC_COLS;
-        for (int kb = 0; kb < tr.k_blocks; ++kb) {
+        const int kb_total = tr.k_blocks * NSEG;       // the K segments of split operands accumulate into the same tile
+        for (int kb = 0; kb < kb_total; ++kb) {
           mbar_wait(&full[st], ph);
           tc_fence_after();
           if (elect_one()) {
@@ -276,7 +299,7 @@ dpa_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                               (kb | k) != 0);
             }
             umma_commit<CG>(&empty[st]);              // smem slot reusable (in both CTAs) once these MMAs retire
-            if (kb == tr.k_blocks - 1) umma_commit<CG>(&tfull[as]);
+            if (kb == kb_total - 1) umma_commit<CG>(&tfull[as]);
           }
           __syncwarp();
           if (++st == STAGES) { st = 0; ph ^= 1; }
@@ -310,6 +333,24 @@ dpa_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();   // remote arrives have landed before either CTA exits
   if (warp == kAllocWarp) tmem_dealloc<CG>(tmem_base, 512);
+}
+
+template <class Cfg, class Epi>
+__global__ void __launch_bounds__(kNumThreads, 1)
+dpa_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                const GemmWork work, const typename Epi::Params ep) {
+  static_assert(Cfg::NSEG == 1, "split operands go through dpa_gemm_split_kernel");
+  dpa_gemm_body<Cfg, Epi>(tmA, tmB, tmA2, tmB2, nullptr, work, ep);
+}
+// split-bf16 operands (fp32 inputs): the same mainloop over six K segments
+template <class Cfg, class Epi>
+__global__ void __launch_bounds__(kNumThreads, 1)
+dpa_gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                      const __grid_constant__ SplitMaps sm, const GemmWork work, const typename Epi::Params ep) {
+  static_assert(Cfg::NSEG == 6, "NSEG");
+  dpa_gemm_body<Cfg, Epi>(tmA, tmB, tmA2, tmB2, &sm, work, ep);
 }
 
 // =====================================================================================================
@@ -439,6 +480,19 @@ __device__ __forceinline__ void store_bf16_chunk(__nv_bfloat16* dst, const float
                       pack_bf16x2(d[8 * i + 4], d[8 * i + 5]), pack_bf16x2(d[8 * i + 6], d[8 * i + 7]));
 }
 
+// split-bf16 store of a dLogits chunk for the fp32 path: hi = bf16(d), mid = bf16(d - hi), lo = bf16(d - hi - mid);
+// the three parts are `part_stride` elements apart
+__device__ __forceinline__ void store_split_chunk(__nv_bfloat16* hi, size_t part_stride, const float (&d)[32]) {
+  float r[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) r[i] = d[i] - bf16_round_f32(d[i]);
+  store_bf16_chunk(hi, d);
+  store_bf16_chunk(hi + part_stride, r);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) r[i] -= bf16_round_f32(r[i]);
+  store_bf16_chunk(hi + 2 * part_stride, r);
+}
+
 // ---- fused-gradient forward, reference-sample rows: per (row, column group) partial {max, sum-exp} of one model's
 //      logits, and the bf16-rounded logits of the row chunk are kept (policy -> the chunk's dz buffer, frozen -> zr) so
 //      that dz = c (p - q) and the KL row are one elementwise pass once the chunk's log-sum-exps are known, instead of a
@@ -476,11 +530,12 @@ struct EpiStatsStore {
 };
 
 // ---- backward recompute, pair rows: dz = coef * (onehot(y) - softmax(z))  -> bf16 scratch [chunk_rows][ldz]
-template <int BN, bool ROUND>
+template <int BN, bool ROUND, bool SPLIT = false>
 struct EpiDzPair {
   struct Params {
     const int* labels; const float* lse; const float* coef;   // indexed by packed row
     __nv_bfloat16* dz; int ldz; int chunk_row0; int v_local, v_offset;
+    size_t part_stride;                                       // SPLIT: elements between the hi / mid / lo copies of dz
   };
   struct State { float nl, c; int yloc; __nv_bfloat16* out; };
   __device__ static void unit_begin(const Params& p, State& s, int erow, int) {
@@ -503,19 +558,21 @@ struct EpiDzPair {
 #pragma unroll
         for (int i = 0; i < 32; ++i) d[i] += (i == j) ? s.c : 0.f;
       }
-      store_bf16_chunk(s.out + cbase, d);
+      if constexpr (SPLIT) store_split_chunk(s.out + cbase, p.part_stride, d);
+      else store_bf16_chunk(s.out + cbase, d);
     }
   }
   __device__ static void unit_end(const Params&, State&, int) {}
 };
 
 // ---- backward recompute, reference-sample rows (DUAL): dz = coef * (softmax(z_pol) - softmax(z_frozen))
-template <int BN, bool ROUND>
+template <int BN, bool ROUND, bool SPLIT = false>
 struct EpiDzRef {
   struct Params {
     const DpaMeta* meta;
     const float* lse_p; const float* lse_r; const float* coef;   // indexed by reference row j
     __nv_bfloat16* dz; int ldz; int chunk_row0; int v_local;
+    size_t part_stride;                                          // SPLIT: elements between the hi / mid / lo copies of dz
   };
   struct State { float nlp, nlr, c; __nv_bfloat16* out; };
   __device__ static void unit_begin(const Params& p, State& s, int erow, int) {
@@ -537,22 +594,29 @@ struct EpiDzRef {
 #pragma unroll
       for (int i = 0; i < 32; ++i)
         d[i] = s.c * (fast_exp2(fmaf(vp[i], kLog2e, s.nlp)) - fast_exp2(fmaf(vr[i], kLog2e, s.nlr)));
-      store_bf16_chunk(s.out + cbase, d);
+      if constexpr (SPLIT) store_split_chunk(s.out + cbase, p.part_stride, d);
+      else store_bf16_chunk(s.out + cbase, d);
     }
   }
   __device__ static void unit_end(const Params&, State&, int) {}
 };
 
 // ---- dH = dZ * W: fp32 accumulators -> bf16 rows scattered to their source positions
-template <int BN>
+__device__ __forceinline__ void store_out_chunk(__nv_bfloat16* dst, const float (&v)[32]) { store_bf16_chunk(dst, v); }
+__device__ __forceinline__ void store_out_chunk(float* dst, const float (&v)[32]) {
+  float4* o = reinterpret_cast<float4*>(dst);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+template <int BN, class OutT = __nv_bfloat16>      // OutT = float: the fp32 path (split-bf16 operands)
 struct EpiStoreRows {
   struct Params {
     const DpaMeta* meta;
     const int* src_pair; const int* src_ref;       // packed row -> flat (sequence*T + t) row of the dense tensors
-    __nv_bfloat16* dH_pair; __nv_bfloat16* dH_ref; int H;
-    __nv_bfloat16* packed;                         // non-null: keep the rows packed ([n_tot][H]; vocab-parallel: the partial
+    OutT* dH_pair; OutT* dH_ref; int H;
+    OutT* packed;                                  // non-null: keep the rows packed ([n_tot][H]; vocab-parallel: the partial
   };                                               // sums are all-reduced in this compact form and scattered afterwards)
-  struct State { __nv_bfloat16* out; };
+  struct State { OutT* out; };
   __device__ static void unit_begin(const Params& p, State& s, int erow, int) {
     const int p0 = p.meta->p0;
     if (p.packed) { s.out = p.packed + (size_t)erow * p.H; return; }
@@ -567,7 +631,7 @@ struct EpiStoreRows {
       if (cbase >= p.H) break;
       float v[32];
       load_chunk(taddr + c * 32, v);                     // warp-collective: every lane loads
-      if (s.out) store_bf16_chunk(s.out + cbase, v);     // H % 32 == 0 is checked on the host
+      if (s.out) store_out_chunk(s.out + cbase, v);      // H % 32 == 0 is checked on the host
     }
   }
   __device__ static void unit_end(const Params&, State&, int) {}

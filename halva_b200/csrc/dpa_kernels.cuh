@@ -278,6 +278,63 @@ __global__ void gather_rows_kernel(GatherArgs a) {
   }
 }
 
+// ---- fp32 inputs (dpa_shape_t::dtype == DPA_F32): the tensor-core operands are split-bf16 triples, x = hi + mid + lo with
+//      hi = bf16(x), mid = bf16(x - hi), lo = bf16(x - hi - mid)  (the residuals are exact in fp32; 24 mantissa bits in all).
+//      8 fp32 -> 3 x 8 bf16; the three parts of a buffer are `part` elements apart.
+__device__ __forceinline__ void split8(const float4& a, const float4& b, uint4 (&out)[3]) {
+  float r[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int p = 0; p < 3; ++p) {
+    out[p] = make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7]));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] -= bf16_round_f32(r[k]);
+  }
+}
+// gather of the active fp32 hidden rows into packed split-bf16 operand buffers (one warp per row)
+struct GatherSplitArgs {
+  const DpaMeta* meta;
+  const int* src_pair; const int* src_ref;
+  const float* h_pair; const float* h_ref_pol; const float* h_ref_frz;
+  __nv_bfloat16* Hp; size_t part_p;   // 3 x [cap_pair + cap_ref][H]
+  __nv_bfloat16* Hf; size_t part_f;   // 3 x [cap_ref][H]
+  int H;
+};
+__global__ void gather_rows_split_kernel(GatherSplitArgs a) {
+  const int p0 = a.meta->p0, n_tot = a.meta->n_tot;
+  const int nr_pad = n_tot - p0;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int vec = a.H / 8;
+  for (int r = wid; r < n_tot + nr_pad; r += warps) {
+    const float4* src = nullptr; uint4* dst; size_t part;
+    if (r < n_tot) {
+      const int sr = r < p0 ? a.src_pair[r] : a.src_ref[r - p0];
+      if (sr >= 0) src = reinterpret_cast<const float4*>((r < p0 ? a.h_pair : a.h_ref_pol) + (size_t)sr * a.H);
+      dst = reinterpret_cast<uint4*>(a.Hp + (size_t)r * a.H); part = a.part_p / 8;
+    } else {
+      const int j = r - n_tot, sr = a.src_ref[j];
+      if (sr >= 0) src = reinterpret_cast<const float4*>(a.h_ref_frz + (size_t)sr * a.H);
+      dst = reinterpret_cast<uint4*>(a.Hf + (size_t)j * a.H); part = a.part_f / 8;
+    }
+    for (int i = lane; i < vec; i += 32) {
+      uint4 o[3] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+      if (src) split8(__ldg(src + 2 * i), __ldg(src + 2 * i + 1), o);
+      dst[i] = o[0]; dst[i + part] = o[1]; dst[i + 2 * part] = o[2];
+    }
+  }
+}
+// lm_head weights fp32 [V][H] -> split-bf16 triple, parts n elements apart (per call: the weights change every optimiser step)
+__global__ void split_f32_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
+  const size_t nv = n >> 3, stride = (size_t)gridDim.x * blockDim.x;
+  const float4* p = reinterpret_cast<const float4*>(in);
+  uint4* o = reinterpret_cast<uint4*>(out);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+    uint4 t[3];
+    split8(__ldg(p + 2 * i), __ldg(p + 2 * i + 1), t);
+    o[i] = t[0]; o[i + nv] = t[1]; o[i + 2 * nv] = t[2];
+  }
+}
+
 // ---- vocab-parallel backward: scatter the all-reduced packed dH rows to their [s,t] positions (one warp per row)
 struct ScatterArgs {
   const DpaMeta* meta;
@@ -714,10 +771,10 @@ __global__ void scale_bf16_kernel(__nv_bfloat16* x, size_t n, const float* __res
 }
 
 // dW when no row at all contributed (no chunk ran): zero it; otherwise the last chunk's GEMM epilogue already wrote it
-__global__ void zero_if_no_rows_kernel(const DpaMeta* meta, __nv_bfloat16* out, size_t n) {
+__global__ void zero_if_no_rows_kernel(const DpaMeta* meta, void* out, size_t bytes) {
   if (meta->n_tot != 0) return;
   uint4* p = reinterpret_cast<uint4*>(out);
-  const size_t nv = n >> 3, stride = (size_t)gridDim.x * blockDim.x;
+  const size_t nv = bytes >> 4, stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) p[i] = make_uint4(0, 0, 0, 0);
 }
 

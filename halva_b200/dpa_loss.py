@@ -48,8 +48,9 @@ def _check_inputs(h_pair, labels_pair, signs_pair, h_ref_pol, h_ref_frozen, labe
     for name, t in (("h_pair", h_pair), ("h_ref_pol", h_ref_pol), ("W", W)) + frozen:
         if not t.is_cuda:
             raise DPAError(f"{name} is on {t.device}: the DPA-loss path is CUDA (sm_100a) only, there is no CPU fallback")
-        if t.dtype != torch.bfloat16:
-            raise TypeError(f"{name} has dtype {t.dtype}; the tensor-core path takes bf16 (the HALVA recipes train in bf16)")
+        if t.dtype not in (torch.bfloat16, torch.float32) or t.dtype != h_pair.dtype:
+            raise TypeError(f"{name} has dtype {t.dtype}; hidden states and lm_head weights must all be bf16 (the HALVA recipes "
+                            "train in bf16) or all fp32 (split-bf16 tensor-core passes, fp32 gradients)")
     for name, t in (("labels_pair", labels_pair), ("signs_pair", signs_pair), ("labels_ref", labels_ref)):
         if t.dtype not in (torch.int64, torch.int32):
             raise TypeError(f"{name} must be int64 or int32")
@@ -93,7 +94,7 @@ class _Call:
             self.keep += [self.norm[0], self.norm[1]]
         self.grads = None
         self.shape = Shape(B=B2 // 2, T=T, B_ref=Br, T_ref=Tr, H=H, V=V_global, V_local=w.shape[0], v_offset=v_offset,
-                           dtype=_lib.DPA_BF16, index_dtype=_lib.DPA_I64 if lp.dtype == torch.int64 else _lib.DPA_I32,
+                           dtype=_lib.DPA_F32 if hp.dtype == torch.float32 else _lib.DPA_BF16, index_dtype=_lib.DPA_I64 if lp.dtype == torch.int64 else _lib.DPA_I32,
                            flags=flags, chunk_rows=chunk_rows)
         ws = Workspace()
         _lib.check(lib.dpa_query_workspace(C.byref(self.shape), C.byref(ws)), "dpa_query_workspace")
@@ -239,6 +240,10 @@ def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.
     alpha                          loss = align + alpha * div            (halva_trainer.py:590)
     round_logits                   True: round logits to bf16 before the fp32 softmax, exactly as the reference's
                                    bf16 nn.Linear does (modeling_llama.py:1028-1029); False: keep fp32 accumulators
+    fp32 inputs                    h_pair / h_ref_pol / h_ref_frozen / W / W_ref may all be fp32 instead (an fp32 model, as in
+                                   the reference's CPU-runnable configuration): every operand goes to the tensor cores as a
+                                   split-bf16 pair (hi + lo, three passes per GEMM), logits and dLogits stay fp32-accurate,
+                                   gradients come back in fp32.  round_logits is ignored (an fp32 nn.Linear does not round).
     need_dW                        default W.requires_grad (False under the shipped LoRA recipe: lm_head frozen)
     dense                          process every fed position instead of compacting to rows with a non-zero
                                    contribution (what the reference executes; benchmarking only)
@@ -287,6 +292,12 @@ def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.
                 raise TypeError(f"{name} must be a CUDA bf16 tensor of H elements")
     if backward not in ("auto", "recompute", "fused"):
         raise ValueError("backward must be 'auto', 'recompute' or 'fused'")
+    if h_pair.dtype == torch.float32:
+        # fp32 model (BASELINE configs[0]): nn.Linear emits fp32 logits, so there is no bf16 rounding point to reproduce and
+        # no bf16 logits to keep -- statistics forward + recompute backward on split-bf16 operands, fp32 dLogits (hi + lo)
+        if ref_logits is not None or norm_weight is not None or backward == "fused":
+            raise ValueError("fp32 inputs: ref_logits, norm_weight and backward='fused' belong to the bf16 execution")
+        round_logits, backward = False, "recompute"
     if backward == "fused" and (not round_logits or vocab_group is not None):
         raise ValueError("backward='fused' needs round_logits=True and no vocab_group")
     fused = backward == "fused" or (backward == "auto" and round_logits and vocab_group is None)
