@@ -652,9 +652,12 @@ struct Plan {
     for (int p = 0; p < 2; ++p) { m.A[p] = A[p]; m.B[p] = B[p]; m.A2[p] = A2[p]; m.B2[p] = B2[p]; }
     return m;
   }
-  // split-bf16 GEMM configurations (fp32 inputs): always CTA pairs
-  template <int AMAJ, int BMAJ> using SplitCfg = GemmCfg<256, false, AMAJ, BMAJ, 2, 6>;
-  using SplitDualCfg = GemmCfg<128, true, KMAJOR, KMAJOR, 2, 6>;
+  // split-bf16 GEMM configurations (fp32 inputs): 128-column accumulators (the K-chunk promotion keeps them in registers),
+  // one CTA per 128-row tile; the column groups of the statistics stay the 1280 columns of the bf16 tilings
+  static constexpr int kBnSplit = 128, kBnSplitDual = 64;
+  static constexpr int kTpuSplit = kBnPair * kTpuPair / kBnSplit, kTpuSplitDual = kBnRef * kTpuRef / kBnSplitDual;
+  template <int AMAJ, int BMAJ> using SplitCfg = GemmCfg<kBnSplit, false, AMAJ, BMAJ, 1, 6>;
+  using SplitDualCfg = GemmCfg<kBnSplitDual, true, KMAJOR, KMAJOR, 1, 6>;
 
   // statistics of every pair row; store_rows > 0 also keeps the bf16 logits of the first store_rows packed rows in dz
   template <bool ROUND> int fwd_pair(int store_rows) {
@@ -663,9 +666,14 @@ struct Plan {
     typename Epi::Params ep{at<int>(a->state, L.lab_pair), part_pair, L.cap_pair, s.V_local, s.v_offset,
                             store_rows > 0 ? dz : nullptr, L.ldz, store_rows};
     ProfScope ps(PK_FWD_PAIR, 1, st);
-    if (split) {
-      const SplitMaps sm = split_maps(tmHpS, tmW128S, tmHpS, tmW128S);
-      return launch_gemm<SplitCfg<KMAJOR, KMAJOR>, Epi>(st, d->sms, tmHp, tmW128, tmHp, tmW128, w, ep, "fwd_pair[split]", &sm);
+    if constexpr (!ROUND) {
+      if (split) {
+        using EpiS = EpiStatsPair<kBnSplit, false>;
+        GemmWork ws = w; ws.tiles_per_unit = kTpuSplit;
+        typename EpiS::Params eps{ep.labels, ep.part, ep.row_cap, ep.v_local, ep.v_offset, nullptr, L.ldz, 0};
+        const SplitMaps sm = split_maps(tmHpS, tmW128S, tmHpS, tmW128S);
+        return launch_gemm<SplitCfg<KMAJOR, KMAJOR>, EpiS>(st, d->sms, tmHp, tmW128, tmHp, tmW128, ws, eps, "fwd_pair[split]", &sm);
+      }
     }
     return launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHp, tmW256, tmW128, w, ep, "fwd_pair");
   }
@@ -675,9 +683,14 @@ struct Plan {
     GemmWork w{meta, KIND_FWD_REF, 0, 0, 0, s.V_local, s.H, kTpuRef};
     typename Epi::Params ep{part_ref, part_u, L.cap_ref, s.V_local};
     ProfScope ps(PK_FWD_REF, 1, st);
-    if (split) {
-      const SplitMaps sm = split_maps(tmHpS, tmW64S, tmHfS, tmWr64S);
-      return launch_gemm<SplitDualCfg, Epi>(st, d->sms, tmHp, tmW64, tmHf, tmWr64, w, ep, "fwd_ref[split]", &sm);
+    if constexpr (!ROUND) {
+      if (split) {
+        using EpiS = EpiStatsRef<kBnSplitDual, false>;
+        GemmWork ws = w; ws.tiles_per_unit = kTpuSplitDual;
+        typename EpiS::Params eps{part_ref, part_u, L.cap_ref, s.V_local};
+        const SplitMaps sm = split_maps(tmHpS, tmW64S, tmHfS, tmWr64S);
+        return launch_gemm<SplitDualCfg, EpiS>(st, d->sms, tmHp, tmW64, tmHf, tmWr64, ws, eps, "fwd_ref[split]", &sm);
+      }
     }
     return launch_dual<Epi>(st, d, tmHp, tmHf, tmW128, tmWr128, tmW64, tmWr64, w, ep, "fwd_ref");
   }
@@ -690,10 +703,11 @@ struct Plan {
     ProfScope ps(PK_DZ_PAIR, 1, st);
     if constexpr (!ROUND) {
       if (split) {
-        using EpiS = EpiDzPair<kBnPair, false, true>;
+        using EpiS = EpiDzPair<kBnSplit, false, true>;
+        GemmWork ws = w; ws.tiles_per_unit = kTpuSplit;
         typename EpiS::Params eps{ep.labels, ep.lse, ep.coef, dz, L.ldz, ch * L.chunk_rows, s.V_local, s.v_offset, dz_part};
         const SplitMaps sm = split_maps(tmHpS, tmW128S, tmHpS, tmW128S);
-        return launch_gemm<SplitCfg<KMAJOR, KMAJOR>, EpiS>(st, d->sms, tmHp, tmW128, tmHp, tmW128, w, eps, "dz_pair[split]", &sm);
+        return launch_gemm<SplitCfg<KMAJOR, KMAJOR>, EpiS>(st, d->sms, tmHp, tmW128, tmHp, tmW128, ws, eps, "dz_pair[split]", &sm);
       }
     }
     return launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHp, tmW256, tmW128, w, ep, "dz_pair");
@@ -707,10 +721,11 @@ struct Plan {
     ProfScope ps(PK_DZ_REF, 1, st);
     if constexpr (!ROUND) {
       if (split) {
-        using EpiS = EpiDzRef<kBnRef, false, true>;
+        using EpiS = EpiDzRef<kBnSplitDual, false, true>;
+        GemmWork ws = w; ws.tiles_per_unit = kTpuSplitDual;
         typename EpiS::Params eps{meta, ep.lse_p, ep.lse_r, ep.coef, dz, L.ldz, ch * L.chunk_rows, s.V_local, dz_part};
         const SplitMaps sm = split_maps(tmHpS, tmW64S, tmHfS, tmWr64S);
-        return launch_gemm<SplitDualCfg, EpiS>(st, d->sms, tmHp, tmW64, tmHf, tmWr64, w, eps, "dz_ref[split]", &sm);
+        return launch_gemm<SplitDualCfg, EpiS>(st, d->sms, tmHp, tmW64, tmHf, tmWr64, ws, eps, "dz_ref[split]", &sm);
       }
     }
     return launch_dual<Epi>(st, d, tmHp, tmHf, tmW128, tmWr128, tmW64, tmWr64, w, ep, "dz_ref");
@@ -748,7 +763,7 @@ struct Plan {
   int grad_gemms(int ch) {
     if (split) {              // fp32 inputs: split-bf16 dz and operands, fp32 gradients; dW accumulates in place
       {
-        using Epi = EpiStoreRows<256, float>;
+        using Epi = EpiStoreRows<kBnSplit, float>;
         GemmWork w{meta, KIND_DH, ch, L.chunk_rows, 0, s.H, s.V_local, 1};
         typename Epi::Params ep{meta, at<int>(a->state, L.src_pair), at<int>(a->state, L.src_ref),
                                 static_cast<float*>(a->dH_pair), static_cast<float*>(a->dH_ref), s.H, nullptr};
@@ -758,7 +773,7 @@ struct Plan {
         if (rc) return rc;
       }
       if (s.flags & DPA_FLAG_NEED_DW) {
-        using Epi = EpiAccumF32<256>;
+        using Epi = EpiAccumF32<kBnSplit>;
         GemmWork w{meta, KIND_DW, ch, L.chunk_rows, s.V_local, s.H, 0, 1};
         typename Epi::Params ep{static_cast<float*>(a->dW), s.H, s.V_local, s.H, ch > 0};
         const SplitMaps sm = split_maps(tmDzMNS, tmHpMNS, tmDzMNS, tmHpMNS);

@@ -143,6 +143,16 @@ struct GemmCfg {
   static constexpr int STAGES_RAW = (227 * 1024 - 1280) / STAGE_BYTES;   // 7 x 32 KiB (pair), 4 x 48 KiB (single CTA / dual pair), 3 x 64 KiB (dual single CTA)
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int ACC_COLS = DUAL ? 2 * BN : BN;             // TMEM columns per accumulator stage
+  // PROMOTE (the split-operand / fp32 path): the tensor core adds each K = 16 step into its fp32 accumulator with
+  // TRUNCATION (tools/tc_accum_probe.py: a same-sign K = 4096 dot product comes out 9e-6 low; the bias grows with the
+  // accumulator's magnitude and the number of steps).  So the K loop is cut into chunks of PROMOTE_KB k-blocks, each chunk
+  // accumulates from zero in one of the two TMEM stages, and the epilogue warps add the chunk results in registers with
+  // round-to-nearest (the other stage is being filled meanwhile); the sum is parked in a third TMEM region for the
+  // unchanged fused epilogue.  Inside a chunk the accumulator stays 1 / #chunks of the result, and so does the bias.
+  static constexpr bool PROMOTE = NSEG > 1;
+  static constexpr int PROMOTE_KB = 4;                             // 4 k-blocks = K 256 = 16 tensor-core steps per chunk
+  static constexpr int MAIN_COL = 2 * ACC_COLS;                    // TMEM column of the promoted sum
+  static_assert(!PROMOTE || (3 * ACC_COLS <= 512 && ACC_COLS <= 128), "promotion keeps ACC_COLS fp32 registers per thread");
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static_assert(2 * ACC_COLS <= 512, "two accumulator stages must fit TMEM");
   static_assert(BN % 64 == 0 && BN <= 256 && BN_CTA % 64 == 0, "BN");
@@ -168,6 +178,15 @@ template <int MAJ> struct OperandDesc {
   static constexpr uint64_t HI = MAJ == KMAJOR ? smem_desc_hi_sw128(0, 1024) : smem_desc_hi_sw128(BK * 128, 1024);
   static constexpr uint32_t KSTEP = (MAJ == KMAJOR ? UMMA_K * 2 : UMMA_K * 128) >> 4;   // in the >>4 address field
 };
+
+__device__ __forceinline__ void load_chunk(uint32_t taddr, float (&v)[32]);
+__device__ __forceinline__ void store_chunk(uint32_t taddr, const float* v) {    // registers -> 32 fp32 TMEM columns
+  __syncwarp();                      // tcgen05.st is warp-collective (.sync.aligned)
+  uint32_t r[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(v[i]);
+  tmem_st_32x32(taddr, r);
+}
 
 template <class Cfg, class Epi>
 __device__ __forceinline__ void dpa_gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA2,
@@ -277,31 +296,47 @@ __device__ __forceinline__ void dpa_gemm_body(const CUtensorMap& tmA, const CUte
     for (int u = group_id; u < n_units; u += n_cta_groups) {
       int mu, ng; decode(u, mu, ng);
       const int nt_end = min((ng + 1) * tpu, n_tiles);
-      for (int nt = ng * tpu; nt < nt_end; ++nt, ++it) {
-        const uint32_t as = it & 1, aph = (it >> 1) & 1;
-        mbar_wait(&tempty[as], aph ^ 1);
-        tc_fence_after();
-        const uint32_t acc = tmem_base + as * Cfg::ACC_COLS;
+      for (int nt = ng * tpu; nt < nt_end; ++nt, it += Cfg::PROMOTE ? 0 : 1) {
+        uint32_t as = it & 1, aph = (it >> 1) & 1;
+        if constexpr (!Cfg::PROMOTE) { mbar_wait(&tempty[as], aph ^ 1); tc_fence_after(); }
+        uint32_t acc = tmem_base + as * Cfg::ACC_COLS;
         const int kb_total = tr.k_blocks * NSEG;       // the K segments of split operands accumulate into the same tile
+        int kc = 0;                                    // PROMOTE: k-block inside the current chunk
         for (int kb = 0; kb < kb_total; ++kb) {
+          if constexpr (Cfg::PROMOTE) {
+            if (kc == 0) {                             // a new chunk starts from zero in the next accumulator stage
+              as = it & 1; aph = (it >> 1) & 1;
+              mbar_wait(&tempty[as], aph ^ 1);
+              tc_fence_after();
+              acc = tmem_base + as * Cfg::ACC_COLS;
+            }
+          }
+          const int kacc = Cfg::PROMOTE ? kc : kb;     // 0 = first k-block of this accumulator: overwrite
           mbar_wait(&full[st], ph);
           tc_fence_after();
           if (elect_one()) {
             const uint32_t a_lo = a_base + st * (Cfg::A_BYTES >> 4), b_lo = b_base + st * (Cfg::B_BYTES >> 4);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k)
-              umma_bf16<CG>(acc, DA::HI | (uint64_t)(a_lo + k * DA::KSTEP), DB::HI | (uint64_t)(b_lo + k * DB::KSTEP), idesc, (kb | k) != 0);
+              umma_bf16<CG>(acc, DA::HI | (uint64_t)(a_lo + k * DA::KSTEP), DB::HI | (uint64_t)(b_lo + k * DB::KSTEP), idesc, (kacc | k) != 0);
             if constexpr (Cfg::DUAL) {
               const uint32_t a2_lo = a2_base + st * (Cfg::A_BYTES >> 4), b2_lo = b2_base + st * (Cfg::B_BYTES >> 4);
 #pragma unroll
               for (int k = 0; k < BK / UMMA_K; ++k)
                 umma_bf16<CG>(acc + BN, DA::HI | (uint64_t)(a2_lo + k * DA::KSTEP), DB::HI | (uint64_t)(b2_lo + k * DB::KSTEP), idesc,
-                              (kb | k) != 0);
+                              (kacc | k) != 0);
             }
             umma_commit<CG>(&empty[st]);              // smem slot reusable (in both CTAs) once these MMAs retire
-            if (kb == kb_total - 1) umma_commit<CG>(&tfull[as]);
+            if constexpr (Cfg::PROMOTE) {
+              if (kc == Cfg::PROMOTE_KB - 1 || kb == kb_total - 1) umma_commit<CG>(&tfull[as]);
+            } else {
+              if (kb == kb_total - 1) umma_commit<CG>(&tfull[as]);
+            }
           }
           __syncwarp();
+          if constexpr (Cfg::PROMOTE) {
+            if (++kc == Cfg::PROMOTE_KB || kb == kb_total - 1) { kc = 0; ++it; }
+          }
           if (++st == STAGES) { st = 0; ph ^= 1; }
         }
       }
@@ -318,6 +353,33 @@ __device__ __forceinline__ void dpa_gemm_body(const CUtensorMap& tmA, const CUte
       typename Epi::State s;
       Epi::unit_begin(ep, s, tr.e_row0 + mt * BM + trow, mt * BM + trow);
       const int nt_end = min((ng + 1) * tpu, n_tiles);
+      if constexpr (Cfg::PROMOTE) {
+        const int n_chunks = (tr.k_blocks * NSEG + Cfg::PROMOTE_KB - 1) / Cfg::PROMOTE_KB;
+        for (int nt = ng * tpu; nt < nt_end; ++nt) {
+          float sum[Cfg::ACC_COLS];
+#pragma unroll
+          for (int i = 0; i < Cfg::ACC_COLS; ++i) sum[i] = 0.f;
+          for (int ch = 0; ch < n_chunks; ++ch, ++it) {
+            const uint32_t as = it & 1, aph = (it >> 1) & 1;
+            mbar_wait(&tfull[as], aph);
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < Cfg::ACC_COLS / 32; ++c) {
+              float v[32];
+              load_chunk(lane_base + as * Cfg::ACC_COLS + c * 32, v);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) sum[c * 32 + i] += v[i];          // fp32 round-to-nearest
+            }
+            tc_fence_before();
+            if (leader) mbar_arrive(&tempty[as]); else mbar_arrive_cluster(&tempty[as], 0);
+          }
+          // park the promoted sum in TMEM (this warp's own lanes) and run the fused epilogue on it unchanged
+#pragma unroll
+          for (int c = 0; c < Cfg::ACC_COLS / 32; ++c) store_chunk(lane_base + Cfg::MAIN_COL + c * 32, &sum[c * 32]);
+          tmem_st_wait();
+          Epi::tile(ep, s, lane_base + Cfg::MAIN_COL, nt * BN);
+        }
+      } else {
       for (int nt = ng * tpu; nt < nt_end; ++nt, ++it) {
         const uint32_t as = it & 1, aph = (it >> 1) & 1;
         mbar_wait(&tfull[as], aph);
@@ -325,6 +387,7 @@ __device__ __forceinline__ void dpa_gemm_body(const CUtensorMap& tmA, const CUte
         Epi::tile(ep, s, lane_base + as * Cfg::ACC_COLS, nt * BN);
         tc_fence_before();
         if (leader) mbar_arrive(&tempty[as]); else mbar_arrive_cluster(&tempty[as], 0);
+      }
       }
       Epi::unit_end(ep, s, ng);
     }

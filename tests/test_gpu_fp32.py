@@ -18,10 +18,11 @@ from oracle import dpa_oracle
 pytestmark = pytest.mark.gpu
 
 TOL_LOSS, TOL_DIV, TOL_GRAD = 1e-5, 1e-4, 1e-4
-# H = 4096: the tensor core adds every K = 16 step into its fp32 accumulator with TRUNCATION (tools/tc_accum_probe.py: a
-# same-sign K = 4096 dot product comes out ~9e-6 low, torch's SIMT fp32 matmul is unbiased), which a sum of ~100 phrase
-# log-probs turns into a few 1e-5 on the alignment loss
-TOL_LOSS_FULL = 5e-5
+# (Holds at H = 4096 too because the K loop of the split GEMMs is promoted chunk-wise through registers: the tensor core
+# adds every K = 16 step into its fp32 accumulator with TRUNCATION -- tools/tc_accum_probe.py: a same-sign K = 4096 dot
+# product comes out 9e-6 low -- which, unpromoted, a sum of ~100 phrase log-probs turns into 3e-5 on the alignment loss.
+# Measured at the cfg-1 shape, tools/fp32_accuracy.py: loss 3e-6, dH 6e-7 / 1.5e-5, dW 5e-7; torch's own fp32 op chain
+# on the same GPU: 2.5e-6, 3.5e-6 / 1.4e-4, 2.2e-6.)
 FP32_GOLDEN = ["tiny_fp32", "small_fp32_fullft", "k1_alpha0_fp32", "sparse_ids_fp32", "no_zero_sign_fp32"]
 
 
@@ -168,4 +169,4 @@ def test_fp32_cfg1_full_size():
     from halva_b200.synth import CONFIGS, make_inputs
     t = make_inputs(CONFIGS["cfg1"], seed=99, dtype=torch.float32, device="cuda", plant=5.0)
     c = _run(t)
-    _check(c, _torch_fp64(t), "cfg1", tol_loss=TOL_LOSS_FULL)
+    _check(c, _torch_fp64(t), "cfg1")
