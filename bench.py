@@ -141,7 +141,7 @@ def config_dict(args, shape):
     from halva_b200.synth import CONFIGS
     shape = shape or CONFIGS[args.config]
     return dict(workload=f"HALVA-7B DPA loss at training shape ({args.config}): {shape.B} pairs + {shape.B_ref} reference samples per GPU, "
-                         f"T={shape.T} incl. {shape.n_img} image tokens, H={shape.H}, V={shape.V}, bf16, phrase density {shape.density:.2f}, "
+                         f"T={shape.T} incl. {shape.n_img} image tokens, H={shape.H}, V={shape.V}, {'fp32' if getattr(args, 'fp32', False) else 'bf16'}, phrase density {shape.density:.2f}, "
                          f"seeded synthetic hidden states (targets planted, gain {PLANT})",
                 parallelism=f"{args.parallelism}{args.gpus}", need_dW=not args.no_dw, dense=bool(args.dense),
                 backward="recompute" if args.backward == "recompute" else "fused (gradients formed in the forward pass)",
@@ -228,7 +228,10 @@ def run_ours(args):
         shape = dataclasses.replace(shape, B=args.pairs, B_ref=args.pairs)
     vp = args.parallelism == "vp" and world > 1
     # dp: every rank its own batch (weak scaling);  vp: the SAME rows on every rank, lm_head rows split over the ranks
-    t = make_inputs(shape, seed=1234 + (0 if vp else rank), device=dev, plant=PLANT)
+    if args.fp32:
+        args.backward, args.no_e2e, args.no_variants = "recompute", True, True
+    t = make_inputs(shape, seed=1234 + (0 if vp else rank), device=dev, plant=PLANT,
+                    dtype=torch.float32 if args.fp32 else torch.bfloat16)
     hp, hr = t["h_pair"].requires_grad_(True), t["h_ref_pol"].requires_grad_(True)
     vp_kw = {}
     if vp:
@@ -412,6 +415,8 @@ def run_ours(args):
     ms_step = ms / K
     value = tokens_step / (ms_step * 1e-3)
     unit_flops = 2.0 * shape.H * W.shape[0]          # per GPU: this rank's lm_head rows
+    if args.fp32:
+        unit_flops *= 6          # executed bf16 tensor-core FLOPs: six split-operand K segments per GEMM
     # executed tensor-core FLOPs of each GEMM class per step (rows actually processed, tile padding not counted)
     n_p, n_r = (2 * shape.B * (shape.T - 1), shape.B_ref * (shape.T_ref - 1)) if args.dense else (rows_pair, rows_ref)
     fused = args.backward != "recompute"
@@ -459,7 +464,8 @@ def run_ours(args):
                          "contribution are run). Whole-step figures: step_tc_frac_*")
     e2e_ms_step = ms_e2e / K if ms_e2e else None
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=max(args.warmup, 3), ms_per_step=ms_step,
-                higher_is_better=True, scaling="strong" if vp else "weak", vs_baseline=None, dtype="bf16", data="synthetic",
+                higher_is_better=True, scaling="strong" if vp else "weak", vs_baseline=None,
+                dtype="f32 (split-bf16 x6 on the tensor cores, fp32 accumulate promoted per K=256)" if args.fp32 else "bf16", data="synthetic",
                 config=config_dict(args, shape),
                 e2e=dict(value=tokens_step / (e2e_ms_step * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=12,
                          ms_per_step=e2e_ms_step, loss=loss_e2e,
@@ -504,6 +510,8 @@ def main():
                     help="dp: data parallel over sample pairs (default); vp: vocab-parallel lm_head (same rows on every rank)")
     ap.add_argument("--vp-torch-exchange", action="store_true",
                     help="vp: exchange through torch.distributed around the C calls instead of the library's own communicator")
+    ap.add_argument("--fp32", action="store_true", help="fp32 hidden states / weights (BASELINE configs[0]'s precision): split-bf16 "
+                    "tensor-core passes with K-chunk promotion, fp32 gradients; the e2e loop and the variants are skipped")
     ap.add_argument("--no-dw", action="store_true", help="lm_head frozen (the shipped LoRA recipe): no dW")
     ap.add_argument("--dense", action="store_true", help="process every fed position (no row compaction)")
     ap.add_argument("--backward", default="auto", choices=["auto", "fused", "recompute"],
