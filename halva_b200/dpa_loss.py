@@ -46,11 +46,12 @@ def _check_inputs(h_pair, labels_pair, signs_pair, h_ref_pol, h_ref_frozen, labe
             raise ValueError("W / W_ref must be [V, H] with H matching the hidden states")
         frozen = (("h_ref_frozen", h_ref_frozen), ("W_ref", W_ref))
     for name, t in (("h_pair", h_pair), ("h_ref_pol", h_ref_pol), ("W", W)) + frozen:
-        if not t.is_cuda:
-            raise DPAError(f"{name} is on {t.device}: the DPA-loss path is CUDA (sm_100a) only, there is no CPU fallback")
         if t.dtype not in (torch.bfloat16, torch.float32) or t.dtype != h_pair.dtype:
             raise TypeError(f"{name} has dtype {t.dtype}; hidden states and lm_head weights must all be bf16 (the HALVA recipes "
                             "train in bf16) or all fp32 (split-bf16 tensor-core passes, fp32 gradients)")
+    for name, t in (("h_pair", h_pair), ("h_ref_pol", h_ref_pol), ("W", W)) + frozen:
+        if not t.is_cuda:
+            raise DPAError(f"{name} is on {t.device}: the DPA-loss path is CUDA (sm_100a) only, there is no CPU fallback")
     for name, t in (("labels_pair", labels_pair), ("signs_pair", signs_pair), ("labels_ref", labels_ref)):
         if t.dtype not in (torch.int64, torch.int32):
             raise TypeError(f"{name} must be int64 or int32")
@@ -273,6 +274,8 @@ def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.
             norm_weight_ref = norm_weight
     else:
         W_ref = W if W_ref is None else W_ref
+    if h_pair.dtype == torch.float32 and (ref_logits is not None or norm_weight is not None or backward == "fused"):
+        raise ValueError("fp32 inputs: ref_logits, norm_weight and backward='fused' belong to the bf16 execution")
     _check_inputs(h_pair, labels_pair, signs_pair, h_ref_pol, h_ref_frozen, labels_ref, W, W_ref, ref_logits)
     if need_dW is None:
         need_dW = bool(W.requires_grad)
@@ -295,8 +298,6 @@ def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.
     if h_pair.dtype == torch.float32:
         # fp32 model (BASELINE configs[0]): nn.Linear emits fp32 logits, so there is no bf16 rounding point to reproduce and
         # no bf16 logits to keep -- statistics forward + recompute backward on split-bf16 operands, fp32 dLogits (hi + lo)
-        if ref_logits is not None or norm_weight is not None or backward == "fused":
-            raise ValueError("fp32 inputs: ref_logits, norm_weight and backward='fused' belong to the bf16 execution")
         round_logits, backward = False, "recompute"
     if backward == "fused" and (not round_logits or vocab_group is not None):
         raise ValueError("backward='fused' needs round_logits=True and no vocab_group")

@@ -184,9 +184,16 @@ def fused_compute_loss(trainer, model, inputs, return_outputs: bool = False, num
 
     W, W_ref = head.weight, ref_head.weight
     with gathered_weight(W, W_ref):
+        shared = W_ref is W
+        if W.dtype != h_pair.dtype:
+            # torch.autocast(bf16) over fp32 master weights: F.linear casts the weight to the activations' dtype
+            # (differentiably), and so does the shim; an fp32 model with fp32 activations goes through the op's fp32 path
+            W_op, W_ref_op = W.to(h_pair.dtype), (None if shared else W_ref.detach().to(h_ref_frz.dtype))
+        else:
+            W_op, W_ref_op = W, (None if shared else W_ref.detach())
         loss, align, div = _dpa_loss_mod.dpa_loss(
-            h_pair, labels_pair, signs_pair, h_ref_pol, labels_ref, W, h_ref_frozen=h_ref_frz,
-            W_ref=None if W_ref is W else W_ref.detach(), alpha=alpha, round_logits=round_logits,
+            h_pair, labels_pair, signs_pair, h_ref_pol, labels_ref, W_op, h_ref_frozen=h_ref_frz,
+            W_ref=W_ref_op, alpha=alpha, round_logits=round_logits,
             need_dW=bool(W.requires_grad), backward=backward, **norm_kw)
 
     holder = getattr(trainer, "loss_holder", None)

@@ -51,6 +51,45 @@ def test_workspace_query_and_shape_validation():
     assert lib.dpa_query_workspace(C.byref(bad), C.byref(ws)) == -2
 
 
+def test_workspace_query_fp32_inputs_and_flag_conflicts():
+    """fp32 hidden states / weights (dtype 1): split-bf16 operands triple the packed buffers and add the split weights;
+    the flags that describe the bf16 execution are refused with them."""
+    from halva_b200._lib import FLAG_FUSED_GRAD, FLAG_NEED_DW, FLAG_ROUND_LOGITS, Shape, Workspace
+    lib = _lib()
+    kw = dict(B=1, T=1024, B_ref=1, T_ref=1024, H=4096, V=32000, V_local=32000, v_offset=0, index_dtype=0, chunk_rows=0)
+    w16, w32 = Workspace(), Workspace()
+    assert lib.dpa_query_workspace(C.byref(Shape(dtype=0, flags=FLAG_NEED_DW, **kw)), C.byref(w16)) == 0
+    assert lib.dpa_query_workspace(C.byref(Shape(dtype=1, flags=FLAG_NEED_DW, **kw)), C.byref(w32)) == 0
+    assert w32.state_bytes == w16.state_bytes
+    assert w32.fwd_bytes >= w16.fwd_bytes + 2 * 3 * 32000 * 4096 * 2          # W and W_ref as three bf16 parts each
+    assert w32.bwd_bytes > w16.bwd_bytes
+    for bad in (FLAG_ROUND_LOGITS, FLAG_FUSED_GRAD | FLAG_ROUND_LOGITS):
+        assert lib.dpa_query_workspace(C.byref(Shape(dtype=1, flags=bad, **kw)), C.byref(w32)) == -7
+        assert b"fp32 inputs" in lib.dpa_last_error()
+
+
+def test_python_op_argument_validation_without_gpu():
+    """The two forms of the frozen branch are exclusive, and ref_logits belongs to the chunked bf16 pass."""
+    import torch
+    from halva_b200 import dpa_loss
+    h = torch.zeros(2, 8, 64, dtype=torch.bfloat16)
+    y = torch.zeros(2, 8, dtype=torch.int64)
+    W = torch.zeros(64, 64, dtype=torch.bfloat16)
+    z = torch.zeros(1, 8, 64, dtype=torch.bfloat16)
+    with pytest.raises(ValueError, match="exactly one"):
+        dpa_loss(h, y, y, h[:1], y[:1], W, alpha=0.4)
+    with pytest.raises(ValueError, match="exactly one"):
+        dpa_loss(h, y, y, h[:1], y[:1], W, h_ref_frozen=h[:1], ref_logits=z, alpha=0.4)
+    with pytest.raises(ValueError, match="ref_logits needs"):
+        dpa_loss(h, y, y, h[:1], y[:1], W, ref_logits=z, alpha=0.4, round_logits=False)
+    with pytest.raises(ValueError, match="ref_logits must be"):
+        dpa_loss(h, y, y, h[:1], y[:1], W, ref_logits=z[:, :4], alpha=0.4)
+    with pytest.raises(TypeError):                        # mixed precisions
+        dpa_loss(h.float(), y, y, h[:1], y[:1], W, h_ref_frozen=h[:1], alpha=0.4)
+    with pytest.raises(ValueError, match="fp32 inputs"):
+        dpa_loss(h.float(), y, y, h[:1].float(), y[:1], W.float(), h_ref_frozen=h[:1].float(), alpha=0.4, backward="fused")
+
+
 def test_python_op_refuses_cpu_tensors():
     import torch
     from halva_b200 import DPAError, dpa_loss

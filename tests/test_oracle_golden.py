@@ -84,3 +84,20 @@ def test_live_reference_if_present():
                       t("labels_ref"), t("W"), t("W_ref"), alpha=float(g["alpha"]))
     assert abs(r["loss"].item() - g["ref_loss"]) < 1e-6
     assert rel(r["dW"].numpy(), g["ref_dW"]) < 1e-5
+
+
+def test_oracle_given_frozen_logits_equals_hidden_state_form(golden):
+    """`ref_logits` (the frozen model's logits handed over, what reference_forward(self.ref_model, ...) returns before its
+    shift, halva_trainer.py:516-520) is the same computation as h_ref_frz / W_ref."""
+    if "norm_w" in golden:
+        pytest.skip("the frozen branch of the norm cases goes through the folded RMSNorm")
+    g = golden
+    for mode in ("fp64", "bf16"):
+        a = _run(g, mode)
+        zr = g["h_ref_frz"].astype(np.float64) @ g["W_ref"].astype(np.float64).T
+        if mode == "bf16":
+            zr = dpa_oracle.bf16_round(zr)
+        b = dpa_oracle.dpa_loss(g["h_pair"], g["labels_pair"], g["signs_pair"], g["h_ref_pol"], None, g["labels_ref"], g["W"], None,
+                                float(g["alpha"]), mode=mode, ref_logits=zr)
+        assert a["loss"] == b["loss"] and a["div"] == b["div"]
+        assert np.array_equal(a["dH_ref"], b["dH_ref"]) and np.array_equal(a["dW"], b["dW"])

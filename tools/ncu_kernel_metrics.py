@@ -5,7 +5,7 @@
 """
 import csv, io, json, re, subprocess, sys
 
-CLASS = {"EpiStatsPair": "fwd_pair", "EpiStatsStore": "stash_ref", "EpiStoreRows": "dH", "EpiAccumF32": "dW", "EpiDzPair": "dz_pair",
+CLASS = {"EpiStatsPair": "fwd_pair", "EpiStatsStore": "stash_ref", "EpiStoreRows": "dH", "EpiAccumF32": "dW", "EpiAccumDW": "dW", "EpiDzPair": "dz_pair",
          "EpiStatsRef": "fwd_ref", "EpiDzRef": "dz_ref"}
 GB = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 T = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
