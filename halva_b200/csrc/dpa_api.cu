@@ -144,6 +144,18 @@ int launch_gemm(cudaStream_t st, int sms, const CUtensorMap& tmA, const CUtensor
   return DPA_OK;
 }
 
+// L2 super-block height (row-tile units that walk the column groups together) per GEMM class; 0 = the kernel's default.
+// The statistics GEMMs (K = H, short) want every row unit of the launch in one super-block -- the packed rows of a chunk
+// (<= 134 MB) then stay L2-resident while the lm_head streams through once; the gradient GEMMs (K = V or rows, long)
+// want a square-ish wave.  Overridable for measurements: DPA_SUPER_STATS / DPA_SUPER_DH / DPA_SUPER_DW.
+struct SuperM { int stats, dh, dw; };
+const SuperM& super_m() {
+  static const SuperM v = [] {
+    auto env = [](const char* n, int dflt) { const char* e = getenv(n); return e ? atoi(e) : dflt; };
+    return SuperM{env("DPA_SUPER_STATS", 0), env("DPA_SUPER_DH", 0), env("DPA_SUPER_DW", 0)};
+  }();
+  return v;
+}
 // cta_group of the single-accumulator GEMMs: 2 = CTA pairs on 256 x 256 tiles (default), 1 = one CTA per 128 x 256 tile.
 // Both are compiled; dpa_set_cta_group() / DPA_CTA_GROUP pick one (A/B measurements, bring-up).
 int g_cta_group = 0;
@@ -662,7 +674,7 @@ struct Plan {
   // statistics of every pair row; store_rows > 0 also keeps the bf16 logits of the first store_rows packed rows in dz
   template <bool ROUND> int fwd_pair(int store_rows) {
     using Epi = EpiStatsPair<kBnPair, ROUND>;
-    GemmWork w{meta, KIND_FWD_PAIR, 0, 0, 0, s.V_local, s.H, kTpuPair};
+    GemmWork w{meta, KIND_FWD_PAIR, 0, 0, 0, s.V_local, s.H, kTpuPair, super_m().stats};
     typename Epi::Params ep{at<int>(a->state, L.lab_pair), part_pair, L.cap_pair, s.V_local, s.v_offset,
                             store_rows > 0 ? dz : nullptr, L.ldz, store_rows};
     ProfScope ps(PK_FWD_PAIR, 1, st);
@@ -680,7 +692,7 @@ struct Plan {
   // policy + frozen logits of every reference-sample row side by side: statistics incl. the KL numerator
   template <bool ROUND> int fwd_ref() {
     using Epi = EpiStatsRef<kBnRef, ROUND>;
-    GemmWork w{meta, KIND_FWD_REF, 0, 0, 0, s.V_local, s.H, kTpuRef};
+    GemmWork w{meta, KIND_FWD_REF, 0, 0, 0, s.V_local, s.H, kTpuRef, super_m().stats};
     typename Epi::Params ep{part_ref, part_u, L.cap_ref, s.V_local};
     ProfScope ps(PK_FWD_REF, 1, st);
     if constexpr (!ROUND) {
@@ -697,7 +709,7 @@ struct Plan {
   // recompute the pair rows of chunk ch -> dz
   template <bool ROUND> int dz_pair(int ch) {
     using Epi = EpiDzPair<kBnPair, ROUND>;
-    GemmWork w{meta, KIND_DZ_PAIR, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair};
+    GemmWork w{meta, KIND_DZ_PAIR, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair, super_m().stats};
     typename Epi::Params ep{at<int>(a->state, L.lab_pair), at<float>(a->state, L.lse_pair), at<float>(a->state, L.coef_pair),
                             dz, L.ldz, ch * L.chunk_rows, s.V_local, s.v_offset, 0};
     ProfScope ps(PK_DZ_PAIR, 1, st);
@@ -715,7 +727,7 @@ struct Plan {
   // recompute the reference-sample rows of chunk ch (both models) -> dz
   template <bool ROUND> int dz_ref(int ch) {
     using Epi = EpiDzRef<kBnRef, ROUND>;
-    GemmWork w{meta, KIND_DZ_REF, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuRef};
+    GemmWork w{meta, KIND_DZ_REF, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuRef, super_m().stats};
     typename Epi::Params ep{meta, at<float>(a->state, L.lse_ref_p), at<float>(a->state, L.lse_ref_r), at<float>(a->state, L.coef_ref),
                             dz, L.ldz, ch * L.chunk_rows, s.V_local, 0};
     ProfScope ps(PK_DZ_REF, 1, st);
@@ -737,12 +749,12 @@ struct Plan {
     const bool given = a->ref_logits != nullptr;
     {
       ProfScope ps(PK_STASH_REF, given ? 1 : 2, st);
-      GemmWork wp{meta, KIND_STASH_POL, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair};
+      GemmWork wp{meta, KIND_STASH_POL, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair, super_m().stats};
       typename Epi::Params epp{meta, part2, dz, L.cap_ref, s.V_local, L.ldz, ch * L.chunk_rows, 0};
       int rc = launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHp, tmW256, tmW128, wp, epp, "stash_pol");
       if (rc) return rc;
       if (!given) {
-        GemmWork wf{meta, KIND_STASH_FRZ, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair};
+        GemmWork wf{meta, KIND_STASH_FRZ, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair, super_m().stats};
         typename Epi::Params epf{meta, part2, zr, L.cap_ref, s.V_local, L.ldz, ch * L.chunk_rows, 1};
         return launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHf, tmWr256, tmWr128, wf, epf, "stash_frz");
       }
@@ -764,7 +776,7 @@ struct Plan {
     if (split) {              // fp32 inputs: split-bf16 dz and operands, fp32 gradients; dW accumulates in place
       {
         using Epi = EpiStoreRows<kBnSplit, float>;
-        GemmWork w{meta, KIND_DH, ch, L.chunk_rows, 0, s.H, s.V_local, 1};
+        GemmWork w{meta, KIND_DH, ch, L.chunk_rows, 0, s.H, s.V_local, 1, super_m().dh};
         typename Epi::Params ep{meta, at<int>(a->state, L.src_pair), at<int>(a->state, L.src_ref),
                                 static_cast<float*>(a->dH_pair), static_cast<float*>(a->dH_ref), s.H, nullptr};
         const SplitMaps sm = split_maps(tmDzKS, tmWmnS, tmDzKS, tmWmnS);
@@ -774,7 +786,7 @@ struct Plan {
       }
       if (s.flags & DPA_FLAG_NEED_DW) {
         using Epi = EpiAccumF32<kBnSplit>;
-        GemmWork w{meta, KIND_DW, ch, L.chunk_rows, s.V_local, s.H, 0, 1};
+        GemmWork w{meta, KIND_DW, ch, L.chunk_rows, s.V_local, s.H, 0, 1, super_m().dw};
         typename Epi::Params ep{static_cast<float*>(a->dW), s.H, s.V_local, s.H, ch > 0};
         const SplitMaps sm = split_maps(tmDzMNS, tmHpMNS, tmDzMNS, tmHpMNS);
         ProfScope ps(PK_DW, 1, st);
@@ -784,7 +796,7 @@ struct Plan {
     }
     {
       using Epi = EpiStoreRows<256>;
-      GemmWork w{meta, KIND_DH, ch, L.chunk_rows, 0, s.H, s.V_local, 1};
+      GemmWork w{meta, KIND_DH, ch, L.chunk_rows, 0, s.H, s.V_local, 1, super_m().dh};
       typename Epi::Params ep{meta, at<int>(a->state, L.src_pair), at<int>(a->state, L.src_ref),
                               static_cast<__nv_bfloat16*>(a->dH_pair), static_cast<__nv_bfloat16*>(a->dH_ref), s.H, dH_packed};
       ProfScope ps(PK_DH, 1, st);
@@ -793,7 +805,7 @@ struct Plan {
     }
     if (dW32) {
       using Epi = EpiAccumDW<256>;
-      GemmWork w{meta, KIND_DW, ch, L.chunk_rows, s.V_local, s.H, 0, 1};
+      GemmWork w{meta, KIND_DW, ch, L.chunk_rows, s.V_local, s.H, 0, 1, super_m().dw};
       typename Epi::Params ep{meta, ch, L.chunk_rows, dW32, static_cast<__nv_bfloat16*>(a->dW), s.H, s.V_local, s.H};
       ProfScope ps(PK_DW, 1, st);
       return launch_single<Epi, MNMAJOR, MNMAJOR>(st, d, tmDzMN, tmHpMN, tmHpMN, w, ep, "dW");
@@ -1143,7 +1155,7 @@ int dpa_debug_gemm(const void* A, const void* B, float* D, int M, int N, int K, 
   CUtensorMap tmA, tmB;
   if ((rc = make_operand_tmap(d, &tmA, A, a_major, M, K, a_major == KMAJOR ? K : M, BM))) return rc;
   if ((rc = make_operand_tmap(d, &tmB, B, b_major, N, K, b_major == KMAJOR ? K : N, bn))) return rc;
-  GemmWork w{nullptr, KIND_STATIC, 0, 0, M, N, K, 1};
+  GemmWork w{nullptr, KIND_STATIC, 0, 0, M, N, K, 1, 0};
   if (bn == 128 && a_major == KMAJOR && b_major == KMAJOR) {     // the tile shape of the dual-accumulator kernels
     using Epi = EpiAccumF32<128>;
     typename Epi::Params ep{D, N, M, N, 0};

@@ -74,6 +74,7 @@ struct GemmWork {
   int n_cols;          // N extent
   int k_static;        // K extent unless KIND_DW
   int tiles_per_unit;  // consecutive column tiles per work unit
+  int super_m;         // row-tile units per L2 super-block of the unit order (0 = kSuperM)
 };
 
 struct TileRange {
@@ -234,13 +235,14 @@ __device__ __forceinline__ void dpa_gemm_body(const CUtensorMap& tmA, const CUte
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // unit -> (row-tile unit, column group): super-blocks of kSuperM row units walk the column groups together
+  // unit -> (row-tile unit, column group): super-blocks of super_m row units walk the column groups together
+  const int super_m = work.super_m > 0 ? work.super_m : kSuperM;
   auto decode = [&](int u, int& mu, int& ng) {
-    const int per_sb = kSuperM * n_groups;
+    const int per_sb = super_m * n_groups;
     const int sb = u / per_sb, r = u - sb * per_sb;
-    const int sb_m = min(kSuperM, m_units - sb * kSuperM);
+    const int sb_m = min(super_m, m_units - sb * super_m);
     ng = r / sb_m;
-    mu = sb * kSuperM + (r - ng * sb_m);
+    mu = sb * super_m + (r - ng * sb_m);
   };
 
   // The producer and MMA warps run their loops with all 32 lanes converged (lane 0 issues): lanes parked at the
