@@ -80,6 +80,22 @@ def test_fp32_golden_vs_reference_and_oracle(name):
     assert np.all(c["dH_ref"][:, -1] == 0) and np.all(c["dH_ref"][:, :-1][~o["active_ref"]] == 0)
 
 
+@pytest.mark.parametrize("name", ["tiny_bf16", "small_bf16"])
+def test_parity_gate_ii_reference_fp32_on_bf16_values(name):
+    """SURVEY.md section 8d, parity gate (ii): the reference executed in fp32 on the SAME bf16-valued inputs (`ref32_*` of the
+    bf16 golden cases) -- <= 1e-5 on the loss, <= 1e-4 on the gradients.  Fed as fp32 tensors, those values go through the
+    split path exactly (mid / lo parts are zero) and the gradients are not squeezed through a bf16 dLogits operand."""
+    g = load_golden(name)
+    assert str(g["dtype"]) == "bf16"
+    t = _cuda32(g)
+    assert torch.equal(t["W"], t["W"].to(torch.bfloat16).float())           # bf16-representable values
+    c = _run(t)
+    assert abs(c["loss"] - float(g["ref32_loss"])) <= TOL_LOSS * abs(float(g["ref32_loss"]))
+    assert abs(c["align"] - float(g["ref32_align"])) <= TOL_LOSS * abs(float(g["ref32_align"]))
+    for k in ("dH_pair", "dH_ref", "dW"):
+        assert rel(c[k], g["ref32_" + k]) <= TOL_GRAD, (name, k, rel(c[k], g["ref32_" + k]))
+
+
 def _synth32(seed=3, **over):
     from halva_b200.synth import CONFIGS, make_inputs
     shape = dataclasses.replace(CONFIGS["small"], **over)

@@ -37,11 +37,12 @@ def _worker(rank, world, port, out):
         shape = dataclasses.replace(CONFIGS["small"], V=1024, B=4, B_ref=4)
         t = make_inputs(shape, seed=5, device=dev, shared_head=False)       # identical on every rank (same seed)
 
-        def run(W, W_ref, sel_pair=None, sel_ref=None, **kw):
-            hp = (t["h_pair"] if sel_pair is None else t["h_pair"][sel_pair]).clone().requires_grad_(True)
-            hr = (t["h_ref_pol"] if sel_ref is None else t["h_ref_pol"][sel_ref]).clone().requires_grad_(True)
+        def run(W, W_ref, sel_pair=None, sel_ref=None, src=None, **kw):
+            src = t if src is None else src
+            hp = (src["h_pair"] if sel_pair is None else src["h_pair"][sel_pair]).clone().requires_grad_(True)
+            hr = (src["h_ref_pol"] if sel_ref is None else src["h_ref_pol"][sel_ref]).clone().requires_grad_(True)
             Wl = W.clone().requires_grad_(True)
-            pick = lambda k, s: t[k] if s is None else t[k][s]
+            pick = lambda k, s: src[k] if s is None else src[k][s]
             loss, align, div = dpa_loss(hp, pick("labels_pair", sel_pair), pick("signs_pair", sel_pair), hr, pick("labels_ref", sel_ref),
                                         Wl, h_ref_frozen=pick("h_ref_frz", sel_ref), W_ref=W_ref, alpha=t["alpha"], **kw)
             loss.backward()
@@ -55,6 +56,14 @@ def _worker(rank, world, port, out):
         assert abs(part[1].item() - full[1].item()) <= 1e-4 * abs(full[1].item()) + 1e-7
         assert _rel(part[2], full[2]) <= 5e-3 and _rel(part[3], full[3]) <= 5e-3        # bf16 partial sums all-reduced
         assert _rel(part[4], full[4][v0:v1]) <= 1e-3                                    # dW stays sharded
+        # ---- the same in fp32 (split-bf16 path; caller-side exchange, fp32 partial sums all-reduced)
+        t32 = {k: (v.float() if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in t.items()}
+        full32 = run(t32["W"], t32["W_ref"], src=t32)
+        part32 = run(t32["W"][v0:v1].contiguous(), t32["W_ref"][v0:v1].contiguous(), src=t32, vocab_group=dist.group.WORLD,
+                     v_offset=v0, vocab_size=shape.V)
+        assert part32[2].dtype == torch.float32
+        assert abs(part32[0].item() - full32[0].item()) <= 2e-6 * abs(full32[0].item()), (part32[0].item(), full32[0].item())
+        assert _rel(part32[2], full32[2]) <= 1e-5 and _rel(part32[3], full32[3]) <= 1e-5 and _rel(part32[4], full32[4][v0:v1]) <= 1e-5
         # the same with the library's own NCCL communicator: both exchange steps inside the two C calls
         from halva_b200 import _lib
         from halva_b200.dist import destroy_library_comm, init_library_comm
