@@ -173,9 +173,18 @@ def fused_compute_loss(trainer, model, inputs, return_outputs: bool = False, num
         ref_images = ref_images.squeeze(1)                                    # vila halva_trainer.py:760 (no-op unless dim 1 is 1)
     h_ref_pol, labels_ref, _ = final_hidden_states(policy, inputs["ref_input_ids"], ref_images, inputs["ref_labels"],
                                                    inputs["ref_attention_mask"], None, fn)
-    with torch.no_grad():
-        h_ref_frz, _, _ = final_hidden_states(frozen, inputs["ref_input_ids"], ref_images, inputs["ref_labels"],
-                                              inputs["ref_attention_mask"], None, fn)
+    # The frozen model's pass does not depend on the policy (halva_trainer.py:576-578): a data pipeline may cache its logits
+    # on the reference sample (post-splice, [B, T', V]) and put them into the batch as "ref_logits" -- then neither the
+    # frozen decoder nor its lm_head runs here, and the op reads the logits in place.
+    ref_logits = inputs.get("ref_logits") if hasattr(inputs, "get") else None
+    h_ref_frz = None
+    if ref_logits is None:
+        with torch.no_grad():
+            h_ref_frz, _, _ = final_hidden_states(frozen, inputs["ref_input_ids"], ref_images, inputs["ref_labels"],
+                                                  inputs["ref_attention_mask"], None, fn)
+    elif tuple(ref_logits.shape[:2]) != tuple(labels_ref.shape):
+        raise ValueError(f"inputs['ref_logits'] is {tuple(ref_logits.shape)}: expected the post-splice shape "
+                         f"[{labels_ref.shape[0]}, {labels_ref.shape[1]}, V] of the reference sample")
     norm_kw = {}
     if fn:
         n_pol, n_frz = decoder_and_head(policy)[0].norm, decoder_and_head(frozen)[0].norm
@@ -188,13 +197,13 @@ def fused_compute_loss(trainer, model, inputs, return_outputs: bool = False, num
         if W.dtype != h_pair.dtype:
             # torch.autocast(bf16) over fp32 master weights: F.linear casts the weight to the activations' dtype
             # (differentiably), and so does the shim; an fp32 model with fp32 activations goes through the op's fp32 path
-            W_op, W_ref_op = W.to(h_pair.dtype), (None if shared else W_ref.detach().to(h_ref_frz.dtype))
+            W_op, W_ref_op = W.to(h_pair.dtype), (None if shared else W_ref.detach().to(h_pair.dtype))
         else:
             W_op, W_ref_op = W, (None if shared else W_ref.detach())
+        frozen_kw = dict(h_ref_frozen=h_ref_frz, W_ref=W_ref_op) if ref_logits is None else dict(ref_logits=ref_logits)
         loss, align, div = _dpa_loss_mod.dpa_loss(
-            h_pair, labels_pair, signs_pair, h_ref_pol, labels_ref, W_op, h_ref_frozen=h_ref_frz,
-            W_ref=W_ref_op, alpha=alpha, round_logits=round_logits,
-            need_dW=bool(W.requires_grad), backward=backward, **norm_kw)
+            h_pair, labels_pair, signs_pair, h_ref_pol, labels_ref, W_op, alpha=alpha, round_logits=round_logits,
+            need_dW=bool(W.requires_grad), backward=backward, **frozen_kw, **norm_kw)
 
     holder = getattr(trainer, "loss_holder", None)
     if isinstance(holder, dict) and all(k in holder for k in ("contrastive_loss", "divergence", "loss")):

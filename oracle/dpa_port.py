@@ -34,8 +34,9 @@ def _phrase_sums(logps, signs):
     return out
 
 
-def dpa_loss_torch(h_pair, labels_pair, signs_pair, h_ref_pol, h_ref_frz, labels_ref, W, W_ref, alpha):
-    """Returns (loss, align, div); differentiable w.r.t. h_pair, h_ref_pol, W."""
+def dpa_loss_torch(h_pair, labels_pair, signs_pair, h_ref_pol, h_ref_frz, labels_ref, W, W_ref, alpha, ref_logits=None):
+    """Returns (loss, align, div); differentiable w.r.t. h_pair, h_ref_pol, W.
+    ref_logits [B,T,V]: the frozen model's (unshifted) logits given instead of h_ref_frz / W_ref."""
     B = h_pair.shape[0] // 2
     lp, _ = _token_logps(h_pair, W, labels_pair)
     y = labels_pair[:, 1:]
@@ -46,7 +47,10 @@ def dpa_loss_torch(h_pair, labels_pair, signs_pair, h_ref_pol, h_ref_frz, labels
     align = torch.log(1 + torch.exp(N - P)).mean()
     _, z_pol = _token_logps(h_ref_pol, W, labels_ref)
     with torch.no_grad():
-        _, z_frz = _token_logps(h_ref_frz, W_ref, labels_ref)
+        if ref_logits is not None:
+            z_frz = ref_logits.float()[:, :-1, :]
+        else:
+            _, z_frz = _token_logps(h_ref_frz, W_ref, labels_ref)
     q = F.softmax(z_frz, -1)
     p = F.softmax(z_pol, -1)
     kl = q * (q.log() - p.log()) * (labels_ref[:, 1:] != IGNORE).unsqueeze(-1)

@@ -139,9 +139,9 @@ def _trainer(policy, frozen, alpha=0.4, vila=False):
     return t
 
 
-def _port_as_op(h_pair, labels_pair, signs_pair, h_ref_pol, labels_ref, W, *, h_ref_frozen, W_ref=None, alpha, **kw):
+def _port_as_op(h_pair, labels_pair, signs_pair, h_ref_pol, labels_ref, W, *, h_ref_frozen=None, W_ref=None, ref_logits=None, alpha, **kw):
     return dpa_port.dpa_loss_torch(h_pair, labels_pair, signs_pair, h_ref_pol, h_ref_frozen, labels_ref, W,
-                                   W if W_ref is None else W_ref, alpha)
+                                   W if W_ref is None else W_ref, alpha, ref_logits=ref_logits)
 
 
 def _grads(model):
@@ -216,6 +216,41 @@ def test_shim_matches_lifted_reference_vila(monkeypatch):
     # the VILA logging keeps working: same three series as the reference appends (vila halva_trainer.py:846-848)
     for k in ("contrastive_loss", "divergence", "loss"):
         assert abs(tr.loss_holder[k][0] - ref_tr.loss_holder[k][0]) <= 2e-6, k
+
+
+def test_shim_takes_cached_frozen_logits_from_the_batch(monkeypatch):
+    """inputs["ref_logits"] (the frozen model's logits on the reference sample, post-splice) replaces the frozen pass:
+    same loss and gradients, and the frozen model is never called."""
+    from halva_b200 import trainer as shim
+    monkeypatch.setattr(shim._dpa_loss_mod, "dpa_loss", _port_as_op)
+    pol, frz = _models(seed=2)
+    inputs = make_inputs(seed=2)
+    base = shim.fused_compute_loss(_trainer(pol, frz), pol, inputs)
+    base.backward()
+    g0 = _grads(pol)
+    pol.zero_grad()
+    with torch.no_grad():
+        h, _, _ = shim.final_hidden_states(frz, inputs["ref_input_ids"], inputs["ref_images"], inputs["ref_labels"],
+                                           inputs["ref_attention_mask"])
+        cached = frz.lm_head(h)
+
+    class Untouchable:
+        def __getattr__(self, name):
+            raise AssertionError("the frozen model must not be used when its logits are given")
+
+    tr = _trainer(pol, frz)
+    calls = []
+    orig = shim.final_hidden_states
+    monkeypatch.setattr(shim, "final_hidden_states", lambda m, *a, **k: (calls.append(m is frz), orig(m, *a, **k))[1])
+    loss = shim.fused_compute_loss(tr, pol, dict(inputs, ref_logits=cached))
+    loss.backward()
+    assert not any(calls), "frozen decoder ran"
+    assert abs(loss.item() - base.item()) <= 1e-6 * abs(base.item())
+    g = _grads(pol)
+    for n in g0:
+        assert torch.allclose(g[n], g0[n], rtol=1e-5, atol=1e-7), n
+    with pytest.raises(ValueError, match="post-splice"):
+        shim.fused_compute_loss(tr, pol, dict(inputs, ref_logits=cached[:, :-1]))
 
 
 def test_stack_pair_batch_pad_values():
