@@ -9,11 +9,12 @@
 //   warp 5 (one lane)  tcgen05.mma issuer; tcgen05.commit frees smem slots and publishes accumulators
 //   warp 6             TMEM allocator (all 512 columns: two accumulator stages)
 //
-// The DPA loss uses it through seven epilogues (see dpa_api.cu, struct Plan): forward row statistics of pair rows
+// The DPA loss uses it through its epilogues (see dpa_api.cu, struct Plan): forward row statistics of pair rows
 // (optionally keeping their bf16 logits), statistics + kept logits of reference-sample rows (fused-gradient forward),
 // the DUAL variants that hold the policy and frozen-model logits of the same tile side by side in TMEM (statistics
 // incl. the KL numerator; recompute of dLogits), the recompute of pair-row dLogits, and the two gradient GEMMs
-// dH = dZ*W, dW = dZ^T*H.
+// dH = dZ*W, dW = dZ^T*H.  fp32 inputs run the same classes through dpa_gemm_split_kernel: split-bf16 operand triples
+// as six K segments, K-chunk promotion of the accumulators through registers (GemmCfg::NSEG / PROMOTE).
 // A work "unit" is (row tile, group of consecutive column tiles); row counts live in device memory
 // (DpaMeta) so that nothing on the path needs a host synchronisation.
 #pragma once
@@ -710,7 +711,8 @@ struct EpiAccumF32 {
   __device__ static void unit_begin(const Params& p, State& s, int, int trow_global) {
     s.out = trow_global < p.m_extent ? p.out + (size_t)trow_global * p.ld : nullptr;
   }
-  // (the chunked dW accumulation of the DPA path uses EpiAccumDW below; this one serves the debug GEMM)
+  // (the chunked bf16 dW accumulation of the DPA path uses EpiAccumDW below; this one serves the fp32 path, whose fp32 dW
+  //  is its own accumulator, and the debug GEMM)
   __device__ static void tile(const Params& p, State& s, uint32_t taddr, int col0) {
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
