@@ -345,6 +345,13 @@ def run_ours(args):
                 traceback.print_exc()
             torch.cuda.synchronize()
 
+    # ---- end to end: host (pinned) buffers in, losses out, H2D double-buffered against the previous step's compute
+    ms_e2e, h2d_bytes, loss_e2e = None, 0, None
+    if not args.no_e2e:
+        ms_e2e, h2d_bytes, loss_e2e = run_e2e(args, tensors, step, barrier, dev, world)
+    # (measured BEFORE the variants: every further minute under load leaves the GPU in a hotter / lower power state, and the
+    #  end-to-end number is the headline -- it should see the same device state as the device-resident timing above)
+
     # ---- variant: lm_head frozen (the shipped LoRA recipe, /root/reference/llava/train/train_halva.py:167-168): no dW
     ms_frozen = None
     if need_dw and not args.no_variants:
@@ -405,10 +412,44 @@ def run_ours(args):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ms_given = tt.item()
 
-    # ---- end to end: host (pinned) buffers in, losses out, H2D double-buffered against the previous step's compute
-    ms_e2e, h2d_bytes, loss_e2e = None, 0, None
-    if not args.no_e2e:
-        ms_e2e, h2d_bytes, loss_e2e = run_e2e(args, tensors, step, barrier, dev, world)
+    # ---- variant: the reference recipe's form of the same 16 pairs -- 4 micro-batches of 4 pairs, gradients accumulated
+    #      (per_device_train_batch_size 4 x gradient_accumulation_steps 4, /root/reference/src/hallava_7b.sh:21-22)
+    ms_micro = None
+    if not args.no_variants and not vp and shape.B % 4 == 0 and shape.B_ref == shape.B and shape.B >= 8:
+        mb = shape.B // 4
+        micro = []
+        for i in range(4):
+            rows = torch.arange(i * mb, (i + 1) * mb, device=dev)
+            pr = torch.cat([rows, shape.B + rows])
+            micro.append(dict(h_pair=t["h_pair"].detach()[pr].clone().requires_grad_(True), labels_pair=t["labels_pair"][pr].contiguous(),
+                              signs_pair=t["signs_pair"][pr].contiguous(), h_ref_pol=t["h_ref_pol"].detach()[rows].clone().requires_grad_(True),
+                              h_ref_frz=t["h_ref_frz"][rows].contiguous(), labels_ref=t["labels_ref"][rows].contiguous()))
+
+        def step_micro():
+            W.grad = None
+            for m in micro:
+                m["h_pair"].grad = None
+                m["h_ref_pol"].grad = None
+                l, _, _ = dpa_loss(m["h_pair"], m["labels_pair"], m["signs_pair"], m["h_ref_pol"], m["labels_ref"], W,
+                                   h_ref_frozen=m["h_ref_frz"], alpha=shape.alpha, dense=args.dense, chunk_rows=args.chunk_rows,
+                                   backward=args.backward)
+                (l / 4).backward()                       # W.grad accumulates over the micro-batches, as under grad accumulation
+
+        for _ in range(3):
+            step_micro()
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step_micro()
+        e1.record()
+        barrier()
+        ms_micro = e0.elapsed_time(e1) / args.steps
+        del micro
+        if world > 1:
+            tt = torch.tensor([ms_micro], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms_micro = tt.item()
+
     clocks = sampler.finish() if sampler else None
 
 
@@ -498,6 +539,11 @@ def run_ours(args):
             ms_per_step=ms_given, value=tokens_step / (ms_given * 1e-3), unit=UNIT, loss=loss_given,
             note="same batch, the frozen model's bf16 logits handed over as ref_logits [B_ref,T_ref,V] instead of its hidden "
                  "states: 3 instead of 4 lm_head GEMMs per reference-sample row")
+    if ms_micro:
+        line.setdefault("variants", {})["micro_4x4"] = dict(
+            ms_per_step=ms_micro, value=tokens_step / (ms_micro * 1e-3), unit=UNIT,
+            note="the same pairs as 4 micro-batches of a quarter each with gradient accumulation (the reference recipe's "
+                 "per-device batch 4 x accumulation 4): 4 forward+backward calls per step, dW accumulated by autograd")
     if world == 1 and not args.no_cpu_baseline:
         r = time_cpu_port(2, 1)
         line["cpu_baseline"] = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="port", sample=r["sample"],

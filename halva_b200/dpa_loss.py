@@ -199,6 +199,7 @@ class DPALossFn(torch.autograd.Function):
         ctx.vocab_group = vocab_group
         loss, align, div = call.losses[0], call.losses[1], call.losses[2]
         ctx.mark_non_differentiable(align, div)
+        DPALossFn._last_status = call.status          # (strict mode under no_grad: there is no grad_fn to carry it)
         return loss, align, div
 
     @staticmethod
@@ -220,7 +221,7 @@ def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.
              round_logits: bool = True, need_dW: Optional[bool] = None, dense: bool = False, chunk_rows: int = 0,
              vocab_group=None, v_offset: Optional[int] = None, vocab_size: Optional[int] = None,
              backward: str = "auto", norm_weight: Optional[torch.Tensor] = None,
-             norm_weight_ref: Optional[torch.Tensor] = None, norm_eps: float = 1e-6,
+             norm_weight_ref: Optional[torch.Tensor] = None, norm_eps: float = 1e-6, strict: bool = False,
              ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """Fused DPA loss.  Returns (loss, alignment_loss, divergence) as 0-dim fp32 CUDA tensors; `loss` carries grad.
 
@@ -262,6 +263,10 @@ def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.
                                    is needed and there is no vocab_group, else "recompute".
     Ill-formed phrase ids (K_pos != K_neg, K == 0, id > 255) make the losses NaN and set bits in
     `read_status(loss)["status"]`; the reference raises / returns NaN there.
+    strict                         True: read the status word back after the forward (ONE host synchronisation) and raise
+                                   like the reference does -- RuntimeError for K_pos != K_neg (the broadcast failure of
+                                   halva_trainer.py:567), ValueError for phrase ids / labels out of range; K == 0 stays a
+                                   NaN loss, as in the reference.  Off by default: the path is free of host syncs.
     """
     if (ref_logits is None) == (h_ref_frozen is None):
         raise ValueError("give exactly one of h_ref_frozen (+ W_ref) and ref_logits")
@@ -305,7 +310,22 @@ def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.
     out = DPALossFn.apply(h_pair, h_ref_pol, W, norm_weight, labels_pair, signs_pair, labels_ref, h_ref_frozen, W_ref, float(alpha),
                           bool(round_logits), bool(need_dW), bool(dense), int(chunk_rows), vocab_group, int(v_offset),
                           int(vocab_size), fused, norm_weight_ref, float(norm_eps), ref_logits)
+    if strict:
+        st = _status_of(out[0])
+        if st is not None:
+            bits = int(st[0])
+            if bits & _lib.STATUS_K_MISMATCH:
+                raise RuntimeError(f"The size of tensor a ({int(st[4])}) must match the size of tensor b ({int(st[5])}) at non-singleton "
+                                   "dimension 1 (phrase columns of the correct / hallucinated halves, halva_trainer.py:567)")
+            if bits & (_lib.STATUS_BAD_SIGN | _lib.STATUS_BAD_LABEL):
+                raise ValueError("phrase id outside [0, 255] or label outside [0, V) (status %d)" % bits)
     return out
+
+
+def _status_of(loss: torch.Tensor):
+    fn = loss.grad_fn
+    st = getattr(fn, "status_t", None) if fn is not None else getattr(DPALossFn, "_last_status", None)
+    return None if st is None else st.cpu().tolist()
 
 
 def read_status(loss: torch.Tensor):

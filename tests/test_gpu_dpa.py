@@ -216,6 +216,17 @@ def test_quirks_match_reference():
     st = read_status(loss)
     if st["K_pos"] != st["K_neg"]:
         assert torch.isnan(loss).item() and (st["status"] & 2)
+        # strict=True: one host sync after the forward, then the reference's own error class (with and without grad)
+        with pytest.raises(RuntimeError, match="must match the size"):
+            dpa_loss(hp, t["labels_pair"], s, t["h_ref_pol"], t["labels_ref"], t["W"], h_ref_frozen=t["h_ref_frz"], alpha=0.4, strict=True)
+        with torch.no_grad(), pytest.raises(RuntimeError, match="must match the size"):
+            dpa_loss(t["h_pair"], t["labels_pair"], s, t["h_ref_pol"], t["labels_ref"], t["W"], h_ref_frozen=t["h_ref_frz"], alpha=0.4, strict=True)
+    bad = t["signs_pair"].clone()
+    bad[0, -3] = 300
+    with pytest.raises(ValueError, match="phrase id"):
+        dpa_loss(hp, t["labels_pair"], bad, t["h_ref_pol"], t["labels_ref"], t["W"], h_ref_frozen=t["h_ref_frz"], alpha=0.4, strict=True)
+    ok, _, _ = dpa_loss(hp, t["labels_pair"], t["signs_pair"], t["h_ref_pol"], t["labels_ref"], t["W"], h_ref_frozen=t["h_ref_frz"], alpha=0.4, strict=True)
+    assert torch.isfinite(ok).item()
 
 
 def test_rejects_cpu_and_fp32_inputs():
