@@ -63,3 +63,56 @@ def test_random_shape_vs_oracle(i):
             assert not f(g).any(), (over, fl, k)
         else:
             assert rel(f(g), o[k]) <= 1e-2, (over, fl, k, rel(f(g), o[k]))
+
+
+@pytest.mark.parametrize("i", range(24))
+def test_random_shape_fp32_and_given_logits(i):
+    """The same kind of sweep for the two other input forms: fp32 hidden states / weights (split-bf16 path, against the fp64
+    oracle at the fp32 tolerances) and the frozen model's logits given (against the oracle fed the same logits)."""
+    from halva_b200 import dpa_loss, read_status
+    from halva_b200.synth import CONFIGS, make_inputs
+    over, fl = _case(100 + i)
+    shape = dataclasses.replace(CONFIGS["tiny"], **over)
+    fp32 = i % 2 == 0
+    t = make_inputs(shape, seed=900 + i, device="cuda", shared_head=fl["shared"], plant=3.0,
+                    dtype=torch.float32 if fp32 else torch.bfloat16)
+    hp = t["h_pair"].clone().requires_grad_(True)
+    hr = t["h_ref_pol"].clone().requires_grad_(True)
+    W = t["W"].clone().requires_grad_(True)
+    ids = {k: (t[k].to(torch.int32) if fl["i32"] else t[k]) for k in ("labels_pair", "signs_pair", "labels_ref")}
+    f = lambda x: x.detach().double().cpu().numpy()
+    common = dict(alpha=t["alpha"], dense=fl["dense"], chunk_rows=fl["chunk_rows"])
+    okw = {}
+    if fp32:
+        frozen = dict(h_ref_frozen=t["h_ref_frz"], W_ref=None if fl["shared"] else t["W_ref"])
+        mode, tol_loss, tol_div, tol_grad = "fp64", 1e-5, 1e-4, 1e-4
+    else:
+        zr = (t["h_ref_frz"].float() @ t["W_ref"].float().T).to(torch.bfloat16)
+        if i % 4 == 1:
+            zr = zr.float()
+        frozen = dict(ref_logits=zr)
+        okw = dict(ref_logits=f(zr))
+        mode, tol_loss, tol_div, tol_grad = "bf16", 1e-3, 1e-3, 1e-2
+    loss, align, div = dpa_loss(hp, ids["labels_pair"], ids["signs_pair"], hr, ids["labels_ref"], W, **frozen, **common)
+    loss.backward()
+    st = read_status(loss)
+    try:
+        o = dpa_oracle.dpa_loss(f(t["h_pair"]), t["labels_pair"].cpu().numpy(), t["signs_pair"].cpu().numpy(), f(t["h_ref_pol"]),
+                                None if okw else f(t["h_ref_frz"]), t["labels_ref"].cpu().numpy(), f(t["W"]),
+                                None if okw else f(t["W_ref"]), t["alpha"], mode=mode, **okw)
+    except dpa_oracle.PhraseShapeError:
+        assert st["status"] != 0 and torch.isnan(loss).item(), (over, fl, st)
+        return
+    assert st["status"] == 0, (over, fl, st)
+    if not np.isfinite(o["loss"]):
+        assert not np.isfinite(loss.item())
+        return
+    assert abs(loss.item() - o["loss"]) <= tol_loss * abs(o["loss"]), (fp32, over, fl, loss.item(), o["loss"])
+    assert abs(align.item() - o["align"]) <= tol_loss * abs(o["align"]), (fp32, over, fl)
+    assert abs(div.item() - o["div"]) <= tol_div * abs(o["div"]) + 5e-7, (fp32, over, fl, div.item(), o["div"])
+    for k, g in (("dH_pair", hp.grad), ("dH_ref", hr.grad), ("dW", W.grad)):
+        assert g.dtype == t["W"].dtype
+        if np.linalg.norm(o[k]) == 0:
+            assert not f(g).any(), (fp32, over, fl, k)
+        else:
+            assert rel(f(g), o[k]) <= tol_grad, (fp32, over, fl, k, rel(f(g), o[k]))
