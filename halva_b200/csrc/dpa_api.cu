@@ -561,7 +561,8 @@ struct NcclApi {
   const char* (*GetErrorString)(int) = nullptr;
 };
 NcclApi g_nccl;
-struct Comm { NcclComm comm = nullptr; int rank = 0, world = 1, device = -1; };
+struct Comm { NcclComm comm = nullptr; int rank = 0, world = 1, device = -1; cudaStream_t stream = nullptr; };   // stream: the exchange
+// of the backward runs beside the caller's stream (fork / join with events) so that it overlaps the remaining GEMMs
 Comm g_comm;
 constexpr int kNcclUint8 = 1, kNcclBfloat16 = 9, kNcclSum = 0;
 
@@ -594,6 +595,9 @@ struct Plan {
   float4* part_pair = nullptr; float4* part_ref = nullptr; float* part_u = nullptr;
   CUtensorMap tmHp, tmHf, tmW256, tmW128, tmW64, tmWr256, tmWr128, tmWr64, tmDzK, tmWmn, tmDzMN, tmHpMN;
   // fp32 inputs: the maps above cover the high-order bf16 parts (in scratch), these the mid ([0]) and low-order ([1]) parts
+  // vocab-parallel with the library's communicator: after chunk ch's dH GEMM its packed rows are all-reduced on the
+  // communicator's own stream while this stream goes on with dW and the next chunk (joined before the final scatter)
+  int n_tot_host = 0;
   const Layout::Split* split = nullptr;
   size_t dz_part = 0;                      // elements between the hi / mid / lo copies of dz
   CUtensorMap tmHpS[2], tmHfS[2], tmW128S[2], tmW64S[2], tmWr64S[2], tmDzKS[2], tmWmnS[2], tmDzMNS[2], tmHpMNS[2];
@@ -799,9 +803,12 @@ struct Plan {
       GemmWork w{meta, KIND_DH, ch, L.chunk_rows, 0, s.H, s.V_local, 1, super_m().dh};
       typename Epi::Params ep{meta, at<int>(a->state, L.src_pair), at<int>(a->state, L.src_ref),
                               static_cast<__nv_bfloat16*>(a->dH_pair), static_cast<__nv_bfloat16*>(a->dH_ref), s.H, dH_packed};
-      ProfScope ps(PK_DH, 1, st);
-      int rc = launch_single<Epi, KMAJOR, MNMAJOR>(st, d, tmDzK, tmWmn, tmWmn, w, ep, "dH");
-      if (rc) return rc;
+      {
+        ProfScope ps(PK_DH, 1, st);
+        int rc = launch_single<Epi, KMAJOR, MNMAJOR>(st, d, tmDzK, tmWmn, tmWmn, w, ep, "dH");
+        if (rc) return rc;
+      }
+      if (dH_packed) { int rc = exchange_dH_chunk(ch); if (rc) return rc; }
     }
     if (dW32) {
       using Epi = EpiAccumDW<256>;
@@ -810,6 +817,25 @@ struct Plan {
       ProfScope ps(PK_DW, 1, st);
       return launch_single<Epi, MNMAJOR, MNMAJOR>(st, d, tmDzMN, tmHpMN, tmHpMN, w, ep, "dW");
     }
+    return DPA_OK;
+  }
+  int exchange_dH_chunk(int ch) {
+    const size_t r0 = (size_t)ch * L.chunk_rows, r1 = std::min<size_t>(r0 + L.chunk_rows, (size_t)n_tot_host);
+    if (r1 <= r0) return DPA_OK;
+    cudaEvent_t e;
+    CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(e, st));
+    CUDA_TRY(cudaStreamWaitEvent(g_comm.stream, e, 0));
+    CUDA_TRY(cudaEventDestroy(e));              // released once it has completed
+    NCCL_TRY(g_nccl.AllReduce(dH_packed + r0 * s.H, dH_packed + r0 * s.H, (r1 - r0) * s.H, kNcclBfloat16, kNcclSum, g_comm.comm, g_comm.stream));
+    return DPA_OK;
+  }
+  int join_exchange() {                          // the caller's stream waits for everything queued on the communicator's stream
+    cudaEvent_t e;
+    CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(e, g_comm.stream));
+    CUDA_TRY(cudaStreamWaitEvent(st, e, 0));
+    CUDA_TRY(cudaEventDestroy(e));
     return DPA_OK;
   }
   int zero_grad_outputs() {
@@ -963,6 +989,7 @@ int run_backward(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, cuda
     p.dH_packed = at<__nv_bfloat16>(a->scratch, L.b_dHp);
     CUDA_TRY(cudaMemcpyAsync(&n_tot_host, &p.meta->n_tot, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    p.n_tot_host = n_tot_host;
   }
   if ((rc = p.coef(a->d_loss))) return rc;
   if ((rc = run_gather(a, L, d, a->scratch, L.b_Hp, L.b_Hf, st))) return rc;
@@ -972,14 +999,10 @@ int run_backward(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, cuda
     if (vp && (long long)ch * L.chunk_rows >= n_tot_host) break;
     if ((long long)ch * L.chunk_rows < L.cap_pair && (rc = p.dz_pair<ROUND>(ch))) return rc;
     if ((rc = p.dz_ref<ROUND>(ch))) return rc;
-    if ((rc = p.grad_gemms(ch))) return rc;
-    if (vp) {
-      const size_t r0 = (size_t)ch * L.chunk_rows, r1 = std::min<size_t>(r0 + L.chunk_rows, (size_t)n_tot_host);
-      ProfScope ps(PK_MISC, 0, st);
-      NCCL_TRY(g_nccl.AllReduce(p.dH_packed + r0 * s.H, p.dH_packed + r0 * s.H, (r1 - r0) * s.H, kNcclBfloat16, kNcclSum, g_comm.comm, st));
-    }
+    if ((rc = p.grad_gemms(ch))) return rc;       // (vp: the chunk's dH rows go to the exchange stream right after the dH GEMM)
   }
   if (vp) {
+    if ((rc = p.join_exchange())) return rc;
     ScatterArgs sc{p.meta, at<int>(a->state, L.src_pair), at<int>(a->state, L.src_ref), p.dH_packed,
                    static_cast<__nv_bfloat16*>(a->dH_pair), static_cast<__nv_bfloat16*>(a->dH_ref), s.H};
     ProfScope ps(PK_MISC, 1, st);
@@ -1100,11 +1123,13 @@ int dpa_comm_init(int rank, int world, const void* unique_id128) {
   NcclComm c = nullptr;
   NCCL_TRY(g_nccl.CommInitRank(&c, world, id, rank));
   g_comm.comm = c; g_comm.rank = rank; g_comm.world = world; g_comm.device = dev;
+  CUDA_TRY(cudaStreamCreateWithFlags(&g_comm.stream, cudaStreamNonBlocking));
   g_layout_comm_world = world;
   return DPA_OK;
 }
 
 int dpa_comm_destroy(void) {
+  if (g_comm.stream) { cudaStreamSynchronize(g_comm.stream); cudaStreamDestroy(g_comm.stream); }
   if (g_comm.comm) NCCL_TRY(g_nccl.CommDestroy(g_comm.comm));
   g_comm = Comm{};
   g_layout_comm_world = 1;
