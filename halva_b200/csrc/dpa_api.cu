@@ -601,6 +601,7 @@ struct Plan {
   const Layout::Split* split = nullptr;
   size_t dz_part = 0;                      // elements between the hi / mid / lo copies of dz
   CUtensorMap tmHpS[2], tmHfS[2], tmW128S[2], tmW64S[2], tmWr64S[2], tmDzKS[2], tmWmnS[2], tmDzMNS[2], tmHpMNS[2];
+  CUtensorMap tmW32, tmWr32, tmW32S[2], tmWr32S[2];       // 32-row boxes: each CTA's half of a 64-column dual tile (CTA pairs)
 
   Plan(const dpa_args_t* a_, const Layout& L_, const DeviceInfo* d_, cudaStream_t st_)
       : a(a_), L(L_), d(d_), st(st_), s(a_->shape), meta(at<DpaMeta>(a_->state, L_.meta)) {}
@@ -644,6 +645,8 @@ struct Plan {
     if (split) {
       const size_t hp_part = (size_t)cap_tot * s.H * 2, hf_part = (size_t)L.cap_ref * s.H * 2;
       dz_part = (size_t)L.chunk_rows * L.ldz;
+      if ((rc = make_operand_tmap(d, &tmW32, Wb, KMAJOR, s.V_local, s.H, s.H, 32))) return rc;
+      if ((rc = make_operand_tmap(d, &tmWr32, Wrb, KMAJOR, s.V_local, s.H, s.H, 32))) return rc;
       for (int p = 0; p < 2; ++p) {
         char* HpP = Hp + (p + 1) * hp_part;
         const char* WP = W3 + (p + 1) * w_part;
@@ -652,6 +655,8 @@ struct Plan {
         if ((rc = make_operand_tmap(d, &tmW128S[p], WP, KMAJOR, s.V_local, s.H, s.H, 128))) return rc;
         if ((rc = make_operand_tmap(d, &tmW64S[p], WP, KMAJOR, s.V_local, s.H, s.H, 64))) return rc;
         if ((rc = make_operand_tmap(d, &tmWr64S[p], Wr3 + (p + 1) * w_part, KMAJOR, s.V_local, s.H, s.H, 64))) return rc;
+        if ((rc = make_operand_tmap(d, &tmW32S[p], WP, KMAJOR, s.V_local, s.H, s.H, 32))) return rc;
+        if ((rc = make_operand_tmap(d, &tmWr32S[p], Wr3 + (p + 1) * w_part, KMAJOR, s.V_local, s.H, s.H, 32))) return rc;
         if (dz) {
           __nv_bfloat16* dzP = dz + (p + 1) * dz_part;
           if ((rc = make_operand_tmap(d, &tmDzKS[p], dzP, KMAJOR, L.chunk_rows, s.V_local, L.ldz, BM))) return rc;
@@ -668,12 +673,41 @@ struct Plan {
     for (int p = 0; p < 2; ++p) { m.A[p] = A[p]; m.B[p] = B[p]; m.A2[p] = A2[p]; m.B2[p] = B2[p]; }
     return m;
   }
-  // split-bf16 GEMM configurations (fp32 inputs): 128-column accumulators (the K-chunk promotion keeps them in registers),
-  // one CTA per 128-row tile; the column groups of the statistics stay the 1280 columns of the bf16 tilings
+  // split-bf16 GEMM configurations (fp32 inputs): 128-column accumulators (the K-chunk promotion keeps them in registers);
+  // the column groups of the statistics stay the 1280 columns of the bf16 tilings
   static constexpr int kBnSplit = 128, kBnSplitDual = 64;
   static constexpr int kTpuSplit = kBnPair * kTpuPair / kBnSplit, kTpuSplitDual = kBnRef * kTpuRef / kBnSplitDual;
-  template <int AMAJ, int BMAJ> using SplitCfg = GemmCfg<kBnSplit, false, AMAJ, BMAJ, 1, 6>;
-  using SplitDualCfg = GemmCfg<kBnSplitDual, true, KMAJOR, KMAJOR, 1, 6>;
+  template <int AMAJ, int BMAJ, int CG> using SplitCfg = GemmCfg<kBnSplit, false, AMAJ, BMAJ, CG, 6>;
+  template <int CG> using SplitDualCfg = GemmCfg<kBnSplitDual, true, KMAJOR, KMAJOR, CG, 6>;
+  // cta_group of the split kernels: 2 (default) = CTA pairs on 256-row tiles, each CTA staging half of the B tile -- less
+  // L2 -> smem traffic per FLOP, which is what bounds these small-tile kernels (ncu: tensor pipe 36-48 % active with one
+  // CTA per tile; cfg-1 fp32 12.1 -> 9.0 ms with pairs); 1 = one CTA per 128-row tile.  DPA_SPLIT_CG_SINGLE /
+  // DPA_SPLIT_CG_DUAL override (measurements).
+  static int split_cg(bool dual) {
+    static const int v[2] = {[] { const char* e = getenv("DPA_SPLIT_CG_SINGLE"); return e ? atoi(e) : 2; }(),
+                             [] { const char* e = getenv("DPA_SPLIT_CG_DUAL"); return e ? atoi(e) : 2; }()};
+    return v[dual ? 1 : 0] == 1 ? 1 : 2;
+  }
+  // K-major B operand: bx1 / bx2 = maps whose box holds BN (one CTA) or BN / 2 (CTA pair) rows, with their mid / lo parts
+  template <int AMAJ, int BMAJ, class Epi>
+  int launch_split(const CUtensorMap& tmA, const CUtensorMap (&tmAS)[2], const CUtensorMap& bx1, const CUtensorMap (&bx1S)[2],
+                   const CUtensorMap& bx2, const CUtensorMap (&bx2S)[2], const GemmWork& w, const typename Epi::Params& ep, const char* what) {
+    if (split_cg(false) == 2) {
+      const SplitMaps sm = split_maps(tmAS, bx2S, tmAS, bx2S);
+      return launch_gemm<SplitCfg<AMAJ, BMAJ, 2>, Epi>(st, d->sms, tmA, bx2, tmA, bx2, w, ep, what, &sm);
+    }
+    const SplitMaps sm = split_maps(tmAS, bx1S, tmAS, bx1S);
+    return launch_gemm<SplitCfg<AMAJ, BMAJ, 1>, Epi>(st, d->sms, tmA, bx1, tmA, bx1, w, ep, what, &sm);
+  }
+  template <class Epi>
+  int launch_split_dual(const GemmWork& w, const typename Epi::Params& ep, const char* what) {
+    if (split_cg(true) == 2) {
+      const SplitMaps sm = split_maps(tmHpS, tmW32S, tmHfS, tmWr32S);
+      return launch_gemm<SplitDualCfg<2>, Epi>(st, d->sms, tmHp, tmW32, tmHf, tmWr32, w, ep, what, &sm);
+    }
+    const SplitMaps sm = split_maps(tmHpS, tmW64S, tmHfS, tmWr64S);
+    return launch_gemm<SplitDualCfg<1>, Epi>(st, d->sms, tmHp, tmW64, tmHf, tmWr64, w, ep, what, &sm);
+  }
 
   // statistics of every pair row; store_rows > 0 also keeps the bf16 logits of the first store_rows packed rows in dz
   template <bool ROUND> int fwd_pair(int store_rows) {
@@ -687,8 +721,7 @@ struct Plan {
         using EpiS = EpiStatsPair<kBnSplit, false>;
         GemmWork ws = w; ws.tiles_per_unit = kTpuSplit;
         typename EpiS::Params eps{ep.labels, ep.part, ep.row_cap, ep.v_local, ep.v_offset, nullptr, L.ldz, 0};
-        const SplitMaps sm = split_maps(tmHpS, tmW128S, tmHpS, tmW128S);
-        return launch_gemm<SplitCfg<KMAJOR, KMAJOR>, EpiS>(st, d->sms, tmHp, tmW128, tmHp, tmW128, ws, eps, "fwd_pair[split]", &sm);
+        return launch_split<KMAJOR, KMAJOR, EpiS>(tmHp, tmHpS, tmW128, tmW128S, tmW64, tmW64S, ws, eps, "fwd_pair[split]");
       }
     }
     return launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHp, tmW256, tmW128, w, ep, "fwd_pair");
@@ -704,8 +737,7 @@ struct Plan {
         using EpiS = EpiStatsRef<kBnSplitDual, false>;
         GemmWork ws = w; ws.tiles_per_unit = kTpuSplitDual;
         typename EpiS::Params eps{part_ref, part_u, L.cap_ref, s.V_local};
-        const SplitMaps sm = split_maps(tmHpS, tmW64S, tmHfS, tmWr64S);
-        return launch_gemm<SplitDualCfg, EpiS>(st, d->sms, tmHp, tmW64, tmHf, tmWr64, ws, eps, "fwd_ref[split]", &sm);
+        return launch_split_dual<EpiS>(ws, eps, "fwd_ref[split]");
       }
     }
     return launch_dual<Epi>(st, d, tmHp, tmHf, tmW128, tmWr128, tmW64, tmWr64, w, ep, "fwd_ref");
@@ -722,8 +754,7 @@ struct Plan {
         using EpiS = EpiDzPair<kBnSplit, false, true>;
         GemmWork ws = w; ws.tiles_per_unit = kTpuSplit;
         typename EpiS::Params eps{ep.labels, ep.lse, ep.coef, dz, L.ldz, ch * L.chunk_rows, s.V_local, s.v_offset, dz_part};
-        const SplitMaps sm = split_maps(tmHpS, tmW128S, tmHpS, tmW128S);
-        return launch_gemm<SplitCfg<KMAJOR, KMAJOR>, EpiS>(st, d->sms, tmHp, tmW128, tmHp, tmW128, ws, eps, "dz_pair[split]", &sm);
+        return launch_split<KMAJOR, KMAJOR, EpiS>(tmHp, tmHpS, tmW128, tmW128S, tmW64, tmW64S, ws, eps, "dz_pair[split]");
       }
     }
     return launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHp, tmW256, tmW128, w, ep, "dz_pair");
@@ -740,8 +771,7 @@ struct Plan {
         using EpiS = EpiDzRef<kBnSplitDual, false, true>;
         GemmWork ws = w; ws.tiles_per_unit = kTpuSplitDual;
         typename EpiS::Params eps{meta, ep.lse_p, ep.lse_r, ep.coef, dz, L.ldz, ch * L.chunk_rows, s.V_local, dz_part};
-        const SplitMaps sm = split_maps(tmHpS, tmW64S, tmHfS, tmWr64S);
-        return launch_gemm<SplitDualCfg, EpiS>(st, d->sms, tmHp, tmW64, tmHf, tmWr64, ws, eps, "dz_ref[split]", &sm);
+        return launch_split_dual<EpiS>(ws, eps, "dz_ref[split]");
       }
     }
     return launch_dual<Epi>(st, d, tmHp, tmHf, tmW128, tmWr128, tmW64, tmWr64, w, ep, "dz_ref");
@@ -783,18 +813,16 @@ struct Plan {
         GemmWork w{meta, KIND_DH, ch, L.chunk_rows, 0, s.H, s.V_local, 1, super_m().dh};
         typename Epi::Params ep{meta, at<int>(a->state, L.src_pair), at<int>(a->state, L.src_ref),
                                 static_cast<float*>(a->dH_pair), static_cast<float*>(a->dH_ref), s.H, nullptr};
-        const SplitMaps sm = split_maps(tmDzKS, tmWmnS, tmDzKS, tmWmnS);
         ProfScope ps(PK_DH, 1, st);
-        int rc = launch_gemm<SplitCfg<KMAJOR, MNMAJOR>, Epi>(st, d->sms, tmDzK, tmWmn, tmDzK, tmWmn, w, ep, "dH[split]", &sm);
+        int rc = launch_split<KMAJOR, MNMAJOR, Epi>(tmDzK, tmDzKS, tmWmn, tmWmnS, tmWmn, tmWmnS, w, ep, "dH[split]");
         if (rc) return rc;
       }
       if (s.flags & DPA_FLAG_NEED_DW) {
         using Epi = EpiAccumF32<kBnSplit>;
         GemmWork w{meta, KIND_DW, ch, L.chunk_rows, s.V_local, s.H, 0, 1, super_m().dw};
         typename Epi::Params ep{static_cast<float*>(a->dW), s.H, s.V_local, s.H, ch > 0};
-        const SplitMaps sm = split_maps(tmDzMNS, tmHpMNS, tmDzMNS, tmHpMNS);
         ProfScope ps(PK_DW, 1, st);
-        return launch_gemm<SplitCfg<MNMAJOR, MNMAJOR>, Epi>(st, d->sms, tmDzMN, tmHpMN, tmDzMN, tmHpMN, w, ep, "dW[split]", &sm);
+        return launch_split<MNMAJOR, MNMAJOR, Epi>(tmDzMN, tmDzMNS, tmHpMN, tmHpMNS, tmHpMN, tmHpMNS, w, ep, "dW[split]");
       }
       return DPA_OK;
     }

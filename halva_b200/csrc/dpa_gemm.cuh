@@ -157,7 +157,7 @@ struct GemmCfg {
   static_assert(!PROMOTE || (3 * ACC_COLS <= 512 && ACC_COLS <= 128), "promotion keeps ACC_COLS fp32 registers per thread");
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static_assert(2 * ACC_COLS <= 512, "two accumulator stages must fit TMEM");
-  static_assert(BN % 64 == 0 && BN <= 256 && BN_CTA % 64 == 0, "BN");
+  static_assert(BN % 64 == 0 && BN <= 256 && (BMAJ_ == 0 /* K-major: one box of BN_CTA rows */ ? BN_CTA % 16 == 0 : BN_CTA % 64 == 0), "BN");
   static_assert(CG == 1 || CG == 2, "cta_group");
 };
 
