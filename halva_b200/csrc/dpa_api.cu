@@ -382,7 +382,7 @@ int run_gather(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, void* 
 }
 
 // fp32 inputs: lm_head weights -> split-bf16 triples in scratch (W_ref shares W's when it aliases W)
-int run_split_weights(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, const Layout::Split& sp, cudaStream_t st) {
+int run_split_weights(const dpa_args_t* a, const Layout&, const DeviceInfo* d, const Layout::Split& sp, cudaStream_t st) {
   const size_t n = (size_t)a->shape.V_local * a->shape.H;
   const bool alias = a->W_ref == a->W;
   ProfScope ps(PK_GATHER, alias ? 1 : 2, st);
@@ -587,7 +587,7 @@ bool comm_active(const dpa_shape_t& s) { return g_comm.comm && g_comm.world > 1 
 // Tensor maps over the packed operands of this call and one method per GEMM class.  `scratch` offsets differ between
 // the forward / backward / fused-forward layouts, everything else is shared.
 struct Plan {
-  const dpa_args_t* a; const Layout& L; const DeviceInfo* d; cudaStream_t st;
+  const dpa_args_t* a; const Layout& L; const DeviceInfo* d = nullptr; cudaStream_t st;
   const dpa_shape_t& s;
   const DpaMeta* meta;
   __nv_bfloat16* dz = nullptr; __nv_bfloat16* zr = nullptr; float* dW32 = nullptr;
@@ -920,7 +920,7 @@ int forward_stats_impl(const dpa_args_t* a, cudaStream_t st, Layout& L, DeviceIn
 // keep the chunk's bf16 logits of both models, an elementwise pass turns them into dz and the KL rows.  Every chunk
 // ends with dH = dz W and dW += dz^T H.  Executed GEMM units per row = the algorithmic count (pair 3, reference 4).
 int forward_fused_impl(const dpa_args_t* a, cudaStream_t st) {
-  Layout L; DeviceInfo* d;
+  Layout L; DeviceInfo* d = nullptr;
   int rc = check_common(a, L, &d);
   if (rc) return rc;
   const dpa_shape_t& s = a->shape;
@@ -979,7 +979,7 @@ int forward_fused_impl(const dpa_args_t* a, cudaStream_t st) {
 
 // fused-gradient backward: scale what the forward left in dH_pair / dH_ref / dW by the upstream gradient
 int backward_scale_impl(const dpa_args_t* a, cudaStream_t st) {
-  Layout L; DeviceInfo* d;
+  Layout L; DeviceInfo* d = nullptr;
   int rc = check_common(a, L, &d);
   if (rc) return rc;
   if (a->shape.flags & DPA_FLAG_LOSS_ONLY) return fail(DPA_ERR_ARG, "DPA_FLAG_LOSS_ONLY: the forward formed no gradients");
@@ -1065,7 +1065,7 @@ int dpa_struct_sizes(int* shape_bytes, int* workspace_bytes, int* args_bytes) {
 }
 
 int dpa_forward_stats(const dpa_args_t* a, void* stream) {
-  Layout L; DeviceInfo* d;
+  Layout L; DeviceInfo* d = nullptr;
   return forward_stats_impl(a, static_cast<cudaStream_t>(stream), L, &d);
 }
 
@@ -1079,7 +1079,7 @@ int dpa_row_stats_view(const dpa_args_t* a, void** ptr, size_t* bytes) {
 }
 
 int dpa_forward_finish(const dpa_args_t* a, const void* gathered, int n_shards, void* stream) {
-  Layout L; DeviceInfo* d;
+  Layout L; DeviceInfo* d = nullptr;
   int rc = check_common(a, L, &d);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1096,7 +1096,7 @@ int dpa_forward_finish(const dpa_args_t* a, const void* gathered, int n_shards, 
 }
 
 int dpa_forward(const dpa_args_t* a, void* stream) {
-  Layout L; DeviceInfo* d;
+  Layout L; DeviceInfo* d = nullptr;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (a && (a->shape.flags & DPA_FLAG_FUSED_GRAD)) {
     if (comm_active(a->shape)) return fail(DPA_ERR_ARG, "DPA_FLAG_FUSED_GRAD is not available with a vocab-sharded lm_head");
@@ -1119,7 +1119,7 @@ int dpa_forward(const dpa_args_t* a, void* stream) {
 }
 
 int dpa_backward(const dpa_args_t* a, void* stream) {
-  Layout L; DeviceInfo* d;
+  Layout L; DeviceInfo* d = nullptr;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (a && (a->shape.flags & DPA_FLAG_FUSED_GRAD)) return backward_scale_impl(a, st);
   int rc = check_common(a, L, &d);
@@ -1200,7 +1200,7 @@ const char* dpa_profile_kind_name(int k) {
 }
 
 int dpa_debug_gemm(const void* A, const void* B, float* D, int M, int N, int K, int a_major, int b_major, int bn, void* stream) {
-  DeviceInfo* d;
+  DeviceInfo* d = nullptr;
   int rc = device_info(&d);
   if (rc) return rc;
   if (N % 32 || K % 8 || M % 8) return fail(DPA_ERR_BAD_SHAPE, "debug gemm: N%%32, K%%8, M%%8 required");
