@@ -10,12 +10,12 @@ LIB_PATH = os.environ.get("HALVA_DPA_LIB") or os.path.join(HERE, "libhalva_dpa.s
 DPA_BF16, DPA_F32 = 0, 1
 DPA_I64, DPA_I32 = 0, 1
 FLAG_ROUND_LOGITS, FLAG_NEED_DW, FLAG_DENSE, FLAG_FUSED_GRAD, FLAG_FUSED_NORM, FLAG_LOSS_ONLY = 1, 2, 4, 8, 16, 32
-ABI_VERSION = 4
+ABI_VERSION = 5
 STATUS_BAD_SIGN, STATUS_K_MISMATCH, STATUS_K_ZERO, STATUS_BAD_LABEL = 1, 2, 4, 8
 EXPORTS = ["dpa_version", "dpa_last_error", "dpa_query_workspace", "dpa_struct_sizes", "dpa_forward", "dpa_backward",
            "dpa_forward_stats", "dpa_forward_finish", "dpa_row_stats_view", "dpa_debug_gemm",
            "dpa_profile_enable", "dpa_profile_collect", "dpa_profile_kind_name", "dpa_set_cta_group",
-           "dpa_comm_unique_id", "dpa_comm_init", "dpa_comm_destroy", "dpa_comm_world"]
+           "dpa_comm_unique_id", "dpa_comm_init", "dpa_comm_destroy", "dpa_comm_world", "dpa_tmap_cache_stats", "dpa_plan_host_spans", "dpa_stage_host_batch"]
 
 
 class Shape(C.Structure):
@@ -38,6 +38,21 @@ class Args(C.Structure):
                 ("d_loss", C.c_void_p), ("dH_pair", C.c_void_p), ("dH_ref", C.c_void_p), ("dW", C.c_void_p),
                 ("norm_w", C.c_void_p), ("norm_w_ref", C.c_void_p), ("d_norm_w", C.c_void_p), ("norm_eps", C.c_float),
                 ("ref_logits", C.c_void_p), ("ref_logits_ld", C.c_int64), ("ref_logits_dtype", C.c_int32)]
+
+
+class Span(C.Structure):
+    _fields_ = [("seq", C.c_int32), ("t0", C.c_int32), ("t1", C.c_int32)]
+
+
+class HostBatch(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("B", "T", "B_ref", "T_ref", "H", "dtype", "index_dtype", "dense", "merge_gap")] + \
+               [(n, C.c_void_p) for n in ("h_pair", "labels_pair", "signs_pair", "h_ref_pol", "h_ref_frz", "labels_ref",
+                                          "d_h_pair", "d_labels_pair", "d_signs_pair", "d_h_ref_pol", "d_h_ref_frz", "d_labels_ref")]
+
+
+class StageInfo(C.Structure):
+    _fields_ = [("bytes", C.c_int64), ("spans_pair", C.c_int32), ("spans_ref", C.c_int32), ("rows_pair", C.c_int32),
+                ("rows_ref", C.c_int32), ("plan_us", C.c_float), ("issue_us", C.c_float)]
 
 
 class DPAError(RuntimeError):
@@ -72,6 +87,9 @@ def load():
     lib.dpa_row_stats_view.argtypes = [C.POINTER(Args), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     lib.dpa_debug_gemm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_void_p]
+    lib.dpa_plan_host_spans.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Span), C.c_int]
+    lib.dpa_stage_host_batch.argtypes = [C.POINTER(HostBatch), C.c_void_p, C.POINTER(StageInfo)]
+    lib.dpa_tmap_cache_stats.argtypes = [C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     lib.dpa_profile_enable.argtypes = [C.c_int]
     lib.dpa_set_cta_group.argtypes = [C.c_int]
     lib.dpa_comm_unique_id.argtypes = [C.c_void_p]
@@ -88,6 +106,14 @@ def check(rc: int, what: str):
     if rc != 0:
         msg = load().dpa_last_error().decode(errors="replace")
         raise DPAError(f"{what} failed ({rc}): {msg}")
+
+
+DEFAULT_CHUNK_ROWS = 16384
+
+
+def default_chunk_rows() -> int:
+    """Rows per chunk of the packed row space when dpa_shape_t::chunk_rows is 0 (include/halva_dpa.h)."""
+    return DEFAULT_CHUNK_ROWS
 
 
 def set_cta_group(cg: int):

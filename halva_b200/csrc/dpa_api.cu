@@ -5,6 +5,8 @@
 #include <cstring>
 #include <cstdarg>
 #include <mutex>
+#include <atomic>
+#include <unordered_map>
 #include <algorithm>
 #include <vector>
 
@@ -29,14 +31,22 @@ enum ProfKind { PK_META = 0, PK_GATHER, PK_FWD_PAIR, PK_FWD_REF, PK_REDUCE, PK_C
                 PK_STASH_REF, PK_DZ_ELEM, PK_SCALE, PK_STASH_GIVEN, PK_COUNT };
 struct ProfSpan { int kind; int launches; cudaEvent_t a, b; };
 std::vector<ProfSpan> g_spans;
+std::vector<cudaEvent_t> g_event_pool;      // timing events are recycled by dpa_profile_collect, never leaked
 std::mutex g_prof_mu;
-bool g_prof_on = false;
+std::atomic<bool> g_prof_on{false};
+cudaEvent_t pooled_event() {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
 struct ProfScope {
   cudaStream_t st; bool on; ProfSpan sp;
-  ProfScope(int kind, int launches, cudaStream_t s) : st(s), on(g_prof_on) {
+  ProfScope(int kind, int launches, cudaStream_t s) : st(s), on(g_prof_on.load(std::memory_order_relaxed)) {
     if (!on) return;
     sp.kind = kind; sp.launches = launches;
-    cudaEventCreate(&sp.a); cudaEventCreate(&sp.b);
+    sp.a = pooled_event(); sp.b = pooled_event();
     cudaEventRecord(sp.a, st);
   }
   ~ProfScope() {
@@ -79,9 +89,49 @@ int device_info(DeviceInfo** out) {
   return DPA_OK;
 }
 
+// Encoded tensor maps are cached per (device, pointer, dims, stride, box): a trainer calls with the same buffers every
+// step (the caching allocator hands the same blocks back), so steady-state calls encode nothing.
+struct TmapKey {
+  const void* ptr; uint64_t inner, outer, stride; uint32_t bi, bo; int dev;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && inner == o.inner && outer == o.outer && stride == o.stride && bi == o.bi && bo == o.bo && dev == o.dev;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = reinterpret_cast<uintptr_t>(k.ptr) * 0x9E3779B97F4A7C15ull;
+    h ^= (k.inner + 0x632BE59BD9B4E019ull) * 0xFF51AFD7ED558CCDull; h ^= h >> 29;
+    h ^= (k.outer * 0xC4CEB9FE1A85EC53ull) ^ (k.stride << 7) ^ ((uint64_t)k.bi << 40) ^ ((uint64_t)k.bo << 20) ^ (uint64_t)k.dev;
+    return (size_t)(h ^ (h >> 32));
+  }
+};
+std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+std::mutex g_tmap_mu;
+std::atomic<long long> g_tmap_hits{0}, g_tmap_misses{0};
+constexpr size_t kTmapCacheMax = 4096;
+
+int make_tmap_uncached(const DeviceInfo* d, CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                       uint32_t box_inner, uint32_t box_outer);
 // 2-D bf16 tensor map, 128-byte swizzle. inner = contiguous dimension.
 int make_tmap(const DeviceInfo* d, CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
               uint32_t box_inner, uint32_t box_outer) {
+  int dev = 0; cudaGetDevice(&dev);
+  const TmapKey key{ptr, inner, outer, row_stride_bytes, box_inner, box_outer, dev};
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) { *tm = it->second; g_tmap_hits.fetch_add(1, std::memory_order_relaxed); return DPA_OK; }
+  }
+  int rc = make_tmap_uncached(d, tm, ptr, inner, outer, row_stride_bytes, box_inner, box_outer);
+  if (rc) return rc;
+  g_tmap_misses.fetch_add(1, std::memory_order_relaxed);
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
+  if (g_tmap_cache.size() >= kTmapCacheMax) g_tmap_cache.clear();
+  g_tmap_cache.emplace(key, *tm);
+  return DPA_OK;
+}
+int make_tmap_uncached(const DeviceInfo* d, CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                       uint32_t box_inner, uint32_t box_outer) {
   cuuint64_t gdim[2] = {inner, outer};
   cuuint64_t gstr[1] = {row_stride_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
@@ -158,13 +208,15 @@ const SuperM& super_m() {
 }
 // cta_group of the single-accumulator GEMMs: 2 = CTA pairs on 256 x 256 tiles (default), 1 = one CTA per 128 x 256 tile.
 // Both are compiled; dpa_set_cta_group() / DPA_CTA_GROUP pick one (A/B measurements, bring-up).
-int g_cta_group = 0;
+std::atomic<int> g_cta_group{0};
 int cta_group() {
-  if (g_cta_group == 0) {
+  int v = g_cta_group.load(std::memory_order_relaxed);
+  if (v == 0) {
     const char* e = getenv("DPA_CTA_GROUP");
-    g_cta_group = (e && e[0] == '1') ? 1 : 2;
+    v = (e && e[0] == '1') ? 1 : 2;
+    g_cta_group.store(v, std::memory_order_relaxed);
   }
-  return g_cta_group;
+  return v;
 }
 // tmB1 / tmB2: the B-operand maps whose box holds BN (cta_group 1) or BN / 2 (cta_group 2) rows; equal for MN-major B
 template <class Epi, int AMAJ, int BMAJ>
@@ -1168,13 +1220,18 @@ int dpa_comm_world(void) { return g_comm.comm ? g_comm.world : 1; }
 
 int dpa_set_cta_group(int cg) {
   if (cg != 1 && cg != 2) return fail(DPA_ERR_ARG, "cta_group must be 1 or 2");
-  g_cta_group = cg;
+  g_cta_group.store(cg);
+  return DPA_OK;
+}
+
+int dpa_tmap_cache_stats(long long* hits, long long* misses) {
+  if (hits) *hits = g_tmap_hits.load();
+  if (misses) *misses = g_tmap_misses.load();
   return DPA_OK;
 }
 
 int dpa_profile_enable(int on) {
-  std::lock_guard<std::mutex> lk(g_prof_mu);
-  g_prof_on = on != 0;
+  g_prof_on.store(on != 0);
   return DPA_OK;
 }
 
@@ -1187,7 +1244,7 @@ int dpa_profile_collect(double* ms, int* launches, int n) {
     cudaEventSynchronize(sp.b);
     cudaEventElapsedTime(&t, sp.a, sp.b);
     if (sp.kind < n) { ms[sp.kind] += t; launches[sp.kind] += sp.launches; }
-    cudaEventDestroy(sp.a); cudaEventDestroy(sp.b);
+    g_event_pool.push_back(sp.a); g_event_pool.push_back(sp.b);
   }
   g_spans.clear();
   return PK_COUNT;

@@ -556,7 +556,11 @@ struct CoefArgs {
 };
 __global__ void coef_kernel(CoefArgs a) {
   const int p0 = a.meta->p0, nr_pad = a.meta->n_tot - p0;
-  const float go = a.d_loss ? *a.d_loss : 1.f;
+  float go = a.d_loss ? *a.d_loss : 1.f;
+  // Ill-formed phrase ids / labels: the reference raises (halva_trainer.py:567) or returns NaN; the device cannot raise,
+  // so the gradients are poisoned the same way loss_kernel poisons the loss -- finite-but-wrong dH / dW must never reach
+  // the optimiser.
+  if (a.meta->status & (DPA_STATUS_BAD_SIGN | DPA_STATUS_K_MISMATCH | DPA_STATUS_K_ZERO | DPA_STATUS_BAD_LABEL)) go = nanf("");
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < p0 + nr_pad; r += gridDim.x * blockDim.x) {
     if (r < p0) {
       const int c = a.col_pair[r], k = c & 0xFFFF, s = c >> 16;

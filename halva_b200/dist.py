@@ -72,6 +72,37 @@ def average_gradients(tensors: Iterable[torch.Tensor], group=None, bucket_bytes:
     flush()
 
 
+_lib_comm_ranks = None          # global ranks of the group the library's communicator was created over
+_shard_offset_cache = {}
+
+
+def library_comm_matches(group) -> bool:
+    """True when `group` is the process group given to init_library_comm (same global ranks in the same order): only then
+    may dpa_loss let the library exchange by itself -- its single communicator would otherwise talk to the wrong ranks."""
+    if _lib_comm_ranks is None:
+        return False
+    return _group_ranks(group) == _lib_comm_ranks
+
+
+def _group_ranks(group):
+    g = dist.group.WORLD if group is None else group
+    return tuple(dist.get_process_group_ranks(g))
+
+
+def shard_offsets(v_local: int, group, device) -> Tuple[int, int]:
+    """(first global vocabulary id of this rank's lm_head shard, global vocabulary size) from the shard sizes of all ranks
+    of `group` (uneven shards allowed).  One small all-gather per (group, v_local), cached afterwards."""
+    key = (_group_ranks(group), int(v_local))
+    if key not in _shard_offset_cache:
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        mine = torch.tensor([int(v_local)], dtype=torch.int64, device=device if dist.get_backend(group) == "nccl" else "cpu")
+        sizes = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(sizes, mine, group=group)
+        sizes = [int(t.item()) for t in sizes]
+        _shard_offset_cache[key] = (sum(sizes[:rank]), sum(sizes))
+    return _shard_offset_cache[key]
+
+
 def init_library_comm(group=None) -> int:
     """Give libhalva_dpa.so its own NCCL communicator over `group` (include/halva_dpa.h: dpa_comm_*): vocab-parallel
     dpa_loss(..., vocab_group=group) then exchanges inside the two C calls instead of through torch.distributed.
@@ -83,8 +114,12 @@ def init_library_comm(group=None) -> int:
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     if world == 1:
         return 1
-    if lib.dpa_comm_world() == world:
+    global _lib_comm_ranks
+    if lib.dpa_comm_world() == world and _lib_comm_ranks == _group_ranks(group):
         return world
+    if lib.dpa_comm_world() > 1:
+        _lib.check(lib.dpa_comm_destroy(), "dpa_comm_destroy")
+        _lib_comm_ranks = None
     buf = (C.c_ubyte * 128)()
     if rank == 0:
         _lib.check(lib.dpa_comm_unique_id(buf), "dpa_comm_unique_id")
@@ -95,12 +130,15 @@ def init_library_comm(group=None) -> int:
     dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
     raw = bytes(t.cpu().tolist())
     _lib.check(lib.dpa_comm_init(rank, world, raw), "dpa_comm_init")
+    _lib_comm_ranks = _group_ranks(group)
     return world
 
 
 def destroy_library_comm() -> None:
     from . import _lib
+    global _lib_comm_ranks
     _lib.check(_lib.load().dpa_comm_destroy(), "dpa_comm_destroy")
+    _lib_comm_ranks = None
 
 
 # ---- layout of the vocab-parallel exchange record (dpa_row_stats_view): [cap_pair x {m,s,z_y,0}] [cap_ref x {m_p,s_p,m_r,s_r}]

@@ -21,7 +21,7 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
-def _check_inputs(h_pair, labels_pair, signs_pair, h_ref_pol, h_ref_frozen, labels_ref, W, W_ref, ref_logits=None):
+def _check_inputs(h_pair, labels_pair, signs_pair, h_ref_pol, h_ref_frozen, labels_ref, W, W_ref, ref_logits=None, extra=()):
     if h_pair.dim() != 3 or h_pair.shape[0] % 2:
         raise ValueError("h_pair must be [2B, T, H] (first B correct, last B hallucinated sequences)")
     if tuple(h_pair.shape[:2]) != tuple(labels_pair.shape) or tuple(labels_pair.shape) != tuple(signs_pair.shape):
@@ -57,6 +57,16 @@ def _check_inputs(h_pair, labels_pair, signs_pair, h_ref_pol, h_ref_frozen, labe
             raise TypeError(f"{name} must be int64 or int32")
     if not (labels_pair.dtype == signs_pair.dtype == labels_ref.dtype):
         raise TypeError("labels_pair, signs_pair and labels_ref must share one integer dtype")
+    # every pointer handed to the kernels must be a pointer on ONE device: a CPU label tensor or a weight on another GPU
+    # would otherwise fault inside a kernel (sticky CUDA error) instead of raising here
+    every = (("h_pair", h_pair), ("labels_pair", labels_pair), ("signs_pair", signs_pair), ("h_ref_pol", h_ref_pol),
+             ("labels_ref", labels_ref), ("W", W)) + frozen + ((("ref_logits", ref_logits),) if ref_logits is not None else ()) + \
+        tuple((n, t) for n, t in extra if t is not None)
+    for name, t in every:
+        if not t.is_cuda:
+            raise DPAError(f"{name} is on {t.device}: the DPA-loss path is CUDA (sm_100a) only, there is no CPU fallback")
+        if t.device != h_pair.device:
+            raise DPAError(f"{name} is on {t.device} but h_pair is on {h_pair.device}: all tensors of one call must share a device")
 
 
 class _Call:
@@ -144,7 +154,8 @@ class _Call:
             scratch = self._with_scratch(self.ws.fwd_bytes)
             # vocab-parallel with the library's own NCCL communicator (halva_b200.dist.init_library_comm): the exchange
             # steps happen inside dpa_forward / dpa_backward
-            self.lib_comm = vocab_group is not None and self.lib.dpa_comm_world() > 1
+            from . import dist as _dist
+            self.lib_comm = vocab_group is not None and self.lib.dpa_comm_world() > 1 and _dist.library_comm_matches(vocab_group)
             if vocab_group is None or self.lib_comm:
                 _lib.check(self.lib.dpa_forward(C.byref(self.args), self._stream()), "dpa_forward")
             else:
@@ -168,6 +179,10 @@ class _Call:
             d_loss = d_loss.detach().to(torch.float32).reshape(1).contiguous()
             self.args.d_loss = _ptr(d_loss)
             if self.fused:
+                if self.grads is None:
+                    raise RuntimeError("dpa_loss(backward='fused') forms its gradients during the forward pass and hands them over "
+                                       "(scaled in place) at the first backward; a second backward through the same call "
+                                       "(retain_graph=True, autograd.grad twice) needs backward='recompute'")
                 _lib.check(self.lib.dpa_backward(C.byref(self.args), self._stream()), "dpa_backward[fused]")
                 grads, self.grads = self.grads, None
                 return grads
@@ -197,20 +212,27 @@ class DPALossFn(torch.autograd.Function):
         ctx.call = call
         ctx.status_t = call.status
         ctx.vocab_group = vocab_group
+        # registered so that autograd's version counters catch an in-place edit of the inputs between forward and backward
+        # (the recompute backward reads them again); no copy is made
+        ctx.save_for_backward(h_pair, h_ref_pol, W)
         loss, align, div = call.losses[0], call.losses[1], call.losses[2]
-        ctx.mark_non_differentiable(align, div)
-        DPALossFn._last_status = call.status          # (strict mode under no_grad: there is no grad_fn to carry it)
-        return loss, align, div
+        ctx.mark_non_differentiable(align, div, call.status)
+        return loss, align, div, call.status
 
     @staticmethod
-    def backward(ctx, g_loss, g_align, g_div):
+    def backward(ctx, g_loss, g_align, g_div, g_status):
         call = ctx.call
+        if call is None:
+            raise RuntimeError("dpa_loss: backward through the same call a second time (its buffers were released); "
+                               "use backward='recompute' and retain_graph=True")
+        _ = ctx.saved_tensors                       # raises if an input was modified in place since the forward
         dH_pair, dH_ref, dW, dnw = call.backward(g_loss)
         if ctx.vocab_group is not None and not call.lib_comm:
             import torch.distributed as dist
             dist.all_reduce(dH_pair, group=ctx.vocab_group)      # partial sums over vocab shards
             dist.all_reduce(dH_ref, group=ctx.vocab_group)
-        ctx.call = None
+        if call.fused:
+            ctx.call = None                         # recompute mode keeps its O(rows) state: a retained graph can run again
         return (dH_pair, dH_ref, dW, dnw) + (None,) * 17
 
 
@@ -244,8 +266,9 @@ def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.
                                    bf16 nn.Linear does (modeling_llama.py:1028-1029); False: keep fp32 accumulators
     fp32 inputs                    h_pair / h_ref_pol / h_ref_frozen / W / W_ref may all be fp32 instead (an fp32 model, as in
                                    the reference's CPU-runnable configuration): every operand goes to the tensor cores as a
-                                   split-bf16 pair (hi + lo, three passes per GEMM), logits and dLogits stay fp32-accurate,
-                                   gradients come back in fp32.  round_logits is ignored (an fp32 nn.Linear does not round).
+                                   split-bf16 triple (hi + mid + lo, six K segments per GEMM with the accumulator promoted
+                                   to fp32 registers every K = 256), logits and dLogits stay fp32-accurate, gradients come
+                                   back in fp32.  round_logits is ignored (an fp32 nn.Linear does not round).
     need_dW                        default W.requires_grad (False under the shipped LoRA recipe: lm_head frozen)
     dense                          process every fed position instead of compacting to rows with a non-zero
                                    contribution (what the reference executes; benchmarking only)
@@ -261,8 +284,9 @@ def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.
                                    instead of 6, 3 instead of 4 per pair row) -- and
                                    backward only scales by d_loss;  "auto" = "fused" when round_logits is on, a gradient
                                    is needed and there is no vocab_group, else "recompute".
-    Ill-formed phrase ids (K_pos != K_neg, K == 0, id > 255) make the losses NaN and set bits in
-    `read_status(loss)["status"]`; the reference raises / returns NaN there.
+    Ill-formed phrase ids (K_pos != K_neg, K == 0, id > 255) or labels make the losses AND every gradient NaN and set
+    bits in `read_status(loss)["status"]` / `loss.dpa_status`; the reference raises / returns NaN there (SURVEY.md
+    section 3.2) -- a truncated batch can never reach the optimiser as finite-but-wrong gradients.
     strict                         True: read the status word back after the forward (ONE host synchronisation) and raise
                                    like the reference does -- RuntimeError for K_pos != K_neg (the broadcast failure of
                                    halva_trainer.py:567), ValueError for phrase ids / labels out of range; K == 0 stays a
@@ -281,14 +305,18 @@ def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.
         W_ref = W if W_ref is None else W_ref
     if h_pair.dtype == torch.float32 and (ref_logits is not None or norm_weight is not None or backward == "fused"):
         raise ValueError("fp32 inputs: ref_logits, norm_weight and backward='fused' belong to the bf16 execution")
-    _check_inputs(h_pair, labels_pair, signs_pair, h_ref_pol, h_ref_frozen, labels_ref, W, W_ref, ref_logits)
+    _check_inputs(h_pair, labels_pair, signs_pair, h_ref_pol, h_ref_frozen, labels_ref, W, W_ref, ref_logits,
+                  extra=(("norm_weight", norm_weight), ("norm_weight_ref", norm_weight_ref)))
     if need_dW is None:
         need_dW = bool(W.requires_grad)
     if vocab_group is not None:
         import torch.distributed as dist
-        G, r = dist.get_world_size(vocab_group), dist.get_rank(vocab_group)
-        v_offset = r * W.shape[0] if v_offset is None else v_offset
-        vocab_size = G * W.shape[0] if vocab_size is None else vocab_size
+        if v_offset is None or vocab_size is None:
+            # shard sizes may differ (halva_b200.dist.vocab_shard_bounds): derive the offsets from the sizes of all shards
+            from .dist import shard_offsets
+            off, total = shard_offsets(W.shape[0], vocab_group, W.device)
+            v_offset = off if v_offset is None else v_offset
+            vocab_size = total if vocab_size is None else vocab_size
     else:
         v_offset, vocab_size = 0, W.shape[0]
     if norm_weight is not None:
@@ -307,11 +335,14 @@ def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.
     if backward == "fused" and (not round_logits or vocab_group is not None):
         raise ValueError("backward='fused' needs round_logits=True and no vocab_group")
     fused = backward == "fused" or (backward == "auto" and round_logits and vocab_group is None)
-    out = DPALossFn.apply(h_pair, h_ref_pol, W, norm_weight, labels_pair, signs_pair, labels_ref, h_ref_frozen, W_ref, float(alpha),
-                          bool(round_logits), bool(need_dW), bool(dense), int(chunk_rows), vocab_group, int(v_offset),
-                          int(vocab_size), fused, norm_weight_ref, float(norm_eps), ref_logits)
+    loss, align, div, status = DPALossFn.apply(h_pair, h_ref_pol, W, norm_weight, labels_pair, signs_pair, labels_ref, h_ref_frozen,
+                                               W_ref, float(alpha), bool(round_logits), bool(need_dW), bool(dense), int(chunk_rows),
+                                               vocab_group, int(v_offset), int(vocab_size), fused, norm_weight_ref, float(norm_eps),
+                                               ref_logits)
+    loss.dpa_status = status                 # device int32[8]: status bits, K, active rows ... (read_status(loss) decodes it)
+    out = (loss, align, div)
     if strict:
-        st = _status_of(out[0])
+        st = status.cpu().tolist()
         if st is not None:
             bits = int(st[0])
             if bits & _lib.STATUS_K_MISMATCH:
@@ -322,18 +353,13 @@ def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.
     return out
 
 
-def _status_of(loss: torch.Tensor):
-    fn = loss.grad_fn
-    st = getattr(fn, "status_t", None) if fn is not None else getattr(DPALossFn, "_last_status", None)
-    return None if st is None else st.cpu().tolist()
-
-
 def read_status(loss: torch.Tensor):
     """Synchronising debug helper: status word / K / active-row counts of the call that produced `loss`."""
-    fn = loss.grad_fn
-    st = getattr(fn, "status_t", None)
+    st = getattr(loss, "dpa_status", None)
     if st is None:
-        raise ValueError("not a dpa_loss output that carries grad")
+        st = getattr(loss.grad_fn, "status_t", None)
+    if st is None:
+        raise ValueError("not a dpa_loss output")
     s = st.cpu().tolist()
     return dict(status=s[0], K=s[1], n_pair_active=s[2], n_ref_active=s[3], K_pos=s[4], K_neg=s[5])
 

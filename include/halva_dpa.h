@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DPA_ABI_VERSION 4
+#define DPA_ABI_VERSION 5
 
 typedef enum {
   DPA_OK = 0,
@@ -160,12 +160,46 @@ int dpa_comm_init(int rank, int world, const void* unique_id_128_bytes);
 int dpa_comm_destroy(void);
 int dpa_comm_world(void);          /* 1 when no communicator is initialised */
 
+/* ---- Host-buffer entry (HOST pointers): the batch as the data collator leaves it in pinned host memory
+ * (llava/train/train_halva.py:963-989 builds labels / phrase ids on the host).  A hidden row (s, t) is read by the kernels
+ * only when it predicts a contributing label (halva_trainer.py:403-407,550-562), so only those rows -- a few contiguous
+ * spans per sequence -- need to cross the host->device link. */
+typedef struct { int32_t seq, t0, t1; } dpa_span_t;            /* rows [t0, t1) of sequence seq */
+/* Host-only, no CUDA call: spans of rows (s, t) with labels[s,t+1] != -100 (and, when signs != NULL, signs[s,t+1] not in
+ * {0, -100}); spans less than merge_gap+1 rows apart are merged.  Returns the number of spans written (<= cap), or a
+ * negative dpa_status_t (DPA_ERR_WORKSPACE: cap too small). */
+int dpa_plan_host_spans(const void* labels, const void* signs, int S, int T, int index_dtype, int merge_gap,
+                        dpa_span_t* out, int cap);
+typedef struct {
+  int32_t B, T, B_ref, T_ref, H;
+  int32_t dtype;            /* dpa_dtype_t of the hidden states */
+  int32_t index_dtype;      /* dpa_index_t of labels / signs */
+  int32_t dense;            /* 1: copy every hidden row (no planning) */
+  int32_t merge_gap;        /* merge spans less than merge_gap+1 rows apart (fewer, larger copies) */
+  /* pinned HOST memory, laid out like the device tensors of dpa_args_t */
+  const void* h_pair; const void* labels_pair; const void* signs_pair;
+  const void* h_ref_pol; const void* h_ref_frz /* may be NULL */; const void* labels_ref;
+  /* DEVICE destinations of the same shapes */
+  void* d_h_pair; void* d_labels_pair; void* d_signs_pair; void* d_h_ref_pol; void* d_h_ref_frz; void* d_labels_ref;
+} dpa_host_batch_t;
+typedef struct {
+  int64_t bytes;                         /* host->device bytes issued */
+  int32_t spans_pair, spans_ref, rows_pair, rows_ref;
+  float plan_us, issue_us;               /* host time spent planning / issuing the copies */
+} dpa_stage_info_t;
+/* Plans (per call, from this batch's labels) and issues the asynchronous copies on `stream`: labels / phrase ids in full,
+ * hidden rows span-wise.  Rows outside the spans are left untouched on the device (never read by dpa_forward). */
+int dpa_stage_host_batch(const dpa_host_batch_t* batch, void* cuda_stream, dpa_stage_info_t* info);
+
 /* Optional live timing of the kernels this library launches (bench.py): when enabled every launch group is
  * bracketed by CUDA events on the caller's stream; collect() synchronises on them and sums milliseconds and
  * kernel-launch counts per kernel class k (name via dpa_profile_kind_name(k)); returns the number of classes. */
 int dpa_profile_enable(int on);
 int dpa_profile_collect(double* ms, int* launches, int n);
 const char* dpa_profile_kind_name(int k);
+
+/* Encoded TMA descriptors are cached per (device, pointer, dims, stride, box); cumulative hit / miss counts (tests). */
+int dpa_tmap_cache_stats(long long* hits, long long* misses);
 
 /* cta_group of the single-accumulator GEMMs: 2 (default; CTA pairs on 256 x 256 tiles, tcgen05 cta_group::2) or 1
  * (one CTA per 128 x 256 tile).  Also settable with the environment variable DPA_CTA_GROUP before the first call. */

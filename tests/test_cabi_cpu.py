@@ -25,7 +25,7 @@ def test_exports_match_header():
     for name in declared:
         assert hasattr(lib, name), name
     from halva_b200._lib import ABI_VERSION
-    assert lib.dpa_version() == ABI_VERSION == 4
+    assert lib.dpa_version() == ABI_VERSION == 5
 
 
 def test_ctypes_structs_mirror_the_header():
@@ -34,6 +34,18 @@ def test_ctypes_structs_mirror_the_header():
     a, b, c = C.c_int(), C.c_int(), C.c_int()
     assert lib.dpa_struct_sizes(C.byref(a), C.byref(b), C.byref(c)) == 0
     assert (a.value, b.value, c.value) == (C.sizeof(Shape), C.sizeof(Workspace), C.sizeof(Args))
+
+
+def test_host_batch_structs_mirror_the_header():
+    """dpa_host_batch_t / dpa_stage_info_t / dpa_span_t: field order and sizes as declared in the header."""
+    from halva_b200._lib import HostBatch, Span, StageInfo
+    assert C.sizeof(Span) == 12 and C.sizeof(HostBatch) == 9 * 4 + 4 + 12 * 8 and C.sizeof(StageInfo) == 8 + 4 * 4 + 2 * 4
+    hdr = open(os.path.join(ROOT, "include", "halva_dpa.h")).read()
+    body = hdr[hdr.index("typedef struct {\n  int32_t B, T, B_ref, T_ref, H;"):hdr.index("} dpa_host_batch_t;")]
+    ptrs = re.findall(r"(?:const )?void\* (\w+)", body)
+    assert ptrs == [n for n, _ in HostBatch._fields_[9:]], ptrs
+    lib = _lib()
+    assert lib.dpa_stage_host_batch(None, None, None) == -7          # argument validation answers without a GPU
 
 
 def test_workspace_query_and_shape_validation():

@@ -273,3 +273,85 @@ def test_cuda_graph_capture_and_replay():
         e = _run_cuda(dict(t, h_pair=hp.detach()))
         assert got[0] == e["loss"]
         assert np.array_equal(got[1].float().cpu().numpy(), e["dH_pair"]) and np.array_equal(got[2].float().cpu().numpy(), e["dW"])
+
+
+@pytest.mark.parametrize("bwd", ["fused", "recompute"])
+def test_ill_formed_batch_poisons_gradients(bwd):
+    """K_pos != K_neg / phrase id > 255: the reference raises (halva_trainer.py:567); here loss AND every gradient are NaN
+    (the device cannot raise) -- a truncated batch must never reach the optimiser as finite-but-wrong gradients."""
+    from halva_b200 import dpa_loss, read_status
+    t, _ = _synth()
+    s = t["signs_pair"].clone()
+    B = s.shape[0] // 2
+    s[B:][s[B:] > 0] = 1
+    s[:B][s[:B] > 2] = 2
+    bad = t["signs_pair"].clone()
+    bad[0, -3] = 300
+    for signs, bit in ((s, 2), (bad, 1)):
+        hp = t["h_pair"].clone().requires_grad_(True)
+        hr = t["h_ref_pol"].clone().requires_grad_(True)
+        W = t["W"].clone().requires_grad_(True)
+        loss, _, _ = dpa_loss(hp, t["labels_pair"], signs, hr, t["labels_ref"], W, h_ref_frozen=t["h_ref_frz"], alpha=0.4, backward=bwd)
+        st = read_status(loss)
+        if not (st["status"] & bit):
+            continue                                         # (this synthetic batch happened to have K_pos == K_neg)
+        loss.backward()
+        assert torch.isnan(loss).item()
+        assert torch.isnan(W.grad).any().item() and torch.isnan(hr.grad).any().item()
+        active = hp.grad[hp.grad != 0]
+        assert active.numel() == 0 or torch.isnan(active).all().item()     # no finite non-zero gradient anywhere
+
+
+def test_second_backward_and_inplace_edit_are_errors():
+    from halva_b200 import dpa_loss
+    t, _ = _synth()
+    hp = t["h_pair"].clone().requires_grad_(True)
+    loss, _, _ = dpa_loss(hp, t["labels_pair"], t["signs_pair"], t["h_ref_pol"], t["labels_ref"], t["W"], h_ref_frozen=t["h_ref_frz"], alpha=0.4)
+    loss.backward(retain_graph=True)
+    with pytest.raises(RuntimeError, match="second"):
+        loss.backward()
+    # recompute mode keeps only O(rows) state: a retained graph can be walked again, with the same result
+    hp.grad = None
+    loss, _, _ = dpa_loss(hp, t["labels_pair"], t["signs_pair"], t["h_ref_pol"], t["labels_ref"], t["W"], h_ref_frozen=t["h_ref_frz"], alpha=0.4,
+                          backward="recompute")
+    g1, = torch.autograd.grad(loss, hp, retain_graph=True)
+    g2, = torch.autograd.grad(loss, hp)
+    assert torch.equal(g1, g2)
+    # an in-place edit of an input between forward and backward is caught by autograd's version counters
+    h2 = t["h_pair"].clone().requires_grad_(True)
+    hh = h2 * 1.0
+    loss, _, _ = dpa_loss(hh, t["labels_pair"], t["signs_pair"], t["h_ref_pol"], t["labels_ref"], t["W"], h_ref_frozen=t["h_ref_frz"], alpha=0.4,
+                          backward="recompute")
+    hh.mul_(2.0)
+    with pytest.raises(RuntimeError, match="modified by an inplace operation"):
+        loss.backward()
+
+
+def test_tensor_maps_are_cached_across_calls():
+    import ctypes as C
+    from halva_b200 import _lib, dpa_loss
+    lib = _lib.load()
+    t, _ = _synth()
+
+    def counts():
+        h, m = C.c_longlong(), C.c_longlong()
+        lib.dpa_tmap_cache_stats(C.byref(h), C.byref(m))
+        return h.value, m.value
+
+    with torch.no_grad():
+        for _ in range(2):                                   # the caching allocator hands the same scratch blocks back
+            dpa_loss(t["h_pair"], t["labels_pair"], t["signs_pair"], t["h_ref_pol"], t["labels_ref"], t["W"], h_ref_frozen=t["h_ref_frz"], alpha=0.4)
+        torch.cuda.synchronize()
+        h0, m0 = counts()
+        dpa_loss(t["h_pair"], t["labels_pair"], t["signs_pair"], t["h_ref_pol"], t["labels_ref"], t["W"], h_ref_frozen=t["h_ref_frz"], alpha=0.4)
+        h1, m1 = counts()
+    assert m1 == m0 and h1 > h0                              # steady state: nothing is re-encoded
+
+
+def test_mixed_device_inputs_raise_before_any_kernel():
+    from halva_b200 import DPAError, dpa_loss
+    t, _ = _synth()
+    with pytest.raises(DPAError, match="labels_pair"):
+        dpa_loss(t["h_pair"], t["labels_pair"].cpu(), t["signs_pair"], t["h_ref_pol"], t["labels_ref"], t["W"], h_ref_frozen=t["h_ref_frz"], alpha=0.4)
+    with pytest.raises(DPAError, match="labels_ref"):
+        dpa_loss(t["h_pair"], t["labels_pair"], t["signs_pair"], t["h_ref_pol"], t["labels_ref"].cpu(), t["W"], h_ref_frozen=t["h_ref_frz"], alpha=0.4)
