@@ -199,13 +199,27 @@ int launch_gemm(cudaStream_t st, int sms, const CUtensorMap& tmA, const CUtensor
 // (<= 134 MB) then stay L2-resident while the lm_head streams through once; the gradient GEMMs (K = V or rows, long)
 // want a square-ish wave.  Overridable for measurements: DPA_SUPER_STATS / DPA_SUPER_DH / DPA_SUPER_DW.
 struct SuperM { int stats, dh, dw; };
+int env_int(const char* n, int dflt) { const char* e = getenv(n); return e ? atoi(e) : dflt; }
 const SuperM& super_m() {
-  static const SuperM v = [] {
-    auto env = [](const char* n, int dflt) { const char* e = getenv(n); return e ? atoi(e) : dflt; };
-    return SuperM{env("DPA_SUPER_STATS", 0), env("DPA_SUPER_DH", 0), env("DPA_SUPER_DW", 0)};
-  }();
+  static const SuperM v = SuperM{env_int("DPA_SUPER_STATS", 0), env_int("DPA_SUPER_DH", 0), env_int("DPA_SUPER_DW", 0)};
   return v;
 }
+// Tile width of the two long-K gradient GEMMs (dH = dz W, dW = dz^T H): 512 (default) = one 256 x 512 tile per CTA pair in a
+// single all-of-TMEM accumulator, 256 = the double-buffered 256 x 256 tile of the statistics GEMMs.  DPA_GRAD_BN overrides.
+int grad_bn() {
+  static const int v = env_int("DPA_GRAD_BN", 512) == 256 ? 256 : 512;
+  return v;
+}
+// L2 eviction-priority hints of the operand loads per GEMM class, "ab" digits (0 none, 1 evict_first, 2 evict_last):
+// DPA_HINT_STATS / DPA_HINT_DH / DPA_HINT_DW, e.g. DPA_HINT_STATS=21 keeps the packed hidden rows and streams the lm_head.
+struct Hints { int a, b; };
+Hints hints_of(const char* name, int dflt) {
+  const int v = env_int(name, dflt);
+  return Hints{(v / 10) % 10, v % 10};
+}
+const Hints& hint_stats() { static const Hints h = hints_of("DPA_HINT_STATS", 0); return h; }
+const Hints& hint_dh() { static const Hints h = hints_of("DPA_HINT_DH", 0); return h; }
+const Hints& hint_dw() { static const Hints h = hints_of("DPA_HINT_DW", 0); return h; }
 // cta_group of the single-accumulator GEMMs: 2 = CTA pairs on 256 x 256 tiles (default), 1 = one CTA per 128 x 256 tile.
 // Both are compiled; dpa_set_cta_group() / DPA_CTA_GROUP pick one (A/B measurements, bring-up).
 std::atomic<int> g_cta_group{0};
@@ -225,6 +239,15 @@ int launch_single(cudaStream_t st, const DeviceInfo* d, const CUtensorMap& tmA, 
   if (cta_group() == 2)
     return launch_gemm<GemmCfg<256, false, AMAJ, BMAJ, 2>, Epi>(st, d->sms, tmA, tmB2, tmA, tmB2, work, ep, what);
   return launch_gemm<GemmCfg<256, false, AMAJ, BMAJ, 1>, Epi>(st, d->sms, tmA, tmB1, tmA, tmB1, work, ep, what);
+}
+
+// the long-K gradient GEMMs on 256 x 512 tiles (CTA pairs only; B is MN-major in both, so the 64-column TMA boxes serve)
+template <template <int> class EpiT, int AMAJ, int BMAJ, class Params>
+int launch_grad(cudaStream_t st, const DeviceInfo* d, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmWork& work,
+                const Params& ep, const char* what) {
+  if (cta_group() == 2 && grad_bn() == 512)
+    return launch_gemm<GemmCfg<512, false, AMAJ, BMAJ, 2>, EpiT<512>>(st, d->sms, tmA, tmB, tmA, tmB, work, ep, what);
+  return launch_single<EpiT<256>, AMAJ, BMAJ>(st, d, tmA, tmB, tmB, work, ep, what);
 }
 
 // dual-accumulator GEMMs (policy + frozen logits of the same rows): 128-wide tiles; tmB*_1 boxes hold 128 rows of W
@@ -764,7 +787,7 @@ struct Plan {
   // statistics of every pair row; store_rows > 0 also keeps the bf16 logits of the first store_rows packed rows in dz
   template <bool ROUND> int fwd_pair(int store_rows) {
     using Epi = EpiStatsPair<kBnPair, ROUND>;
-    GemmWork w{meta, KIND_FWD_PAIR, 0, 0, 0, s.V_local, s.H, kTpuPair, super_m().stats};
+    GemmWork w{meta, KIND_FWD_PAIR, 0, 0, 0, s.V_local, s.H, kTpuPair, super_m().stats, hint_stats().a, hint_stats().b};
     typename Epi::Params ep{at<int>(a->state, L.lab_pair), part_pair, L.cap_pair, s.V_local, s.v_offset,
                             store_rows > 0 ? dz : nullptr, L.ldz, store_rows};
     ProfScope ps(PK_FWD_PAIR, 1, st);
@@ -781,7 +804,7 @@ struct Plan {
   // policy + frozen logits of every reference-sample row side by side: statistics incl. the KL numerator
   template <bool ROUND> int fwd_ref() {
     using Epi = EpiStatsRef<kBnRef, ROUND>;
-    GemmWork w{meta, KIND_FWD_REF, 0, 0, 0, s.V_local, s.H, kTpuRef, super_m().stats};
+    GemmWork w{meta, KIND_FWD_REF, 0, 0, 0, s.V_local, s.H, kTpuRef, super_m().stats, hint_stats().a, hint_stats().b};
     typename Epi::Params ep{part_ref, part_u, L.cap_ref, s.V_local};
     ProfScope ps(PK_FWD_REF, 1, st);
     if constexpr (!ROUND) {
@@ -797,7 +820,7 @@ struct Plan {
   // recompute the pair rows of chunk ch -> dz
   template <bool ROUND> int dz_pair(int ch) {
     using Epi = EpiDzPair<kBnPair, ROUND>;
-    GemmWork w{meta, KIND_DZ_PAIR, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair, super_m().stats};
+    GemmWork w{meta, KIND_DZ_PAIR, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair, super_m().stats, hint_stats().a, hint_stats().b};
     typename Epi::Params ep{at<int>(a->state, L.lab_pair), at<float>(a->state, L.lse_pair), at<float>(a->state, L.coef_pair),
                             dz, L.ldz, ch * L.chunk_rows, s.V_local, s.v_offset, 0};
     ProfScope ps(PK_DZ_PAIR, 1, st);
@@ -814,7 +837,7 @@ struct Plan {
   // recompute the reference-sample rows of chunk ch (both models) -> dz
   template <bool ROUND> int dz_ref(int ch) {
     using Epi = EpiDzRef<kBnRef, ROUND>;
-    GemmWork w{meta, KIND_DZ_REF, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuRef, super_m().stats};
+    GemmWork w{meta, KIND_DZ_REF, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuRef, super_m().stats, hint_stats().a, hint_stats().b};
     typename Epi::Params ep{meta, at<float>(a->state, L.lse_ref_p), at<float>(a->state, L.lse_ref_r), at<float>(a->state, L.coef_ref),
                             dz, L.ldz, ch * L.chunk_rows, s.V_local, 0};
     ProfScope ps(PK_DZ_REF, 1, st);
@@ -835,12 +858,12 @@ struct Plan {
     const bool given = a->ref_logits != nullptr;
     {
       ProfScope ps(PK_STASH_REF, given ? 1 : 2, st);
-      GemmWork wp{meta, KIND_STASH_POL, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair, super_m().stats};
+      GemmWork wp{meta, KIND_STASH_POL, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair, super_m().stats, hint_stats().a, hint_stats().b};
       typename Epi::Params epp{meta, part2, dz, L.cap_ref, s.V_local, L.ldz, ch * L.chunk_rows, 0};
       int rc = launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHp, tmW256, tmW128, wp, epp, "stash_pol");
       if (rc) return rc;
       if (!given) {
-        GemmWork wf{meta, KIND_STASH_FRZ, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair, super_m().stats};
+        GemmWork wf{meta, KIND_STASH_FRZ, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair, super_m().stats, hint_stats().a, hint_stats().b};
         typename Epi::Params epf{meta, part2, zr, L.cap_ref, s.V_local, L.ldz, ch * L.chunk_rows, 1};
         return launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHf, tmWr256, tmWr128, wf, epf, "stash_frz");
       }
@@ -879,23 +902,26 @@ struct Plan {
       return DPA_OK;
     }
     {
-      using Epi = EpiStoreRows<256>;
-      GemmWork w{meta, KIND_DH, ch, L.chunk_rows, 0, s.H, s.V_local, 1, super_m().dh};
-      typename Epi::Params ep{meta, at<int>(a->state, L.src_pair), at<int>(a->state, L.src_ref),
-                              static_cast<__nv_bfloat16*>(a->dH_pair), static_cast<__nv_bfloat16*>(a->dH_ref), s.H, dH_packed};
+      using P = typename EpiStoreRows<256>::Params;
+      const int wide = (cta_group() == 2 && grad_bn() == 512) ? 1 : 0;
+      // 512-wide tiles: a super-block of 9 row units x all column tiles is one wave of the 74 CTA pairs
+      GemmWork w{meta, KIND_DH, ch, L.chunk_rows, 0, s.H, s.V_local, 1, super_m().dh ? super_m().dh : (wide ? 9 : 0), hint_dh().a, hint_dh().b};
+      P ep{meta, at<int>(a->state, L.src_pair), at<int>(a->state, L.src_ref),
+           static_cast<__nv_bfloat16*>(a->dH_pair), static_cast<__nv_bfloat16*>(a->dH_ref), s.H, dH_packed};
       {
         ProfScope ps(PK_DH, 1, st);
-        int rc = launch_single<Epi, KMAJOR, MNMAJOR>(st, d, tmDzK, tmWmn, tmWmn, w, ep, "dH");
+        int rc = launch_grad<EpiStoreRowsBf16, KMAJOR, MNMAJOR>(st, d, tmDzK, tmWmn, w, ep, "dH");
         if (rc) return rc;
       }
       if (dH_packed) { int rc = exchange_dH_chunk(ch); if (rc) return rc; }
     }
     if (dW32) {
-      using Epi = EpiAccumDW<256>;
-      GemmWork w{meta, KIND_DW, ch, L.chunk_rows, s.V_local, s.H, 0, 1, super_m().dw};
-      typename Epi::Params ep{meta, ch, L.chunk_rows, dW32, static_cast<__nv_bfloat16*>(a->dW), s.H, s.V_local, s.H};
+      using P = typename EpiAccumDW<256>::Params;
+      const int wide = (cta_group() == 2 && grad_bn() == 512) ? 1 : 0;
+      GemmWork w{meta, KIND_DW, ch, L.chunk_rows, s.V_local, s.H, 0, 1, super_m().dw ? super_m().dw : (wide ? 9 : 0), hint_dw().a, hint_dw().b};
+      P ep{meta, ch, L.chunk_rows, dW32, static_cast<__nv_bfloat16*>(a->dW), s.H, s.V_local, s.H};
       ProfScope ps(PK_DW, 1, st);
-      return launch_single<Epi, MNMAJOR, MNMAJOR>(st, d, tmDzMN, tmHpMN, tmHpMN, w, ep, "dW");
+      return launch_grad<EpiAccumDW, MNMAJOR, MNMAJOR>(st, d, tmDzMN, tmHpMN, w, ep, "dW");
     }
     return DPA_OK;
   }
@@ -1270,6 +1296,19 @@ int dpa_debug_gemm(const void* A, const void* B, float* D, int M, int N, int K, 
     using Epi = EpiAccumF32<128>;
     typename Epi::Params ep{D, N, M, N, 0};
     return launch_gemm<GemmCfg<128, false, KMAJOR, KMAJOR, 1>, Epi>(st, d->sms, tmA, tmB, tmA, tmB, w, ep, "debug_gemm");
+  }
+  if (bn == 512) {                                                 // the 256 x 512 tile of the gradient GEMMs (CTA pairs)
+    CUtensorMap tmB5;                                              // K-major B: boxes of 128 rows (one per MMA and CTA)
+    if ((rc = make_operand_tmap(d, &tmB5, B, b_major, N, K, b_major == KMAJOR ? K : N, 128))) return rc;
+    using Epi = EpiAccumF32<512>;
+    typename Epi::Params ep{D, N, M, N, 0};
+#define DBG_CASE5(AM, BMJ) \
+    if (a_major == AM && b_major == BMJ) return launch_gemm<GemmCfg<512, false, AM, BMJ, 2>, Epi>(st, d->sms, tmA, tmB5, tmA, tmB5, w, ep, "debug_gemm512");
+    DBG_CASE5(KMAJOR, KMAJOR)
+    DBG_CASE5(KMAJOR, MNMAJOR)
+    DBG_CASE5(MNMAJOR, MNMAJOR)
+    DBG_CASE5(MNMAJOR, KMAJOR)
+#undef DBG_CASE5
   }
   CUtensorMap tmBh;                                                // B box of BN / 2 rows for cta_group 2
   if ((rc = make_operand_tmap(d, &tmBh, B, b_major, N, K, b_major == KMAJOR ? K : N, bn / 2))) return rc;

@@ -76,6 +76,7 @@ struct GemmWork {
   int k_static;        // K extent unless KIND_DW
   int tiles_per_unit;  // consecutive column tiles per work unit
   int super_m;         // row-tile units per L2 super-block of the unit order (0 = kSuperM)
+  int hint_a, hint_b;  // L2 eviction priority of the A / B operand loads: 0 = none, 1 = evict_first, 2 = evict_last
 };
 
 struct TileRange {
@@ -145,6 +146,14 @@ struct GemmCfg {
   static constexpr int STAGES_RAW = (227 * 1024 - 1280) / STAGE_BYTES;   // 7 x 32 KiB (pair), 4 x 48 KiB (single CTA / dual pair), 3 x 64 KiB (dual single CTA)
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int ACC_COLS = DUAL ? 2 * BN : BN;             // TMEM columns per accumulator stage
+  // BN = 512 (the long-K gradient GEMMs): one accumulator stage of all 512 TMEM columns, two N = 256 MMAs per K step.
+  // A 256 x 512 tile per CTA pair moves 25 % fewer operand bytes per FLOP than 256 x 256, a wave of 74 pairs covers every
+  // column tile of its row units (so each dz panel is read once), and the CTAs of a wave re-align at every tile boundary
+  // (there is no second stage to run ahead into); the epilogue is no longer hidden, but K is 250-500 blocks long.
+  static constexpr int ACC_STAGES = 2 * ACC_COLS <= 512 ? 2 : 1;
+  static constexpr int UMMA_N = BN > 256 ? 256 : BN;              // N of one tcgen05.mma
+  static constexpr int NMMA = BN / UMMA_N;
+  static constexpr uint32_t B_MMA_STEP = ((UMMA_N / CG) * 128) >> 4;   // smem distance (>>4) between the B rows of two MMAs
   // PROMOTE (the split-operand / fp32 path): the tensor core adds each K = 16 step into its fp32 accumulator with
   // TRUNCATION (tools/tc_accum_probe.py: a same-sign K = 4096 dot product comes out 9e-6 low; the bias grows with the
   // accumulator's magnitude and the number of steps).  So the K loop is cut into chunks of PROMOTE_KB k-blocks, each chunk
@@ -156,24 +165,32 @@ struct GemmCfg {
   static constexpr int MAIN_COL = 2 * ACC_COLS;                    // TMEM column of the promoted sum
   static_assert(!PROMOTE || (3 * ACC_COLS <= 512 && ACC_COLS <= 128), "promotion keeps ACC_COLS fp32 registers per thread");
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-  static_assert(2 * ACC_COLS <= 512, "two accumulator stages must fit TMEM");
-  static_assert(BN % 64 == 0 && BN <= 256 && (BMAJ_ == 0 /* K-major: one box of BN_CTA rows */ ? BN_CTA % 16 == 0 : BN_CTA % 64 == 0), "BN");
+  static_assert(ACC_STAGES * ACC_COLS <= 512, "the accumulator stages must fit TMEM");
+  static_assert(BN % 64 == 0 && BN <= 512 && (BMAJ_ == 0 /* K-major: one box of BN_CTA rows */ ? (BN_CTA % 16 == 0 && BN_CTA <= 256) : BN_CTA % 64 == 0), "BN");
+  static_assert(BN <= 256 || (!DUAL && NSEG == 1), "512-column tiles: single accumulator, plain bf16 operands");
   static_assert(CG == 1 || CG == 2, "cta_group");
 };
 
 // issue the TMA loads of one operand tile for one K block
-template <int MAJ, int ROWS, int CG>
-__device__ __forceinline__ void load_operand(uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int row, int k) {
-  if constexpr (MAJ == KMAJOR) {                               // box {64 k, ROWS}
-    if constexpr (CG == 1) tma_load_2d(dst, tm, bar, k, row); else tma_load_2d_pair(dst, tm, bar, k, row);
+template <int CG>
+__device__ __forceinline__ void load_box(uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, uint64_t policy) {
+  if (policy) {
+    if constexpr (CG == 1) tma_load_2d_hint(dst, tm, bar, c0, c1, policy); else tma_load_2d_pair_hint(dst, tm, bar, c0, c1, policy);
   } else {
-#pragma unroll
-    for (int j = 0; j < ROWS / 64; ++j) {                      // box {64 mn, 64 k}: [atom][k][64 mn]
-      if constexpr (CG == 1) tma_load_2d(dst + j * (BK * 128), tm, bar, row + j * 64, k);
-      else tma_load_2d_pair(dst + j * (BK * 128), tm, bar, row + j * 64, k);
-    }
+    if constexpr (CG == 1) tma_load_2d(dst, tm, bar, c0, c1); else tma_load_2d_pair(dst, tm, bar, c0, c1);
   }
 }
+template <int MAJ, int ROWS, int CG>
+__device__ __forceinline__ void load_operand(uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int row, int k, uint64_t policy = 0) {
+  if constexpr (MAJ == KMAJOR) {                               // box {64 k, ROWS}
+    load_box<CG>(dst, tm, bar, k, row, policy);
+  } else {
+#pragma unroll
+    for (int j = 0; j < ROWS / 64; ++j)                        // box {64 mn, 64 k}: [atom][k][64 mn]
+      load_box<CG>(dst + j * (BK * 128), tm, bar, row + j * 64, k, policy);
+  }
+}
+__device__ __forceinline__ uint64_t l2_policy(int hint) { return hint == 1 ? kPolicyEvictFirst : hint == 2 ? kPolicyEvictLast : 0ull; }
 // K-major: rows of 128 B, 8-row swizzle atoms 1024 B apart, K advances inside the row (UMMA_K * 2 bytes per MMA).
 // MN-major: atoms [64 mn x 8 k] 1024 B apart along K, BK * 128 B apart along MN (UMMA_K * 128 bytes per MMA).
 template <int MAJ> struct OperandDesc {
@@ -225,7 +242,7 @@ __device__ __forceinline__ void dpa_gemm_body(const CUtensorMap& tmA, const CUte
   if constexpr (CG == 2) cluster_sync_all();                   // both CTAs resident before the paired TMEM allocation
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], CG); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], CG * BM); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], CG * BM); }   // (ACC_STAGES == 1 uses [0] only)
     fence_barrier_init();
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
     if (Cfg::DUAL) { tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); }
@@ -251,6 +268,7 @@ __device__ __forceinline__ void dpa_gemm_body(const CUtensorMap& tmA, const CUte
   if (warp == kProducerWarp) {
     // ------------------------------------------------------------- TMA producer (one per CTA)
     int st = 0; uint32_t ph = 0;
+    const uint64_t pol_a = l2_policy(work.hint_a), pol_b = l2_policy(work.hint_b);
     for (int u = group_id; u < n_units; u += n_cta_groups) {
       int mu, ng; decode(u, mu, ng);
       const int mt = mu * CG + cta_rank;
@@ -268,9 +286,17 @@ __device__ __forceinline__ void dpa_gemm_body(const CUtensorMap& tmA, const CUte
           mbar_wait(&empty[st], ph ^ 1);
           if (elect_one()) {
             if constexpr (CG == 1) mbar_arrive_expect_tx(&full[st], Cfg::STAGE_BYTES);
-            load_operand<Cfg::AMAJ, BM, CG>(sA + st * Cfg::A_BYTES, mA, &full[st], tr.a_row0 + mt * BM, tr.a_k0 + kb * BK);
-            load_operand<Cfg::BMAJ, Cfg::BN_CTA, CG>(sB + st * Cfg::B_BYTES, mB, &full[st], nt * BN + cta_rank * Cfg::BN_CTA,
-                                                     tr.b_k0 + kb * BK);
+            load_operand<Cfg::AMAJ, BM, CG>(sA + st * Cfg::A_BYTES, mA, &full[st], tr.a_row0 + mt * BM, tr.a_k0 + kb * BK, pol_a);
+            if constexpr (Cfg::NMMA == 1) {
+              load_operand<Cfg::BMAJ, Cfg::BN_CTA, CG>(sB + st * Cfg::B_BYTES, mB, &full[st], nt * BN + cta_rank * Cfg::BN_CTA,
+                                                       tr.b_k0 + kb * BK, pol_b);
+            } else {
+              // 512-column tile: MMA h covers columns [h * 256, h * 256 + 256); this CTA stages its half of each
+#pragma unroll
+              for (int h = 0; h < Cfg::NMMA; ++h)
+                load_operand<Cfg::BMAJ, Cfg::UMMA_N / CG, CG>(sB + st * Cfg::B_BYTES + h * (Cfg::UMMA_N / CG) * 128, mB, &full[st],
+                                                              nt * BN + h * Cfg::UMMA_N + cta_rank * (Cfg::UMMA_N / CG), tr.b_k0 + kb * BK, pol_b);
+            }
             if constexpr (Cfg::DUAL) {
               load_operand<Cfg::AMAJ, BM, CG>(sA2 + st * Cfg::A_BYTES, mA2, &full[st], tr.a2_row0 + mt * BM, tr.a_k0 + kb * BK);
               load_operand<Cfg::BMAJ, Cfg::BN_CTA, CG>(sB2 + st * Cfg::B_BYTES, mB2, &full[st], nt * BN + cta_rank * Cfg::BN_CTA,
@@ -290,7 +316,8 @@ __device__ __forceinline__ void dpa_gemm_body(const CUtensorMap& tmA, const CUte
     }
   } else if (warp == kMmaWarp && leader) {
     // ------------------------------------------------------------- MMA issuer (leader CTA only)
-    constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN, Cfg::AMAJ, Cfg::BMAJ);
+    constexpr uint32_t idesc = make_idesc_bf16(BM * CG, Cfg::UMMA_N, Cfg::AMAJ, Cfg::BMAJ);
+    constexpr uint32_t AS = Cfg::ACC_STAGES;
     using DA = OperandDesc<Cfg::AMAJ>;
     using DB = OperandDesc<Cfg::BMAJ>;
     const uint32_t a_base = smem_u32(sA) >> 4, b_base = smem_u32(sB) >> 4;
@@ -300,7 +327,7 @@ __device__ __forceinline__ void dpa_gemm_body(const CUtensorMap& tmA, const CUte
       int mu, ng; decode(u, mu, ng);
       const int nt_end = min((ng + 1) * tpu, n_tiles);
       for (int nt = ng * tpu; nt < nt_end; ++nt, it += Cfg::PROMOTE ? 0 : 1) {
-        uint32_t as = it & 1, aph = (it >> 1) & 1;
+        uint32_t as = it % AS, aph = (it / AS) & 1;
         if constexpr (!Cfg::PROMOTE) { mbar_wait(&tempty[as], aph ^ 1); tc_fence_after(); }
         uint32_t acc = tmem_base + as * Cfg::ACC_COLS;
         const int kb_total = tr.k_blocks * NSEG;       // the K segments of split operands accumulate into the same tile
@@ -308,7 +335,7 @@ __device__ __forceinline__ void dpa_gemm_body(const CUtensorMap& tmA, const CUte
         for (int kb = 0; kb < kb_total; ++kb) {
           if constexpr (Cfg::PROMOTE) {
             if (kc == 0) {                             // a new chunk starts from zero in the next accumulator stage
-              as = it & 1; aph = (it >> 1) & 1;
+              as = it % AS; aph = (it / AS) & 1;
               mbar_wait(&tempty[as], aph ^ 1);
               tc_fence_after();
               acc = tmem_base + as * Cfg::ACC_COLS;
@@ -320,8 +347,12 @@ __device__ __forceinline__ void dpa_gemm_body(const CUtensorMap& tmA, const CUte
           if (elect_one()) {
             const uint32_t a_lo = a_base + st * (Cfg::A_BYTES >> 4), b_lo = b_base + st * (Cfg::B_BYTES >> 4);
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k)
-              umma_bf16<CG>(acc, DA::HI | (uint64_t)(a_lo + k * DA::KSTEP), DB::HI | (uint64_t)(b_lo + k * DB::KSTEP), idesc, (kacc | k) != 0);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+#pragma unroll
+              for (int h = 0; h < Cfg::NMMA; ++h)
+                umma_bf16<CG>(acc + h * Cfg::UMMA_N, DA::HI | (uint64_t)(a_lo + k * DA::KSTEP),
+                              DB::HI | (uint64_t)(b_lo + h * Cfg::B_MMA_STEP + k * DB::KSTEP), idesc, (kacc | k) != 0);
+            }
             if constexpr (Cfg::DUAL) {
               const uint32_t a2_lo = a2_base + st * (Cfg::A_BYTES >> 4), b2_lo = b2_base + st * (Cfg::B_BYTES >> 4);
 #pragma unroll
@@ -363,7 +394,7 @@ __device__ __forceinline__ void dpa_gemm_body(const CUtensorMap& tmA, const CUte
 #pragma unroll
           for (int i = 0; i < Cfg::ACC_COLS; ++i) sum[i] = 0.f;
           for (int ch = 0; ch < n_chunks; ++ch, ++it) {
-            const uint32_t as = it & 1, aph = (it >> 1) & 1;
+            const uint32_t as = it % Cfg::ACC_STAGES, aph = (it / Cfg::ACC_STAGES) & 1;
             mbar_wait(&tfull[as], aph);
             tc_fence_after();
 #pragma unroll
@@ -384,7 +415,7 @@ __device__ __forceinline__ void dpa_gemm_body(const CUtensorMap& tmA, const CUte
         }
       } else {
       for (int nt = ng * tpu; nt < nt_end; ++nt, ++it) {
-        const uint32_t as = it & 1, aph = (it >> 1) & 1;
+        const uint32_t as = it % Cfg::ACC_STAGES, aph = (it / Cfg::ACC_STAGES) & 1;
         mbar_wait(&tfull[as], aph);
         tc_fence_after();
         Epi::tile(ep, s, lane_base + as * Cfg::ACC_COLS, nt * BN);
@@ -674,14 +705,15 @@ __device__ __forceinline__ void store_out_chunk(float* dst, const float (&v)[32]
 #pragma unroll
   for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
 }
+template <class OutT> struct StoreRowsParams {
+  const DpaMeta* meta;
+  const int* src_pair; const int* src_ref;       // packed row -> flat (sequence*T + t) row of the dense tensors
+  OutT* dH_pair; OutT* dH_ref; int H;
+  OutT* packed;                                  // non-null: keep the rows packed ([n_tot][H]; vocab-parallel: the partial
+};                                               // sums are all-reduced in this compact form and scattered afterwards)
 template <int BN, class OutT = __nv_bfloat16>      // OutT = float: the fp32 path (split-bf16 operands)
 struct EpiStoreRows {
-  struct Params {
-    const DpaMeta* meta;
-    const int* src_pair; const int* src_ref;       // packed row -> flat (sequence*T + t) row of the dense tensors
-    OutT* dH_pair; OutT* dH_ref; int H;
-    OutT* packed;                                  // non-null: keep the rows packed ([n_tot][H]; vocab-parallel: the partial
-  };                                               // sums are all-reduced in this compact form and scattered afterwards)
+  using Params = StoreRowsParams<OutT>;            // (independent of the tile width: the 256- and 512-column kernels share it)
   struct State { OutT* out; };
   __device__ static void unit_begin(const Params& p, State& s, int erow, int) {
     const int p0 = p.meta->p0;
@@ -702,6 +734,8 @@ struct EpiStoreRows {
   }
   __device__ static void unit_end(const Params&, State&, int) {}
 };
+
+template <int BN> using EpiStoreRowsBf16 = EpiStoreRows<BN, __nv_bfloat16>;
 
 // ---- dW += dZ^T * H: fp32 accumulate into the [V][ld] fp32 buffer (thread == vocabulary row)
 template <int BN>
@@ -742,12 +776,13 @@ struct EpiAccumF32 {
 // ---- dW += dZ^T * H over the row chunks: the first chunk overwrites the fp32 accumulator (no memset), middle chunks add,
 //      the last chunk that has rows adds and writes bf16 straight to dW (no conversion pass).  Which chunk is first / last
 //      is decided on the device from DpaMeta (the host does not know the active row count).
+struct AccumDWParams {
+  const DpaMeta* meta; int chunk, chunk_rows;
+  float* acc32; __nv_bfloat16* out; int ld; int m_extent; int n_extent;
+};
 template <int BN>
 struct EpiAccumDW {
-  struct Params {
-    const DpaMeta* meta; int chunk, chunk_rows;
-    float* acc32; __nv_bfloat16* out; int ld; int m_extent; int n_extent;
-  };
+  using Params = AccumDWParams;
   struct State { float* acc; __nv_bfloat16* out; int first, last; };
   __device__ static void unit_begin(const Params& p, State& s, int, int trow_global) {
     const bool ok = trow_global < p.m_extent;

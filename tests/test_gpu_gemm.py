@@ -35,3 +35,19 @@ def test_debug_gemm(a_major, b_major, bn, M, N, K, cg):
     err = (D - ref).abs().max().item()
     scale = ref.abs().max().item()
     assert err <= 2e-3 * scale + 1e-3, f"max abs err {err} (scale {scale})"
+
+
+@pytest.mark.parametrize("a_major,b_major", [(0, 0), (0, 1), (1, 1), (1, 0)])
+@pytest.mark.parametrize("M,N,K", [(256, 512, 64), (384, 1024, 328), (1000, 1312, 4096), (2304, 4096, 1024)])
+def test_debug_gemm_512_wide_tiles(a_major, b_major, M, N, K):
+    """The 256 x 512 tile of the long-K gradient GEMMs: one accumulator stage of all 512 TMEM columns, two N = 256 MMAs
+    per K step, CTA pairs (incl. ragged M / N / K edges and several tiles per CTA)."""
+    from halva_b200 import debug_gemm
+    if (a_major == 1 and M % 8) or (b_major == 1 and N % 8):
+        pytest.skip("alignment")
+    As, Bs, ref = _mk(M, N, K, a_major, b_major, seed=3)
+    D = debug_gemm(As, Bs, a_major, b_major, 512)
+    torch.cuda.synchronize()
+    err = (D - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 2e-3 * scale + 1e-3, f"max abs err {err} (scale {scale})"
