@@ -108,7 +108,7 @@ def check(rc: int, what: str):
         raise DPAError(f"{what} failed ({rc}): {msg}")
 
 
-DEFAULT_CHUNK_ROWS = 16384
+DEFAULT_CHUNK_ROWS = 32768
 
 
 def default_chunk_rows() -> int:

@@ -267,8 +267,14 @@ constexpr int kTpuRef = 10;     // 128-wide column tiles per unit  (V=32000: 250
 constexpr int kBnPair = 256, kBnRef = 128;
 static_assert(kBnPair * kTpuPair == kBnRef * kTpuRef, "both tilings must produce the same column groups (shared partials)");
 
+// Rows per chunk of the packed row space (kept logits / dLogits scratch = chunk_rows x V x 2 B, twice in the fused-gradient
+// forward).  32768 holds every contributing row of a cfg-2 batch (24.8 K at 10 % phrase density) in ONE chunk: each GEMM class
+// then runs once per step, dW needs no fp32 accumulation pass, and 4 of 6 launch groups of the 16384-row chunking disappear.
+constexpr int kDefaultChunkRows = 32768;
+
 struct Layout {
   int n_pos_pair, n_pos_ref, cap_pair, cap_ref, nblk_pair, nblk_ref, ng_pair, ng_ref, ldz, chunk_rows, n_chunks;
+  int n_slots;      // fused-gradient forward: row chunks whose pair-row logits are KEPT (slot c = chunk c); later chunks reuse slot 0
   // state offsets
   size_t meta, bitmap, block_counts, src_pair, lab_pair, col_pair, src_ref, act_ref, stats_pair, stats_ref, stats_u,
       lse_pair, logp_pair, lse_ref_p, lse_ref_r, kl_row, PN, sigma, coef_pair, coef_ref, rinv, dnw32, state_total;
@@ -308,7 +314,7 @@ int make_layout(const dpa_shape_t& s, Layout& L) {
   L.ng_pair = ((s.V_local + kBnPair - 1) / kBnPair + kTpuPair - 1) / kTpuPair;
   L.ng_ref = ((s.V_local + kBnRef - 1) / kBnRef + kTpuRef - 1) / kTpuRef;
   L.ldz = round_up_i(s.V_local, 64);
-  L.chunk_rows = s.chunk_rows > 0 ? s.chunk_rows : 16384;
+  L.chunk_rows = s.chunk_rows > 0 ? s.chunk_rows : kDefaultChunkRows;
   if (L.chunk_rows % kRowPad) return fail(DPA_ERR_BAD_SHAPE, "chunk_rows=%d must be a multiple of %d", L.chunk_rows, kRowPad);
   const int cap_tot = L.cap_pair + L.cap_ref;
   L.chunk_rows = std::min(L.chunk_rows, cap_tot);
@@ -369,7 +375,12 @@ int make_layout(const dpa_shape_t& s, Layout& L) {
   L.u_part_pair = take((size_t)L.ng_pair * L.cap_pair * 16);
   L.u_part_ref = take((size_t)L.ng_ref * L.cap_ref * 16);
   L.u_part_u = take((size_t)L.ng_ref * L.cap_ref * 4);
-  L.u_dz = take((size_t)L.chunk_rows * L.ldz * 2);
+  // Kept bf16 logits: chunk c < n_slots owns slot c (its pair rows' logits are written by the statistics GEMM and turned into
+  // dLogits in place, never recomputed); chunks past the pair segment reuse slot 0.  One slot unless every position is
+  // processed (DPA_FLAG_DENSE: the pair segment then spans several chunks and all of them are kept -- 180 GB of HBM).
+  L.n_slots = (s.flags & DPA_FLAG_DENSE) ? std::max(1, (L.cap_pair + L.chunk_rows - 1) / L.chunk_rows) : 1;
+  L.n_slots = std::min(L.n_slots, L.n_chunks);
+  L.u_dz = take((size_t)L.n_slots * L.chunk_rows * L.ldz * 2);
   L.u_zr = take((size_t)L.chunk_rows * L.ldz * 2);
   L.u_dW32 = (s.flags & DPA_FLAG_NEED_DW) ? take((size_t)s.V_local * s.H * 4) : o;
   L.fused_total = o;
@@ -493,9 +504,10 @@ int run_norm_backward(const dpa_args_t* a, const Layout& L, const DeviceInfo* d,
   return DPA_OK;
 }
 
+enum : int { MERGE_ONLY = 0, MERGE_FINISH = 1, MERGE_FINISH_KL_LATER = 2 };
 int run_merge(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, const float4* part_pair, const float4* part_ref,
               const float* part_u, int n_pair, int n_ref, size_t stride_pair, size_t stride_ref, size_t stride_u, cudaStream_t st,
-              RowRange rr = RowRange{SEG_ALL, 0, 0});
+              RowRange rr = RowRange{SEG_ALL, 0, 0}, int finish = MERGE_ONLY);
 
 }  // namespace
 
@@ -508,6 +520,10 @@ struct MergeStrided {
   int n_parts_pair, n_parts_ref;
   size_t stride_pair, stride_ref, stride_u;     // element strides between partial records
   float4* stats_pair; float4* stats_ref; float* stats_u;
+  // finish != 0: also the per-row results (what finish_rows_kernel computes), in the same pass over the merged statistics
+  int finish, kl_from_stats;
+  const int* act_ref;
+  float* lse_pair; float* logp_pair; float* lse_ref_p; float* lse_ref_r; float* kl_row;
 };
 __global__ void merge_strided_kernel(MergeStrided a) {
   const int p0 = a.meta->p0;
@@ -522,6 +538,10 @@ __global__ void merge_strided_kernel(MergeStrided a) {
         s += p.y * expf(p.x - m); zy += p.z;
       }
       a.stats_pair[r] = make_float4(m, s, zy, 0.f);
+      if (a.finish) {
+        const float lse = m + logf(s);
+        a.lse_pair[r] = lse; a.logp_pair[r] = zy - lse;          // z[y] - LSE (halva_trainer.py:407)
+      }
     } else {
       const int j = r - p0;
       float mp = -INFINITY, mr = -INFINITY;
@@ -538,6 +558,12 @@ __global__ void merge_strided_kernel(MergeStrided a) {
       }
       a.stats_ref[j] = make_float4(mp, sp, mr, sr);
       if (a.part_u) a.stats_u[j] = u;
+      if (a.finish) {                                  // same maths as finish_rows_kernel (dpa_kernels.cuh)
+        a.lse_ref_p[j] = mp + logf(sp); a.lse_ref_r[j] = mr + logf(sr);
+        const float dlse = (mr - mp) + logf(sr / sp);
+        if (a.kl_from_stats) a.kl_row[j] = a.act_ref[j] ? (u / sr - dlse) : 0.f;
+        else a.kl_row[j] = dlse;                       // fused-gradient forward: dz_kl_elem_kernel finishes the row
+      }
     }
   }
 }
@@ -547,9 +573,12 @@ namespace {
 
 int run_merge(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, const float4* part_pair, const float4* part_ref,
               const float* part_u, int n_pair, int n_ref, size_t stride_pair, size_t stride_ref, size_t stride_u, cudaStream_t st,
-              RowRange rr) {
+              RowRange rr, int finish) {
   MergeStrided m{at<DpaMeta>(a->state, L.meta), rr, part_pair, part_ref, part_u, n_pair, n_ref, stride_pair, stride_ref, stride_u,
-                 at<float4>(a->state, L.stats_pair), at<float4>(a->state, L.stats_ref), at<float>(a->state, L.stats_u)};
+                 at<float4>(a->state, L.stats_pair), at<float4>(a->state, L.stats_ref), at<float>(a->state, L.stats_u),
+                 finish != MERGE_ONLY, finish == MERGE_FINISH, at<int>(a->state, L.act_ref), at<float>(a->state, L.lse_pair),
+                 at<float>(a->state, L.logp_pair), at<float>(a->state, L.lse_ref_p), at<float>(a->state, L.lse_ref_r),
+                 at<float>(a->state, L.kl_row)};
   ProfScope ps(PK_REDUCE, 1, st);
   merge_strided_kernel<<<d->sms * 2, 256, 0, st>>>(m);
   LAUNCH_CHECK("merge_partials");
@@ -567,19 +596,14 @@ int run_finish_rows(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, c
   return DPA_OK;
 }
 
-// P[b,k] / N[b,k] sums, then the loss phases asked for (LOSS_ALIGN needs the pair rows, LOSS_TOTAL every kl_row)
-int run_losses(const dpa_args_t* a, const Layout& L, cudaStream_t st, int phases) {
-  const DpaMeta* meta = at<DpaMeta>(a->state, L.meta);
-  ProfScope ps(PK_REDUCE, (phases & LOSS_ALIGN) ? 2 : 1, st);
-  if (phases & LOSS_ALIGN) {
-    PhraseArgs p{meta, at<int>(a->state, L.src_pair), at<int>(a->state, L.col_pair), at<float>(a->state, L.logp_pair),
-                 at<float>(a->state, L.PN), a->shape.T};
-    phrase_sums_kernel<<<2 * a->shape.B, 256, 0, st>>>(p);
-    LAUNCH_CHECK("phrase_sums");
-  }
-  LossArgs l{meta, at<float>(a->state, L.PN), at<float>(a->state, L.kl_row), at<float>(a->state, L.sigma), a->losses,
-             a->shape.B, a->shape.B_ref, a->alpha, phases};
-  loss_kernel<<<1, 1024, 0, st>>>(l);
+// P[b,k] / N[b,k] sums and the loss phases asked for, one launch (LOSS_ALIGN needs the pair rows' log-probs, LOSS_TOTAL every
+// kl_row).  `ticket`: DpaMeta::pad slot that counts finished blocks -- a different one per launch of the same call.
+int run_losses(const dpa_args_t* a, const Layout& L, cudaStream_t st, int phases, int ticket) {
+  LossArgs l{at<DpaMeta>(a->state, L.meta), at<int>(a->state, L.src_pair), at<int>(a->state, L.col_pair), at<float>(a->state, L.logp_pair),
+             at<float>(a->state, L.PN), at<float>(a->state, L.kl_row), at<float>(a->state, L.sigma), a->losses,
+             a->shape.B, a->shape.B_ref, a->shape.T, a->alpha, phases, ticket};
+  ProfScope ps(PK_REDUCE, 1, st);
+  loss_kernel<<<(phases & LOSS_ALIGN) ? 2 * a->shape.B : 1, 256, 0, st>>>(l);
   LAUNCH_CHECK("loss");
   return DPA_OK;
 }
@@ -587,7 +611,7 @@ int run_losses(const dpa_args_t* a, const Layout& L, cudaStream_t st, int phases
 int run_finish(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, cudaStream_t st) {
   int rc = run_finish_rows(a, L, d, st, RowRange{SEG_ALL, 0, 0});
   if (rc) return rc;
-  return run_losses(a, L, st, LOSS_ALIGN | LOSS_TOTAL);
+  return run_losses(a, L, st, LOSS_ALIGN | LOSS_TOTAL, 0);
 }
 
 int run_meta(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, cudaStream_t st) {
@@ -658,6 +682,16 @@ int nccl_bind() {
 #define NCCL_TRY(x) do { int r_ = (x); if (r_ != 0) return fail(DPA_ERR_NCCL, "%s: %s", #x, g_nccl.GetErrorString(r_)); } while (0)
 bool comm_active(const dpa_shape_t& s) { return g_comm.comm && g_comm.world > 1 && s.V_local < s.V; }
 
+// ---------------------------------------------------------------------------------- auxiliary stream
+// The dense gradient tensors must come back fully written (zeros for rows without a contribution): 0.8 GB of memset per
+// cfg-2 step.  It runs on a library-owned side stream, forked from the caller's stream at the start of the pass and joined
+// before the first dH GEMM, so the HBM-bound fill hides behind the tensor-bound statistics GEMM (event fork / join: legal
+// inside a CUDA-graph capture).  One stream + two events per device, created on first use.  DPA_ASYNC_ZERO=0 disables.
+struct Aux { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+Aux g_aux[16];
+std::mutex g_aux_mu;
+bool async_zero() { static const bool v = env_int("DPA_ASYNC_ZERO", 1) != 0; return v; }
+
 // ---------------------------------------------------------------------------------- one call's GEMM plan
 // Tensor maps over the packed operands of this call and one method per GEMM class.  `scratch` offsets differ between
 // the forward / backward / fused-forward layouts, everything else is shared.
@@ -666,6 +700,9 @@ struct Plan {
   const dpa_shape_t& s;
   const DpaMeta* meta;
   __nv_bfloat16* dz = nullptr; __nv_bfloat16* zr = nullptr; float* dW32 = nullptr;
+  int n_slots = 1;                        // kept-logit slots behind `dz` (fused-gradient forward; 1 elsewhere)
+  int slot_of(int ch) const { return ch < n_slots ? ch : 0; }
+  __nv_bfloat16* dz_of(int ch) const { return dz + (size_t)slot_of(ch) * L.chunk_rows * L.ldz; }
   __nv_bfloat16* dH_packed = nullptr;     // vocab-parallel with the library's communicator: dH rows stay packed until reduced
   float4* part_pair = nullptr; float4* part_ref = nullptr; float* part_u = nullptr;
   CUtensorMap tmHp, tmHf, tmW256, tmW128, tmW64, tmWr256, tmWr128, tmWr64, tmDzK, tmWmn, tmDzMN, tmHpMN;
@@ -682,9 +719,10 @@ struct Plan {
       : a(a_), L(L_), d(d_), st(st_), s(a_->shape), meta(at<DpaMeta>(a_->state, L_.meta)) {}
 
   int init(size_t oHp, size_t oHf, size_t oPartPair, size_t oPartRef, size_t oPartU, bool has_parts, __nv_bfloat16* dz_, __nv_bfloat16* zr_,
-           float* dW32_, const Layout::Split* split_ = nullptr) {
+           float* dW32_, const Layout::Split* split_ = nullptr, int n_slots_ = 1) {
     const int cap_tot = L.cap_pair + L.cap_ref;
-    dz = dz_; zr = zr_; dW32 = dW32_; split = split_;
+    dz = dz_; zr = zr_; dW32 = dW32_; split = split_; n_slots = n_slots_;
+    const int dz_rows = n_slots * L.chunk_rows;
     if (has_parts) {
       part_pair = at<float4>(a->scratch, oPartPair); part_ref = at<float4>(a->scratch, oPartRef); part_u = at<float>(a->scratch, oPartU);
     }
@@ -712,9 +750,9 @@ struct Plan {
     if (dz) {
       // dH = dZ[rows x V] * W[V x H]:      A = dz K-major (K = vocab),  B = W MN-major (N = hidden contiguous)
       // dW = dZ^T[V x rows] * H[rows x H]: A = dz MN-major (M = vocab), B = packed hidden rows MN-major
-      if ((rc = make_operand_tmap(d, &tmDzK, dz, KMAJOR, L.chunk_rows, s.V_local, L.ldz, BM))) return rc;
+      if ((rc = make_operand_tmap(d, &tmDzK, dz, KMAJOR, dz_rows, s.V_local, L.ldz, BM))) return rc;
       if ((rc = make_operand_tmap(d, &tmWmn, Wb, MNMAJOR, s.H, s.V_local, s.H, 0))) return rc;
-      if ((rc = make_operand_tmap(d, &tmDzMN, dz, MNMAJOR, s.V_local, L.chunk_rows, L.ldz, 0))) return rc;
+      if ((rc = make_operand_tmap(d, &tmDzMN, dz, MNMAJOR, s.V_local, dz_rows, L.ldz, 0))) return rc;
       if ((rc = make_operand_tmap(d, &tmHpMN, Hp, MNMAJOR, s.H, cap_tot, s.H, 0))) return rc;
     }
     if (split) {
@@ -822,7 +860,7 @@ struct Plan {
     using Epi = EpiDzPair<kBnPair, ROUND>;
     GemmWork w{meta, KIND_DZ_PAIR, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair, super_m().stats, hint_stats().a, hint_stats().b};
     typename Epi::Params ep{at<int>(a->state, L.lab_pair), at<float>(a->state, L.lse_pair), at<float>(a->state, L.coef_pair),
-                            dz, L.ldz, ch * L.chunk_rows, s.V_local, s.v_offset, 0};
+                            dz_of(ch), L.ldz, ch * L.chunk_rows, s.V_local, s.v_offset, 0};
     ProfScope ps(PK_DZ_PAIR, 1, st);
     if constexpr (!ROUND) {
       if (split) {
@@ -859,7 +897,7 @@ struct Plan {
     {
       ProfScope ps(PK_STASH_REF, given ? 1 : 2, st);
       GemmWork wp{meta, KIND_STASH_POL, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair, super_m().stats, hint_stats().a, hint_stats().b};
-      typename Epi::Params epp{meta, part2, dz, L.cap_ref, s.V_local, L.ldz, ch * L.chunk_rows, 0};
+      typename Epi::Params epp{meta, part2, dz_of(ch), L.cap_ref, s.V_local, L.ldz, ch * L.chunk_rows, 0};
       int rc = launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHp, tmW256, tmW128, wp, epp, "stash_pol");
       if (rc) return rc;
       if (!given) {
@@ -882,6 +920,7 @@ struct Plan {
   }
   // dH = dz W (rows scattered to their [s,t] positions) and, if lm_head is trainable, dW += dz^T H for chunk ch
   int grad_gemms(int ch) {
+    { int rc = join_zero(); if (rc) return rc; }
     if (split) {              // fp32 inputs: split-bf16 dz and operands, fp32 gradients; dW accumulates in place
       {
         using Epi = EpiStoreRows<kBnSplit, float>;
@@ -905,7 +944,8 @@ struct Plan {
       using P = typename EpiStoreRows<256>::Params;
       const int wide = (cta_group() == 2 && grad_bn() == 512) ? 1 : 0;
       // 512-wide tiles: a super-block of 9 row units x all column tiles is one wave of the 74 CTA pairs
-      GemmWork w{meta, KIND_DH, ch, L.chunk_rows, 0, s.H, s.V_local, 1, super_m().dh ? super_m().dh : (wide ? 9 : 0), hint_dh().a, hint_dh().b};
+      GemmWork w{meta, KIND_DH, ch, L.chunk_rows, 0, s.H, s.V_local, 1, super_m().dh ? super_m().dh : (wide ? 9 : 0), hint_dh().a, hint_dh().b,
+                 slot_of(ch) * L.chunk_rows};
       P ep{meta, at<int>(a->state, L.src_pair), at<int>(a->state, L.src_ref),
            static_cast<__nv_bfloat16*>(a->dH_pair), static_cast<__nv_bfloat16*>(a->dH_ref), s.H, dH_packed};
       {
@@ -918,7 +958,8 @@ struct Plan {
     if (dW32) {
       using P = typename EpiAccumDW<256>::Params;
       const int wide = (cta_group() == 2 && grad_bn() == 512) ? 1 : 0;
-      GemmWork w{meta, KIND_DW, ch, L.chunk_rows, s.V_local, s.H, 0, 1, super_m().dw ? super_m().dw : (wide ? 9 : 0), hint_dw().a, hint_dw().b};
+      GemmWork w{meta, KIND_DW, ch, L.chunk_rows, s.V_local, s.H, 0, 1, super_m().dw ? super_m().dw : (wide ? 9 : 0), hint_dw().a, hint_dw().b,
+                 slot_of(ch) * L.chunk_rows};
       P ep{meta, ch, L.chunk_rows, dW32, static_cast<__nv_bfloat16*>(a->dW), s.H, s.V_local, s.H};
       ProfScope ps(PK_DW, 1, st);
       return launch_grad<EpiAccumDW, MNMAJOR, MNMAJOR>(st, d, tmDzMN, tmHpMN, w, ep, "dW");
@@ -944,14 +985,41 @@ struct Plan {
     CUDA_TRY(cudaEventDestroy(e));
     return DPA_OK;
   }
+  bool zero_pending = false;
   int zero_grad_outputs() {
     ProfScope ps(PK_MISC, 0, st);
     const size_t es = split ? 4 : 2;
-    CUDA_TRY(cudaMemsetAsync(a->dH_pair, 0, (size_t)2 * s.B * s.T * s.H * es, st));
-    CUDA_TRY(cudaMemsetAsync(a->dH_ref, 0, (size_t)s.B_ref * s.T_ref * s.H * es, st));
+    cudaStream_t zs = st;
+    Aux* aux = nullptr;
+    std::unique_lock<std::mutex> lk(g_aux_mu, std::defer_lock);
+    if (async_zero()) {
+      int dev = 0; CUDA_TRY(cudaGetDevice(&dev));
+      lk.lock();
+      aux = &g_aux[dev & 15];
+      if (!aux->s) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&aux->s, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&aux->fork, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&aux->join, cudaEventDisableTiming));
+      }
+      CUDA_TRY(cudaEventRecord(aux->fork, st));
+      CUDA_TRY(cudaStreamWaitEvent(aux->s, aux->fork, 0));
+      zs = aux->s;
+    }
+    CUDA_TRY(cudaMemsetAsync(a->dH_pair, 0, (size_t)2 * s.B * s.T * s.H * es, zs));
+    CUDA_TRY(cudaMemsetAsync(a->dH_ref, 0, (size_t)s.B_ref * s.T_ref * s.H * es, zs));
+    if (aux) { CUDA_TRY(cudaEventRecord(aux->join, aux->s)); zero_pending = true; }
     return DPA_OK;      // (the dW accumulator needs no memset: the first chunk's epilogue overwrites it)
   }
+  int join_zero() {       // the caller's stream waits for the fill: before the first kernel that writes dH rows
+    if (!zero_pending) return DPA_OK;
+    zero_pending = false;
+    int dev = 0; CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_aux_mu);
+    CUDA_TRY(cudaStreamWaitEvent(st, g_aux[dev & 15].join, 0));
+    return DPA_OK;
+  }
   int finish_dW() {
+    { int rc = join_zero(); if (rc) return rc; }
     if (!(s.flags & DPA_FLAG_NEED_DW) || !a->dW) return DPA_OK;
     ProfScope ps(PK_MISC, 1, st);      // the last chunk with rows wrote dW; only the no-rows-at-all case is left
     zero_if_no_rows_kernel<<<d->sms * 2, 256, 0, st>>>(meta, a->dW, (size_t)s.V_local * s.H * (split ? 4 : 2));
@@ -966,13 +1034,13 @@ struct Plan {
     LAUNCH_CHECK("coef");
     return DPA_OK;
   }
-  int merge(RowRange rr, bool with_u) {
-    return run_merge(a, L, d, part_pair, part_ref, with_u ? part_u : nullptr, L.ng_pair, L.ng_ref, L.cap_pair, L.cap_ref, L.cap_ref, st, rr);
+  int merge(RowRange rr, bool with_u, int finish = MERGE_ONLY) {
+    return run_merge(a, L, d, part_pair, part_ref, with_u ? part_u : nullptr, L.ng_pair, L.ng_ref, L.cap_pair, L.cap_ref, L.cap_ref, st, rr, finish);
   }
 };
 
 // ---------------------------------------------------------------------------------- statistics-only forward
-int forward_stats_impl(const dpa_args_t* a, cudaStream_t st, Layout& L, DeviceInfo** dev) {
+int forward_stats_impl(const dpa_args_t* a, cudaStream_t st, Layout& L, DeviceInfo** dev, int finish = MERGE_ONLY) {
   int rc = check_common(a, L, dev);
   if (rc) return rc;
   DeviceInfo* d = *dev;
@@ -988,7 +1056,7 @@ int forward_stats_impl(const dpa_args_t* a, cudaStream_t st, Layout& L, DeviceIn
   const bool round = (a->shape.flags & DPA_FLAG_ROUND_LOGITS) != 0;
   if ((rc = round ? p.fwd_pair<true>(0) : p.fwd_pair<false>(0))) return rc;
   if ((rc = round ? p.fwd_ref<true>() : p.fwd_ref<false>())) return rc;
-  return p.merge(RowRange{SEG_ALL, 0, 0}, true);
+  return p.merge(RowRange{SEG_ALL, 0, 0}, true, finish);
 }
 
 // ---------------------------------------------------------------------------------- fused-gradient forward
@@ -1010,38 +1078,39 @@ int forward_fused_impl(const dpa_args_t* a, cudaStream_t st) {
   Plan p(a, L, d, st);
   if ((rc = p.init(L.u_Hp, L.u_Hf, L.u_part_pair, L.u_part_ref, L.u_part_u, true, at<__nv_bfloat16>(a->scratch, L.u_dz),
                    at<__nv_bfloat16>(a->scratch, L.u_zr),
-                   ((s.flags & DPA_FLAG_NEED_DW) && !loss_only) ? at<float>(a->scratch, L.u_dW32) : nullptr))) return rc;
+                   ((s.flags & DPA_FLAG_NEED_DW) && !loss_only) ? at<float>(a->scratch, L.u_dW32) : nullptr, nullptr, L.n_slots))) return rc;
 
   if ((rc = run_meta(a, L, d, st))) return rc;
   if ((rc = run_gather(a, L, d, a->scratch, L.u_Hp, L.u_Hf, st))) return rc;
   if (!loss_only && (rc = p.zero_grad_outputs())) return rc;
 
   // ---- alignment half: statistics of every pair row -> P, N -> sigma, alignment loss -> row coefficients
-  if ((rc = p.fwd_pair<true>(loss_only ? 0 : L.chunk_rows))) return rc;   // nothing else touches chunk 0's dz buffer until its turn
-  if ((rc = p.merge(RowRange{SEG_PAIR, 0, 0}, true))) return rc;
-  if ((rc = run_finish_rows(a, L, d, st, RowRange{SEG_PAIR, 0, 0}))) return rc;
-  if ((rc = run_losses(a, L, st, LOSS_ALIGN))) return rc;
+  // (the statistics GEMM keeps the logits of the pair rows of every slot; nothing else touches a slot until its chunk's turn)
+  if ((rc = p.fwd_pair<true>(loss_only ? 0 : L.n_slots * L.chunk_rows))) return rc;
+  if ((rc = p.merge(RowRange{SEG_PAIR, 0, 0}, true, MERGE_FINISH))) return rc;
+  if ((rc = run_losses(a, L, st, LOSS_ALIGN, 0))) return rc;
   if ((rc = p.coef(nullptr /* d_loss = 1 */))) return rc;
 
   // ---- row chunks of the packed space [pair rows | reference-sample rows]
   for (int ch = 0; ch < L.n_chunks; ++ch) {
     if (loss_only) {
       // no dz of the pair rows is needed
-    } else if (ch == 0) {
-      DzPairElemArgs e{p.meta, L.chunk_rows, p.dz, L.ldz, s.V_local, s.v_offset, at<int>(a->state, L.lab_pair),
+    } else if ((long long)ch * L.chunk_rows >= L.cap_pair) {
+      // past the pair segment
+    } else if (ch < L.n_slots) {                                  // kept logits -> dLogits in place
+      DzPairElemArgs e{p.meta, ch * L.chunk_rows, (ch + 1) * L.chunk_rows, p.dz, L.ldz, s.V_local, s.v_offset, at<int>(a->state, L.lab_pair),
                        at<float>(a->state, L.lse_pair), at<float>(a->state, L.coef_pair)};
       ProfScope ps(PK_DZ_ELEM, 1, st);
       dz_pair_elem_kernel<<<d->sms * 8, 256, 0, st>>>(e);
       LAUNCH_CHECK("dz_pair_elem");
-    } else if ((long long)ch * L.chunk_rows < L.cap_pair) {      // pair rows beyond chunk 0 (if any): recompute
+    } else {                                                       // pair rows beyond the kept slots (if any): recompute
       if ((rc = p.dz_pair<true>(ch))) return rc;
     }
     if ((rc = p.stash_ref(ch))) return rc;
     const RowRange rr{SEG_REF_CHUNK, ch, L.chunk_rows};
-    if ((rc = p.merge(rr, false))) return rc;
-    if ((rc = run_finish_rows(a, L, d, st, rr, /*kl_from_stats=*/false))) return rc;
+    if ((rc = p.merge(rr, false, MERGE_FINISH_KL_LATER))) return rc;
     {
-      DzElemArgs e{p.meta, ch, L.chunk_rows, p.dz, p.zr, L.ldz, s.V_local, at<float>(a->state, L.lse_ref_p), at<float>(a->state, L.lse_ref_r),
+      DzElemArgs e{p.meta, ch, L.chunk_rows, p.dz_of(ch), p.zr, L.ldz, s.V_local, at<float>(a->state, L.lse_ref_p), at<float>(a->state, L.lse_ref_r),
                    at<float>(a->state, L.coef_ref), at<int>(a->state, L.act_ref), at<float>(a->state, L.kl_row)};
       ProfScope ps(PK_DZ_ELEM, 1, st);
       dz_kl_elem_kernel<<<d->sms * 8, 256, 0, st>>>(e);
@@ -1049,7 +1118,7 @@ int forward_fused_impl(const dpa_args_t* a, cudaStream_t st) {
     }
     if (!loss_only && (rc = p.grad_gemms(ch))) return rc;
   }
-  if ((rc = run_losses(a, L, st, LOSS_TOTAL))) return rc;
+  if ((rc = run_losses(a, L, st, LOSS_TOTAL, 1))) return rc;
   if (loss_only) return DPA_OK;
   if ((rc = run_norm_backward(a, L, d, st))) return rc;
   return p.finish_dW();
@@ -1167,8 +1236,10 @@ int dpa_forward_finish(const dpa_args_t* a, const void* gathered, int n_shards, 
     const size_t rec = L.row_stats_bytes;
     if (rec % 16) return fail(DPA_ERR_BAD_SHAPE, "row-stats record not 16-byte sized");
     rc = run_merge(a, L, d, reinterpret_cast<const float4*>(g), reinterpret_cast<const float4*>(g + (L.stats_ref - L.stats_pair)),
-                   reinterpret_cast<const float*>(g + (L.stats_u - L.stats_pair)), n_shards, n_shards, rec / 16, rec / 16, rec / 4, st);
+                   reinterpret_cast<const float*>(g + (L.stats_u - L.stats_pair)), n_shards, n_shards, rec / 16, rec / 16, rec / 4, st,
+                   RowRange{SEG_ALL, 0, 0}, MERGE_FINISH);
     if (rc) return rc;
+    return run_losses(a, L, st, LOSS_ALIGN | LOSS_TOTAL, 0);
   }
   return run_finish(a, L, d, st);
 }
@@ -1180,9 +1251,10 @@ int dpa_forward(const dpa_args_t* a, void* stream) {
     if (comm_active(a->shape)) return fail(DPA_ERR_ARG, "DPA_FLAG_FUSED_GRAD is not available with a vocab-sharded lm_head");
     return forward_fused_impl(a, st);
   }
-  int rc = forward_stats_impl(a, st, L, &d);
+  const bool exchange = a && comm_active(a->shape);
+  int rc = forward_stats_impl(a, st, L, &d, exchange ? MERGE_ONLY : MERGE_FINISH);
   if (rc) return rc;
-  if (comm_active(a->shape)) {
+  if (exchange) {
     // the one exchange step of the forward: every shard's per-row statistics record -> all ranks -> max-rescale merge
     if (a->shape.flags & DPA_FLAG_FUSED_NORM) return fail(DPA_ERR_ARG, "DPA_FLAG_FUSED_NORM is not available with a vocab-sharded lm_head");
     char* g = at<char>(a->scratch, L.f_gather);
@@ -1190,10 +1262,11 @@ int dpa_forward(const dpa_args_t* a, void* stream) {
     NCCL_TRY(g_nccl.AllGather(at<char>(a->state, L.stats_pair), g, rec, kNcclUint8, g_comm.comm, st));
     const int G = g_comm.world;
     rc = run_merge(a, L, d, reinterpret_cast<const float4*>(g), reinterpret_cast<const float4*>(g + (L.stats_ref - L.stats_pair)),
-                   reinterpret_cast<const float*>(g + (L.stats_u - L.stats_pair)), G, G, rec / 16, rec / 16, rec / 4, st);
+                   reinterpret_cast<const float*>(g + (L.stats_u - L.stats_pair)), G, G, rec / 16, rec / 16, rec / 4, st,
+                   RowRange{SEG_ALL, 0, 0}, MERGE_FINISH);
     if (rc) return rc;
   }
-  return run_finish(a, L, d, st);
+  return run_losses(a, L, st, LOSS_ALIGN | LOSS_TOTAL, 0);
 }
 
 int dpa_backward(const dpa_args_t* a, void* stream) {
@@ -1290,7 +1363,7 @@ int dpa_debug_gemm(const void* A, const void* B, float* D, int M, int N, int K, 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUtensorMap tmA, tmB;
   if ((rc = make_operand_tmap(d, &tmA, A, a_major, M, K, a_major == KMAJOR ? K : M, BM))) return rc;
-  if ((rc = make_operand_tmap(d, &tmB, B, b_major, N, K, b_major == KMAJOR ? K : N, bn))) return rc;
+  if ((rc = make_operand_tmap(d, &tmB, B, b_major, N, K, b_major == KMAJOR ? K : N, bn > 256 ? 256 : bn))) return rc;
   GemmWork w{nullptr, KIND_STATIC, 0, 0, M, N, K, 1, 0};
   if (bn == 128 && a_major == KMAJOR && b_major == KMAJOR) {     // the tile shape of the dual-accumulator kernels
     using Epi = EpiAccumF32<128>;

@@ -77,6 +77,7 @@ struct GemmWork {
   int tiles_per_unit;  // consecutive column tiles per work unit
   int super_m;         // row-tile units per L2 super-block of the unit order (0 = kSuperM)
   int hint_a, hint_b;  // L2 eviction priority of the A / B operand loads: 0 = none, 1 = evict_first, 2 = evict_last
+  int dz_row0;         // KIND_DH / KIND_DW: first row of this chunk's slot inside the kept-logits / dz buffer the dz map spans
 };
 
 struct TileRange {
@@ -106,12 +107,12 @@ __device__ __forceinline__ TileRange compute_range(const GemmWork& w) {
     case KIND_DZ_REF:
     case KIND_STASH_POL: lo = max(c_lo, p0); hi = min(c_hi, n_tot); r.a_row0 = lo; r.a2_row0 = lo - p0; r.e_row0 = lo; break;
     case KIND_STASH_FRZ: lo = max(c_lo, p0); hi = min(c_hi, n_tot); r.a_row0 = lo - p0; r.e_row0 = lo; break;
-    case KIND_DH: lo = c_lo; hi = min(c_hi, n_tot); r.a_row0 = 0; r.e_row0 = lo; break;
+    case KIND_DH: lo = c_lo; hi = min(c_hi, n_tot); r.a_row0 = w.dz_row0; r.e_row0 = lo; break;
     case KIND_DW: {
       lo = c_lo; hi = min(c_hi, n_tot);
       const int rows = max(hi - lo, 0);
       r.m_tiles = rows > 0 ? (w.m_static + BM - 1) / BM : 0;
-      r.a_row0 = 0; r.e_row0 = 0; r.k_blocks = rows / BK; r.a_k0 = 0; r.b_k0 = lo;
+      r.a_row0 = 0; r.e_row0 = 0; r.k_blocks = rows / BK; r.a_k0 = w.dz_row0; r.b_k0 = lo;
       return r;
     }
   }

@@ -460,44 +460,21 @@ __global__ void finish_rows_kernel(FinishArgs a) {
   }
 }
 
-// ---- P[b,k], N[b,k]: one block per sequence, one warp per phrase column round-robin; fixed summation order
-struct PhraseArgs {
-  const DpaMeta* meta;
+// ---- P[b,k], N[b,k] and the loss assembly in ONE launch: one block per sequence computes its row of P / N (one warp per
+//      phrase column round-robin, fixed summation order); the last block to finish (ticket in DpaMeta) assembles
+//      align = mean log(1+exp(N-P)), sigma for the backward and / or div = sum(kl)/B_ref and the total.
+enum : int { LOSS_ALIGN = 1, LOSS_TOTAL = 2 };
+struct LossArgs {
+  DpaMeta* meta;
   const int* src_pair; const int* col_pair; const float* logp_pair;
   float* PN;        // [2B][kMaxSign+1]
-  int T;
-};
-__global__ void phrase_sums_kernel(PhraseArgs a) {
-  const int s = blockIdx.x;
-  const int n = a.meta->n_pair, K = a.meta->K;
-  // packed rows are sequence-major: binary-search this sequence's range by source row
-  const int lo_key = s * a.T, hi_key = (s + 1) * a.T;
-  int lo = 0, hi = n;
-  while (lo < hi) { const int mid = (lo + hi) >> 1; if (a.src_pair[mid] < lo_key) lo = mid + 1; else hi = mid; }
-  const int r0 = lo;
-  hi = n;
-  while (lo < hi) { const int mid = (lo + hi) >> 1; if (a.src_pair[mid] < hi_key) lo = mid + 1; else hi = mid; }
-  const int r1 = lo;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int k = warp; k < K && k <= kMaxSign; k += nw) {
-    float acc = 0.f;
-    for (int r = r0 + lane; r < r1; r += 32)
-      if ((a.col_pair[r] & 0xFFFF) == k) acc += a.logp_pair[r];
-    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) a.PN[(size_t)s * (kMaxSign + 1) + k] = acc;
-  }
-}
-
-// ---- loss assembly (one block): align = mean log(1+exp(N-P)), div = sum(kl)/B_ref, sigma for the backward
-struct LossArgs {
-  const DpaMeta* meta;
-  const float* PN; const float* kl_row;
+  const float* kl_row;
   float* sigma;     // [B][kMaxSign+1]  d align / d x
   float* losses;    // [4]
-  int B, B_ref; float alpha;
-  int phases;       // bit 0: alignment loss + sigma (needs P, N);  bit 1: divergence + total (needs every kl_row)
+  int B, B_ref, T; float alpha;
+  int phases;       // bit 0: P / N sums, alignment loss + sigma;  bit 1: divergence + total (needs every kl_row)
+  int ticket;       // which DpaMeta::pad slot counts finished blocks (one per launch of a call)
 };
-enum : int { LOSS_ALIGN = 1, LOSS_TOTAL = 2 };
 __device__ __forceinline__ float block_sum(float v, float* sh) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -513,16 +490,45 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
   __syncthreads();
   return sh[0];
 }
-__global__ void loss_kernel(LossArgs a) {
+__global__ void __launch_bounds__(256) loss_kernel(LossArgs a) {
   __shared__ float sh[32];
+  __shared__ int is_last;
   const int K = a.meta->K, status = a.meta->status;
-  const int BK_ = a.B * max(K, 0);
   if (a.phases & LOSS_ALIGN) {
+    const int s = blockIdx.x;                         // grid = 2B sequences
+    const int n = a.meta->n_pair;
+    // packed rows are sequence-major: binary-search this sequence's range by source row
+    const int lo_key = s * a.T, hi_key = (s + 1) * a.T;
+    int lo = 0, hi = n;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (a.src_pair[mid] < lo_key) lo = mid + 1; else hi = mid; }
+    const int r0 = lo;
+    hi = n;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (a.src_pair[mid] < hi_key) lo = mid + 1; else hi = mid; }
+    const int r1 = lo;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int k = warp; k < K && k <= kMaxSign; k += nw) {
+      float acc = 0.f;
+      for (int r = r0 + lane; r < r1; r += 32)
+        if ((a.col_pair[r] & 0xFFFF) == k) acc += a.logp_pair[r];
+      for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) a.PN[(size_t)s * (kMaxSign + 1) + k] = acc;
+    }
+    if (gridDim.x > 1) {                              // the last block to get here assembles the loss
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) is_last = atomicAdd(&a.meta->pad[a.ticket], 1) == (int)gridDim.x - 1;
+      __syncthreads();
+      if (!is_last) return;
+      __threadfence();
+    } else {
+      __syncthreads();
+    }
+    const int BK_ = a.B * max(K, 0);
     float acc = 0.f;
     for (int i = threadIdx.x; i < BK_; i += blockDim.x) {
       const int b = i / K, k = i - b * K;
-      const float P = a.PN[(size_t)b * (kMaxSign + 1) + k];
-      const float N = a.PN[(size_t)(a.B + b) * (kMaxSign + 1) + k];
+      const float P = __ldcg(&a.PN[(size_t)b * (kMaxSign + 1) + k]);
+      const float N = __ldcg(&a.PN[(size_t)(a.B + b) * (kMaxSign + 1) + k]);
       const float e = expf(N - P);                       // literal log(1 + exp(x)) (halva_trainer.py:567)
       acc += logf(1.f + e);
       a.sigma[(size_t)b * (kMaxSign + 1) + k] = (e / (1.f + e)) / (float)BK_;
@@ -533,6 +539,8 @@ __global__ void loss_kernel(LossArgs a) {
       if (status & (DPA_STATUS_BAD_SIGN | DPA_STATUS_K_MISMATCH | DPA_STATUS_K_ZERO | DPA_STATUS_BAD_LABEL)) align = nanf("");
       a.losses[1] = align;
     }
+  } else if (blockIdx.x != 0) {
+    return;
   }
   if (a.phases & LOSS_TOTAL) {
     float kacc = 0.f;
@@ -714,7 +722,7 @@ __global__ void __launch_bounds__(256) stash_given_kernel(StashGivenArgs a) {
 // ---- fused-gradient forward, pair rows of row chunk 0: dz = coef (onehot(y) - softmax(z)) in place over the logits the
 //      statistics GEMM kept (2 B read + 2 B written per logit) -- the recompute GEMM only runs for pair rows beyond chunk 0
 struct DzPairElemArgs {
-  const DpaMeta* meta; int chunk_rows;
+  const DpaMeta* meta; int row_lo, row_hi;          // packed pair rows [row_lo, min(row_hi, p0)) -- the chunk's kept logits
   __nv_bfloat16* dz; int ldz, v_local, v_offset;
   const int* labels; const float* lse; const float* coef;        // indexed by packed row
 };
@@ -726,10 +734,10 @@ __device__ __forceinline__ uint32_t dzp_pack2(uint32_t z, float c, float nl, int
   return pack_bf16x2(a, b);
 }
 __global__ void __launch_bounds__(256) dz_pair_elem_kernel(DzPairElemArgs a) {
-  const int hi = min(a.meta->p0, a.chunk_rows);
+  const int hi = min(a.meta->p0, a.row_hi);
   const int nvec = (a.v_local + 7) >> 3;
   constexpr int U = 4;
-  for (int r = blockIdx.x; r < hi; r += gridDim.x) {
+  for (int r = a.row_lo + blockIdx.x; r < hi; r += gridDim.x) {
     uint4* pz = reinterpret_cast<uint4*>(a.dz + (size_t)r * a.ldz);
     const float c = a.coef[r];
     if (c == 0.f) {                                   // padding rows (and ignored rows in dense mode)
