@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhalva_dpa.so")
 SOURCES = [os.path.join(CSRC, "dpa_api.cu"), os.path.join(CSRC, "dpa_host.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("dpa_ptx.cuh", "dpa_gemm.cuh", "dpa_kernels.cuh")] + \
+DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("dpa_ptx.cuh", "dpa_gemm.cuh", "dpa_kernels.cuh", "dpa_peer.cuh")] + \
     [os.path.join(os.path.dirname(HERE), "include", "halva_dpa.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "--use_fast_math" if False else "-DDPA_BUILD=1"]

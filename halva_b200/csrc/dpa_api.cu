@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "dpa_kernels.cuh"
+#include "dpa_peer.cuh"
 
 using namespace dpa;
 
@@ -288,7 +289,7 @@ struct Layout {
   struct Split { size_t W3, Wr3; } f_split, b_split;
   bool split;
   // fused-gradient forward scratch offsets (DPA_FLAG_FUSED_GRAD)
-  size_t u_Hp, u_Hf, u_part_pair, u_part_ref, u_part_u, u_dz, u_zr, u_dW32, fused_total;
+  size_t u_Hp, u_Hf, u_part_pair, u_part_ref, u_part_u, u_dz, u_zr, u_dW32, u_gather, fused_total;
 };
 
 int g_layout_comm_world = 1;   // set by dpa_comm_init / dpa_comm_destroy (declared before the communicator itself)
@@ -365,8 +366,7 @@ int make_layout(const dpa_shape_t& s, Layout& L) {
   L.b_dz = take(parts * L.chunk_rows * L.ldz * 2);
   L.b_dW32 = ((s.flags & DPA_FLAG_NEED_DW) && !L.split) ? take((size_t)s.V_local * s.H * 4) : o;   // fp32: dW itself accumulates
   take_split(L.b_split);
-  // library-side vocab-parallel exchange: dH partial sums stay packed (active rows only) for the all-reduce
-  L.b_dHp = (comm_world > 1 && s.V_local < s.V) ? take((size_t)cap_tot * s.H * 2) : o;
+  L.b_dHp = o;    // (library-side vocab-parallel exchange: the packed dH partial sums live in the communicator's peer memory)
   L.bwd_total = o;
 
   o = 0;
@@ -383,6 +383,8 @@ int make_layout(const dpa_shape_t& s, Layout& L) {
   L.u_dz = take((size_t)L.n_slots * L.chunk_rows * L.ldz * 2);
   L.u_zr = take((size_t)L.chunk_rows * L.ldz * 2);
   L.u_dW32 = (s.flags & DPA_FLAG_NEED_DW) ? take((size_t)s.V_local * s.H * 4) : o;
+  L.u_gather = o;                       // statistics records of all vocab shards (library-side exchange)
+  if (comm_world > 1 && s.V_local < s.V) take((size_t)comm_world * L.row_stats_bytes);
   L.fused_total = o;
   return DPA_OK;
 }
@@ -660,10 +662,17 @@ struct NcclApi {
   const char* (*GetErrorString)(int) = nullptr;
 };
 NcclApi g_nccl;
-struct Comm { NcclComm comm = nullptr; int rank = 0, world = 1, device = -1; cudaStream_t stream = nullptr; };   // stream: the exchange
-// of the backward runs beside the caller's stream (fork / join with events) so that it overlaps the remaining GEMMs
+// Symmetric peer memory (dpa_peer.cuh): one cudaMalloc per rank, mapped into every peer with CUDA IPC.  (Re)allocated
+// collectively, on first use or when a larger shape arrives -- the only place the communicator synchronises the device.
+struct PeerMem {
+  char* base = nullptr; size_t bytes = 0;
+  char* peer[kPeerMax] = {};           // peer[rank] == base
+  bool failed = false; char why[160] = "";
+};
+struct Comm { NcclComm comm = nullptr; int rank = 0, world = 1, device = -1; cudaStream_t stream = nullptr; PeerMem pm; };   // stream: the
+// exchange of the backward runs beside the caller's stream (fork / join with events) so that it overlaps the remaining GEMMs
 Comm g_comm;
-constexpr int kNcclUint8 = 1, kNcclBfloat16 = 9, kNcclSum = 0;
+constexpr int kNcclUint8 = 1, kNcclFloat32 = 7, kNcclBfloat16 = 9, kNcclSum = 0;
 
 int nccl_bind() {
   if (g_nccl.lib) return DPA_OK;
@@ -682,15 +691,64 @@ int nccl_bind() {
 #define NCCL_TRY(x) do { int r_ = (x); if (r_ != 0) return fail(DPA_ERR_NCCL, "%s: %s", #x, g_nccl.GetErrorString(r_)); } while (0)
 bool comm_active(const dpa_shape_t& s) { return g_comm.comm && g_comm.world > 1 && s.V_local < s.V; }
 
-// ---------------------------------------------------------------------------------- auxiliary stream
-// The dense gradient tensors must come back fully written (zeros for rows without a contribution): 0.8 GB of memset per
-// cfg-2 step.  It runs on a library-owned side stream, forked from the caller's stream at the start of the pass and joined
-// before the first dH GEMM, so the HBM-bound fill hides behind the tensor-bound statistics GEMM (event fork / join: legal
-// inside a CUDA-graph capture).  One stream + two events per device, created on first use.  DPA_ASYNC_ZERO=0 disables.
-struct Aux { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
-Aux g_aux[16];
-std::mutex g_aux_mu;
-bool async_zero() { static const bool v = env_int("DPA_ASYNC_ZERO", 1) != 0; return v; }
+void peer_mem_release() {
+  PeerMem& pm = g_comm.pm;
+  for (int r = 0; r < kPeerMax; ++r)
+    if (pm.peer[r] && pm.peer[r] != pm.base) cudaIpcCloseMemHandle(pm.peer[r]);
+  if (pm.base) cudaFree(pm.base);
+  pm = PeerMem{};
+}
+// Collective over the communicator: make sure every rank's symmetric allocation holds `data_bytes` behind the control block.
+int ensure_peer_mem(size_t data_bytes) {
+  PeerMem& pm = g_comm.pm;
+  if (pm.failed) return fail(DPA_ERR_NCCL, "peer memory unavailable: %s", pm.why);
+  const size_t need = kPeerCtrlBytes + align_up(data_bytes, 256);
+  if (pm.base && pm.bytes >= need) return DPA_OK;
+  const int G = g_comm.world, me = g_comm.rank;
+  if (G > kPeerMax) { pm.failed = true; snprintf(pm.why, sizeof(pm.why), "world %d > %d", G, kPeerMax); return fail(DPA_ERR_NCCL, "peer memory unavailable: %s", pm.why); }
+  auto bad = [&](const char* what, cudaError_t e) {
+    pm.failed = true;
+    snprintf(pm.why, sizeof(pm.why), "%s: %s", what, cudaGetErrorString(e));
+    cudaGetLastError();
+    return fail(DPA_ERR_NCCL, "peer memory unavailable: %s", pm.why);
+  };
+  cudaError_t e = cudaDeviceSynchronize();           // nothing may still use the old allocation
+  if (e != cudaSuccess) return bad("cudaDeviceSynchronize", e);
+  peer_mem_release();
+  const size_t bytes = align_up(need + need / 4, 2u << 20);       // some headroom: shapes grow a little from batch to batch
+  if ((e = cudaMalloc(&pm.base, bytes)) != cudaSuccess) return bad("cudaMalloc(symmetric buffer)", e);
+  pm.bytes = bytes;
+  cudaStream_t st = g_comm.stream;
+  if ((e = cudaMemsetAsync(pm.base, 0, kPeerCtrlBytes, st)) != cudaSuccess) return bad("cudaMemsetAsync", e);
+  cudaIpcMemHandle_t mine;
+  if ((e = cudaIpcGetMemHandle(&mine, pm.base)) != cudaSuccess) return bad("cudaIpcGetMemHandle", e);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+  char* stage = nullptr;                              // [G + 1][64]: every rank's handle, then mine as the send buffer
+  if ((e = cudaMalloc(&stage, (size_t)(G + 1) * 64)) != cudaSuccess) return bad("cudaMalloc(stage)", e);
+  if ((e = cudaMemcpyAsync(stage + (size_t)G * 64, &mine, 64, cudaMemcpyHostToDevice, st)) != cudaSuccess) { cudaFree(stage); return bad("cudaMemcpyAsync", e); }
+  // (stream order: the control block is zeroed before this rank's handle can reach any peer)
+  int nr = g_nccl.AllGather(stage + (size_t)G * 64, stage, 64, kNcclUint8, g_comm.comm, st);
+  if (nr != 0) { cudaFree(stage); pm.failed = true; snprintf(pm.why, sizeof(pm.why), "ncclAllGather(handles): %s", g_nccl.GetErrorString(nr)); return fail(DPA_ERR_NCCL, "%s", pm.why); }
+  std::vector<cudaIpcMemHandle_t> all(G);
+  e = cudaMemcpyAsync(all.data(), stage, (size_t)G * 64, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(stage);
+  if (e != cudaSuccess) return bad("handle read-back", e);
+  for (int r = 0; r < G; ++r) {
+    if (r == me) { pm.peer[r] = pm.base; continue; }
+    void* ptr = nullptr;
+    if ((e = cudaIpcOpenMemHandle(&ptr, all[r], cudaIpcMemLazyEnablePeerAccess)) != cudaSuccess) return bad("cudaIpcOpenMemHandle", e);
+    pm.peer[r] = static_cast<char*>(ptr);
+  }
+  if (getenv("DPA_VERBOSE")) fprintf(stderr, "dpa: rank %d/%d: symmetric peer buffer of %.1f MB mapped\n", me, G, bytes / 1e6);
+  return DPA_OK;
+}
+PeerView peer_view() {
+  PeerView v{};
+  for (int r = 0; r < kPeerMax; ++r) v.base[r] = g_comm.pm.peer[r];
+  v.rank = g_comm.rank; v.world = g_comm.world;
+  return v;
+}
 
 // ---------------------------------------------------------------------------------- one call's GEMM plan
 // Tensor maps over the packed operands of this call and one method per GEMM class.  `scratch` offsets differ between
@@ -709,7 +767,6 @@ struct Plan {
   // fp32 inputs: the maps above cover the high-order bf16 parts (in scratch), these the mid ([0]) and low-order ([1]) parts
   // vocab-parallel with the library's communicator: after chunk ch's dH GEMM its packed rows are all-reduced on the
   // communicator's own stream while this stream goes on with dW and the next chunk (joined before the final scatter)
-  int n_tot_host = 0;
   const Layout::Split* split = nullptr;
   size_t dz_part = 0;                      // elements between the hi / mid / lo copies of dz
   CUtensorMap tmHpS[2], tmHfS[2], tmW128S[2], tmW64S[2], tmWr64S[2], tmDzKS[2], tmWmnS[2], tmDzMNS[2], tmHpMNS[2];
@@ -920,7 +977,6 @@ struct Plan {
   }
   // dH = dz W (rows scattered to their [s,t] positions) and, if lm_head is trainable, dW += dz^T H for chunk ch
   int grad_gemms(int ch) {
-    { int rc = join_zero(); if (rc) return rc; }
     if (split) {              // fp32 inputs: split-bf16 dz and operands, fp32 gradients; dW accumulates in place
       {
         using Epi = EpiStoreRows<kBnSplit, float>;
@@ -946,8 +1002,10 @@ struct Plan {
       // 512-wide tiles: a super-block of 9 row units x all column tiles is one wave of the 74 CTA pairs
       GemmWork w{meta, KIND_DH, ch, L.chunk_rows, 0, s.H, s.V_local, 1, super_m().dh ? super_m().dh : (wide ? 9 : 0), hint_dh().a, hint_dh().b,
                  slot_of(ch) * L.chunk_rows};
+      if (dH_packed) { int rc = before_dH_chunk(ch); if (rc) return rc; }
       P ep{meta, at<int>(a->state, L.src_pair), at<int>(a->state, L.src_ref),
-           static_cast<__nv_bfloat16*>(a->dH_pair), static_cast<__nv_bfloat16*>(a->dH_ref), s.H, dH_packed};
+           static_cast<__nv_bfloat16*>(a->dH_pair), static_cast<__nv_bfloat16*>(a->dH_ref), s.H,
+           dH_packed ? reinterpret_cast<__nv_bfloat16*>(g_comm.pm.base + peer_buf_off(ch)) : nullptr, ch * L.chunk_rows};
       {
         ProfScope ps(PK_DH, 1, st);
         int rc = launch_grad<EpiStoreRowsBf16, KMAJOR, MNMAJOR>(st, d, tmDzK, tmWmn, w, ep, "dH");
@@ -966,18 +1024,43 @@ struct Plan {
     }
     return DPA_OK;
   }
+  // ---- vocab-parallel with the library's communicator: this rank's dH partial sums of chunk ch (packed rows, written by the
+  //      dH GEMM into peer-memory buffer ch & 1) are all-reduced in place over NVLink and scattered, on the communicator's
+  //      stream, while this stream goes on with dW and the next chunk.  Row ranges come from DpaMeta: no host count.
+  size_t peer_buf_off(int ch) const { return kPeerCtrlBytes + (size_t)(ch & 1) * L.chunk_rows * s.H * 2; }
+  cudaEvent_t buf_free[2] = {nullptr, nullptr};      // recorded on the communicator's stream after chunk's scatter
+  int before_dH_chunk(int ch) {                      // buffer ch & 1 must have been scattered (chunk ch - 2) before it is rewritten
+    cudaEvent_t& e = buf_free[ch & 1];
+    if (!e) return DPA_OK;
+    CUDA_TRY(cudaStreamWaitEvent(st, e, 0));
+    CUDA_TRY(cudaEventDestroy(e));
+    e = nullptr;
+    return DPA_OK;
+  }
   int exchange_dH_chunk(int ch) {
-    const size_t r0 = (size_t)ch * L.chunk_rows, r1 = std::min<size_t>(r0 + L.chunk_rows, (size_t)n_tot_host);
-    if (r1 <= r0) return DPA_OK;
     cudaEvent_t e;
     CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CUDA_TRY(cudaEventRecord(e, st));
     CUDA_TRY(cudaStreamWaitEvent(g_comm.stream, e, 0));
     CUDA_TRY(cudaEventDestroy(e));              // released once it has completed
-    NCCL_TRY(g_nccl.AllReduce(dH_packed + r0 * s.H, dH_packed + r0 * s.H, (r1 - r0) * s.H, kNcclBfloat16, kNcclSum, g_comm.comm, g_comm.stream));
+    cudaStream_t cs = g_comm.stream;
+    const PeerView v = peer_view();
+    peer_barrier_kernel<<<1, 32, 0, cs>>>(v, 2 * (ch & 3));
+    PeerReduceArgs ra{v, meta, ch, L.chunk_rows, s.H, peer_buf_off(ch)};
+    peer_reduce_rows_kernel<<<d->sms * 2, 256, 0, cs>>>(ra);
+    peer_barrier_kernel<<<1, 32, 0, cs>>>(v, 2 * (ch & 3) + 1);
+    ScatterChunkArgs sc{meta, ch, L.chunk_rows, at<int>(a->state, L.src_pair), at<int>(a->state, L.src_ref),
+                        reinterpret_cast<const __nv_bfloat16*>(g_comm.pm.base + peer_buf_off(ch)),
+                        static_cast<__nv_bfloat16*>(a->dH_pair), static_cast<__nv_bfloat16*>(a->dH_ref), s.H};
+    scatter_chunk_rows_kernel<<<d->sms * 4, 256, 0, cs>>>(sc);
+    LAUNCH_CHECK("peer exchange");
+    CUDA_TRY(cudaEventCreateWithFlags(&buf_free[ch & 1], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(buf_free[ch & 1], cs));
     return DPA_OK;
   }
   int join_exchange() {                          // the caller's stream waits for everything queued on the communicator's stream
+    for (int i = 0; i < 2; ++i)
+      if (buf_free[i]) { CUDA_TRY(cudaEventDestroy(buf_free[i])); buf_free[i] = nullptr; }
     cudaEvent_t e;
     CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CUDA_TRY(cudaEventRecord(e, g_comm.stream));
@@ -985,41 +1068,23 @@ struct Plan {
     CUDA_TRY(cudaEventDestroy(e));
     return DPA_OK;
   }
-  bool zero_pending = false;
+  // collective part of enabling the library-side exchange for this call (peer memory sized for two chunk buffers)
+  int enable_peer_exchange() {
+    int rc = ensure_peer_mem((size_t)2 * L.chunk_rows * s.H * 2);
+    if (rc) return rc;
+    dH_packed = reinterpret_cast<__nv_bfloat16*>(g_comm.pm.base);     // (per-chunk buffer: see grad_gemms)
+    return DPA_OK;
+  }
+  // (Tried: the fill on a side stream, hidden behind the statistics GEMM -- the GEMM slows down by what the fill costs,
+  //  the step is bound by power / HBM energy, not by idle tensor cores.  profiles/r02a.)
   int zero_grad_outputs() {
     ProfScope ps(PK_MISC, 0, st);
     const size_t es = split ? 4 : 2;
-    cudaStream_t zs = st;
-    Aux* aux = nullptr;
-    std::unique_lock<std::mutex> lk(g_aux_mu, std::defer_lock);
-    if (async_zero()) {
-      int dev = 0; CUDA_TRY(cudaGetDevice(&dev));
-      lk.lock();
-      aux = &g_aux[dev & 15];
-      if (!aux->s) {
-        CUDA_TRY(cudaStreamCreateWithFlags(&aux->s, cudaStreamNonBlocking));
-        CUDA_TRY(cudaEventCreateWithFlags(&aux->fork, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&aux->join, cudaEventDisableTiming));
-      }
-      CUDA_TRY(cudaEventRecord(aux->fork, st));
-      CUDA_TRY(cudaStreamWaitEvent(aux->s, aux->fork, 0));
-      zs = aux->s;
-    }
-    CUDA_TRY(cudaMemsetAsync(a->dH_pair, 0, (size_t)2 * s.B * s.T * s.H * es, zs));
-    CUDA_TRY(cudaMemsetAsync(a->dH_ref, 0, (size_t)s.B_ref * s.T_ref * s.H * es, zs));
-    if (aux) { CUDA_TRY(cudaEventRecord(aux->join, aux->s)); zero_pending = true; }
+    CUDA_TRY(cudaMemsetAsync(a->dH_pair, 0, (size_t)2 * s.B * s.T * s.H * es, st));
+    CUDA_TRY(cudaMemsetAsync(a->dH_ref, 0, (size_t)s.B_ref * s.T_ref * s.H * es, st));
     return DPA_OK;      // (the dW accumulator needs no memset: the first chunk's epilogue overwrites it)
   }
-  int join_zero() {       // the caller's stream waits for the fill: before the first kernel that writes dH rows
-    if (!zero_pending) return DPA_OK;
-    zero_pending = false;
-    int dev = 0; CUDA_TRY(cudaGetDevice(&dev));
-    std::lock_guard<std::mutex> lk(g_aux_mu);
-    CUDA_TRY(cudaStreamWaitEvent(st, g_aux[dev & 15].join, 0));
-    return DPA_OK;
-  }
   int finish_dW() {
-    { int rc = join_zero(); if (rc) return rc; }
     if (!(s.flags & DPA_FLAG_NEED_DW) || !a->dW) return DPA_OK;
     ProfScope ps(PK_MISC, 1, st);      // the last chunk with rows wrote dW; only the no-rows-at-all case is left
     zero_if_no_rows_kernel<<<d->sms * 2, 256, 0, st>>>(meta, a->dW, (size_t)s.V_local * s.H * (split ? 4 : 2));
@@ -1075,7 +1140,23 @@ int forward_fused_impl(const dpa_args_t* a, cudaStream_t st) {
   if (!a->losses || !a->status) return fail(DPA_ERR_ARG, "losses/status is NULL");
   const bool loss_only = (s.flags & DPA_FLAG_LOSS_ONLY) != 0;      // evaluation: same chunked pass, no gradient GEMMs
   if (!loss_only && (rc = check_grad_outputs(a))) return rc;
+  // Vocab-parallel lm_head with the library's communicator: every rank runs this pass on the same rows and its own lm_head
+  // rows; the per-row statistics of the shards are exchanged (all-gather of the 36 B/row record + max-rescale merge) once for
+  // the pair segment and once per row chunk, the dH partial sums through peer memory (dpa_peer.cuh), dW stays sharded.
+  const bool vp = comm_active(s);
+  if (s.V_local < s.V && !vp) return fail(DPA_ERR_ARG, "DPA_FLAG_FUSED_GRAD with a vocab-sharded lm_head needs the library's communicator (dpa_comm_init)");
+  if (vp && (s.flags & DPA_FLAG_FUSED_NORM)) return fail(DPA_ERR_ARG, "DPA_FLAG_FUSED_NORM is not available with a vocab-sharded lm_head");
+  if (vp && a->ref_logits) return fail(DPA_ERR_ARG, "ref_logits is not available with a vocab-sharded lm_head");
   Plan p(a, L, d, st);
+  if (vp && !loss_only && (rc = p.enable_peer_exchange())) return rc;
+  auto exchange_stats = [&](RowRange rr, int finish) -> int {      // all shards' records -> every rank -> merge (+ per-row results)
+    char* g = at<char>(a->scratch, L.u_gather);
+    const size_t rec = L.row_stats_bytes;
+    NCCL_TRY(g_nccl.AllGather(at<char>(a->state, L.stats_pair), g, rec, kNcclUint8, g_comm.comm, st));
+    const int G = g_comm.world;
+    return run_merge(a, L, d, reinterpret_cast<const float4*>(g), reinterpret_cast<const float4*>(g + (L.stats_ref - L.stats_pair)), nullptr,
+                     G, G, rec / 16, rec / 16, rec / 4, st, rr, finish);
+  };
   if ((rc = p.init(L.u_Hp, L.u_Hf, L.u_part_pair, L.u_part_ref, L.u_part_u, true, at<__nv_bfloat16>(a->scratch, L.u_dz),
                    at<__nv_bfloat16>(a->scratch, L.u_zr),
                    ((s.flags & DPA_FLAG_NEED_DW) && !loss_only) ? at<float>(a->scratch, L.u_dW32) : nullptr, nullptr, L.n_slots))) return rc;
@@ -1087,7 +1168,8 @@ int forward_fused_impl(const dpa_args_t* a, cudaStream_t st) {
   // ---- alignment half: statistics of every pair row -> P, N -> sigma, alignment loss -> row coefficients
   // (the statistics GEMM keeps the logits of the pair rows of every slot; nothing else touches a slot until its chunk's turn)
   if ((rc = p.fwd_pair<true>(loss_only ? 0 : L.n_slots * L.chunk_rows))) return rc;
-  if ((rc = p.merge(RowRange{SEG_PAIR, 0, 0}, true, MERGE_FINISH))) return rc;
+  if ((rc = p.merge(RowRange{SEG_PAIR, 0, 0}, true, vp ? MERGE_ONLY : MERGE_FINISH))) return rc;
+  if (vp && (rc = exchange_stats(RowRange{SEG_PAIR, 0, 0}, MERGE_FINISH))) return rc;
   if ((rc = run_losses(a, L, st, LOSS_ALIGN, 0))) return rc;
   if ((rc = p.coef(nullptr /* d_loss = 1 */))) return rc;
 
@@ -1108,10 +1190,12 @@ int forward_fused_impl(const dpa_args_t* a, cudaStream_t st) {
     }
     if ((rc = p.stash_ref(ch))) return rc;
     const RowRange rr{SEG_REF_CHUNK, ch, L.chunk_rows};
-    if ((rc = p.merge(rr, false, MERGE_FINISH_KL_LATER))) return rc;
+    if ((rc = p.merge(rr, false, vp ? MERGE_ONLY : MERGE_FINISH_KL_LATER))) return rc;
+    if (vp && (rc = exchange_stats(rr, MERGE_FINISH_KL_LATER))) return rc;
     {
       DzElemArgs e{p.meta, ch, L.chunk_rows, p.dz_of(ch), p.zr, L.ldz, s.V_local, at<float>(a->state, L.lse_ref_p), at<float>(a->state, L.lse_ref_r),
-                   at<float>(a->state, L.coef_ref), at<int>(a->state, L.act_ref), at<float>(a->state, L.kl_row)};
+                   at<float>(a->state, L.coef_ref), at<int>(a->state, L.act_ref), at<float>(a->state, L.kl_row),
+                   (!vp || g_comm.rank == 0) ? 1 : 0};
       ProfScope ps(PK_DZ_ELEM, 1, st);
       dz_kl_elem_kernel<<<d->sms * 8, 256, 0, st>>>(e);
       LAUNCH_CHECK("dz_kl_elem");
@@ -1119,7 +1203,12 @@ int forward_fused_impl(const dpa_args_t* a, cudaStream_t st) {
     if (!loss_only && (rc = p.grad_gemms(ch))) return rc;
   }
   if ((rc = run_losses(a, L, st, LOSS_TOTAL, 1))) return rc;
+  if (vp) {                      // the divergence is the sum of the shards' parts: one float over the communicator
+    NCCL_TRY(g_nccl.AllReduce(a->losses + 2, a->losses + 2, 1, kNcclFloat32, kNcclSum, g_comm.comm, st));
+    if ((rc = run_losses(a, L, st, LOSS_FINAL, 2))) return rc;
+  }
   if (loss_only) return DPA_OK;
+  if (vp && (rc = p.join_exchange())) return rc;
   if ((rc = run_norm_backward(a, L, d, st))) return rc;
   return p.finish_dW();
 }
@@ -1155,35 +1244,20 @@ int run_backward(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, cuda
   if ((rc = p.init(L.b_Hp, L.b_Hf, 0, 0, 0, false, at<__nv_bfloat16>(a->scratch, L.b_dz), nullptr,
                    ((s.flags & DPA_FLAG_NEED_DW) && !sp) ? at<float>(a->scratch, L.b_dW32) : nullptr, sp))) return rc;
   // Vocab-parallel with the library's own communicator: the dH partial sums of this rank's vocabulary shard stay packed
-  // (active rows only -- a quarter of the dense tensors at 10 % phrase density), are all-reduced chunk by chunk and
-  // scattered at the end.  The all-reduce count is a host value, so this (optional) mode reads the active row count
-  // back once; the forward that produced it has long finished by the time the backward is called.
+  // (active rows only -- a quarter of the dense tensors at 10 % phrase density), are all-reduced chunk by chunk through
+  // peer memory (dpa_peer.cuh; row counts read from DpaMeta on the device, nothing is read back) and scattered.
   const bool vp = comm_active(s);
-  int n_tot_host = 0;
-  if (vp) {
-    p.dH_packed = at<__nv_bfloat16>(a->scratch, L.b_dHp);
-    CUDA_TRY(cudaMemcpyAsync(&n_tot_host, &p.meta->n_tot, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    p.n_tot_host = n_tot_host;
-  }
+  if (vp && (rc = p.enable_peer_exchange())) return rc;
   if ((rc = p.coef(a->d_loss))) return rc;
   if ((rc = run_gather(a, L, d, a->scratch, L.b_Hp, L.b_Hf, st))) return rc;
   if (sp && (rc = run_split_weights(a, L, d, *sp, st))) return rc;
   if ((rc = p.zero_grad_outputs())) return rc;
   for (int ch = 0; ch < L.n_chunks; ++ch) {
-    if (vp && (long long)ch * L.chunk_rows >= n_tot_host) break;
     if ((long long)ch * L.chunk_rows < L.cap_pair && (rc = p.dz_pair<ROUND>(ch))) return rc;
     if ((rc = p.dz_ref<ROUND>(ch))) return rc;
     if ((rc = p.grad_gemms(ch))) return rc;       // (vp: the chunk's dH rows go to the exchange stream right after the dH GEMM)
   }
-  if (vp) {
-    if ((rc = p.join_exchange())) return rc;
-    ScatterArgs sc{p.meta, at<int>(a->state, L.src_pair), at<int>(a->state, L.src_ref), p.dH_packed,
-                   static_cast<__nv_bfloat16*>(a->dH_pair), static_cast<__nv_bfloat16*>(a->dH_ref), s.H};
-    ProfScope ps(PK_MISC, 1, st);
-    scatter_rows_kernel<<<d->sms * 8, 256, 0, st>>>(sc);
-    LAUNCH_CHECK("scatter_rows");
-  }
+  if (vp && (rc = p.join_exchange())) return rc;
   if ((rc = run_norm_backward(a, L, d, st))) return rc;
   return p.finish_dW();
 }
@@ -1248,7 +1322,6 @@ int dpa_forward(const dpa_args_t* a, void* stream) {
   Layout L; DeviceInfo* d = nullptr;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (a && (a->shape.flags & DPA_FLAG_FUSED_GRAD)) {
-    if (comm_active(a->shape)) return fail(DPA_ERR_ARG, "DPA_FLAG_FUSED_GRAD is not available with a vocab-sharded lm_head");
     return forward_fused_impl(a, st);
   }
   const bool exchange = a && comm_active(a->shape);
@@ -1308,7 +1381,9 @@ int dpa_comm_init(int rank, int world, const void* unique_id128) {
 }
 
 int dpa_comm_destroy(void) {
-  if (g_comm.stream) { cudaStreamSynchronize(g_comm.stream); cudaStreamDestroy(g_comm.stream); }
+  if (g_comm.stream) { cudaStreamSynchronize(g_comm.stream); }
+  if (g_comm.comm) { cudaDeviceSynchronize(); peer_mem_release(); }
+  if (g_comm.stream) cudaStreamDestroy(g_comm.stream);
   if (g_comm.comm) NCCL_TRY(g_nccl.CommDestroy(g_comm.comm));
   g_comm = Comm{};
   g_layout_comm_world = 1;

@@ -710,15 +710,16 @@ template <class OutT> struct StoreRowsParams {
   const DpaMeta* meta;
   const int* src_pair; const int* src_ref;       // packed row -> flat (sequence*T + t) row of the dense tensors
   OutT* dH_pair; OutT* dH_ref; int H;
-  OutT* packed;                                  // non-null: keep the rows packed ([n_tot][H]; vocab-parallel: the partial
-};                                               // sums are all-reduced in this compact form and scattered afterwards)
+  OutT* packed;                                  // non-null: keep the rows packed (vocab-parallel: the partial sums of the
+  int packed_row0;                               // chunk, first packed row packed_row0, are all-reduced in this compact form)
+};
 template <int BN, class OutT = __nv_bfloat16>      // OutT = float: the fp32 path (split-bf16 operands)
 struct EpiStoreRows {
   using Params = StoreRowsParams<OutT>;            // (independent of the tile width: the 256- and 512-column kernels share it)
   struct State { OutT* out; };
   __device__ static void unit_begin(const Params& p, State& s, int erow, int) {
     const int p0 = p.meta->p0;
-    if (p.packed) { s.out = p.packed + (size_t)erow * p.H; return; }
+    if (p.packed) { s.out = p.packed + (size_t)(erow - p.packed_row0) * p.H; return; }
     s.out = nullptr;
     if (erow < p0) { if (erow < p.meta->n_pair) s.out = p.dH_pair + (size_t)p.src_pair[erow] * p.H; }
     else { const int j = erow - p0; if (j < p.meta->n_ref) s.out = p.dH_ref + (size_t)p.src_ref[j] * p.H; }

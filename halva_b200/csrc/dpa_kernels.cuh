@@ -335,27 +335,6 @@ __global__ void split_f32_kernel(const float* __restrict__ in, __nv_bfloat16* __
   }
 }
 
-// ---- vocab-parallel backward: scatter the all-reduced packed dH rows to their [s,t] positions (one warp per row)
-struct ScatterArgs {
-  const DpaMeta* meta;
-  const int* src_pair; const int* src_ref;
-  const __nv_bfloat16* packed; __nv_bfloat16* dH_pair; __nv_bfloat16* dH_ref; int H;
-};
-__global__ void scatter_rows_kernel(ScatterArgs a) {
-  const int p0 = a.meta->p0, n_pair = a.meta->n_pair, n_ref = a.meta->n_ref;
-  const int warps = (gridDim.x * blockDim.x) >> 5;
-  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const int vec = a.H / 8;
-  for (int q = wid; q < n_pair + n_ref; q += warps) {
-    const bool is_pair = q < n_pair;
-    const int r = is_pair ? q : p0 + (q - n_pair);
-    const int s = is_pair ? a.src_pair[q] : a.src_ref[q - n_pair];
-    const uint4* src = reinterpret_cast<const uint4*>(a.packed + (size_t)r * a.H);
-    uint4* dst = reinterpret_cast<uint4*>((is_pair ? a.dH_pair : a.dH_ref) + (size_t)s * a.H);
-    for (int i = lane; i < vec; i += 32) dst[i] = src[i];
-  }
-}
-
 // ---- backward of the folded final RMSNorm, in place over the dH rows of the active policy rows:
 //      dn = bf16(dy * w), dx = r dn - x r^3 mean(dn x), d_norm_w += dy * bf16(x r)   (autograd of modelling_llama.py:64-69)
 struct NormBwdArgs {
@@ -463,7 +442,7 @@ __global__ void finish_rows_kernel(FinishArgs a) {
 // ---- P[b,k], N[b,k] and the loss assembly in ONE launch: one block per sequence computes its row of P / N (one warp per
 //      phrase column round-robin, fixed summation order); the last block to finish (ticket in DpaMeta) assembles
 //      align = mean log(1+exp(N-P)), sigma for the backward and / or div = sum(kl)/B_ref and the total.
-enum : int { LOSS_ALIGN = 1, LOSS_TOTAL = 2 };
+enum : int { LOSS_ALIGN = 1, LOSS_TOTAL = 2, LOSS_FINAL = 4 };
 struct LossArgs {
   DpaMeta* meta;
   const int* src_pair; const int* col_pair; const float* logp_pair;
@@ -553,6 +532,8 @@ __global__ void __launch_bounds__(256) loss_kernel(LossArgs a) {
       a.losses[0] = align + a.alpha * div; a.losses[2] = div; a.losses[3] = 0.f;
     }
   }
+  // vocab-parallel: losses[2] held this shard's part of the divergence and has just been summed over the shards
+  if ((a.phases & LOSS_FINAL) && threadIdx.x == 0) a.losses[0] = a.losses[1] + a.alpha * a.losses[2];
 }
 
 // ---- backward row coefficients (incl. the upstream gradient): dz = coef (onehot - p) / coef (p - q)
@@ -594,7 +575,8 @@ struct DzElemArgs {
   __nv_bfloat16* dz; const __nv_bfloat16* zr; int ldz, v_local;
   const float* lse_p; const float* lse_r; const float* coef; const int* act;   // indexed by reference row j
   float* kl_row;                                                               // in: LSE_r - LSE_p, out: KL of the row
-};
+  int sub_dlse;     // vocab-parallel: the row's KL is the SUM over the shards of sum_v q (z_r - z_p) minus (LSE_r - LSE_p) once --
+};                  // only one shard (rank 0) subtracts it; 1 without vocabulary sharding
 __device__ __forceinline__ uint32_t dz_pack2(uint32_t zp, uint32_t zr, float c, float nlp, float nlr, float& t) {
   const float2 p = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&zp));
   const float2 r = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&zr));
@@ -638,7 +620,7 @@ __global__ void __launch_bounds__(256) dz_kl_elem_kernel(DzElemArgs a) {
       }
     }
     const float tot = block_sum(t, sh);
-    if (threadIdx.x == 0) a.kl_row[j] = tot - a.kl_row[j];                 // sum_v q (z_r - z_p) - (LSE_r - LSE_p)
+    if (threadIdx.x == 0) a.kl_row[j] = a.sub_dlse ? tot - a.kl_row[j] : tot;   // sum_v q (z_r - z_p) - (LSE_r - LSE_p)
   }
 }
 

@@ -144,7 +144,9 @@ class _Call:
     def forward(self, vocab_group=None):
         with torch.cuda.device(self.state.device):
             if self.fused:
-                # loss and (d_loss = 1) gradients in one pass; backward() only scales
+                # loss and (d_loss = 1) gradients in one pass; backward() only scales.  With a vocab_group this is the
+                # library-side exchange (statistics all-gather per segment / chunk, dH through peer memory) inside the one call
+                self.lib_comm = vocab_group is not None
                 self.grads = None if self.loss_only else self._alloc_grads()
                 scratch = self._with_scratch(self.ws.fused_bytes)
                 _lib.check(self.lib.dpa_forward(C.byref(self.args), self._stream()), "dpa_forward[fused]")
@@ -283,7 +285,8 @@ def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.
                                    turned into dLogits in place (executed GEMMs = the algorithmic count: 4 per such row
                                    instead of 6, 3 instead of 4 per pair row) -- and
                                    backward only scales by d_loss;  "auto" = "fused" when round_logits is on, a gradient
-                                   is needed and there is no vocab_group, else "recompute".
+                                   is needed and there is no vocab_group (or the library's own communicator spans it:
+                                   halva_b200.dist.init_library_comm), else "recompute".
     Ill-formed phrase ids (K_pos != K_neg, K == 0, id > 255) or labels make the losses AND every gradient NaN and set
     bits in `read_status(loss)["status"]` / `loss.dpa_status`; the reference raises / returns NaN there (SURVEY.md
     section 3.2) -- a truncated batch can never reach the optimiser as finite-but-wrong gradients.
@@ -332,9 +335,14 @@ def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.
         # fp32 model (BASELINE configs[0]): nn.Linear emits fp32 logits, so there is no bf16 rounding point to reproduce and
         # no bf16 logits to keep -- statistics forward + recompute backward on split-bf16 operands, fp32 dLogits (hi + lo)
         round_logits, backward = False, "recompute"
-    if backward == "fused" and (not round_logits or vocab_group is not None):
-        raise ValueError("backward='fused' needs round_logits=True and no vocab_group")
-    fused = backward == "fused" or (backward == "auto" and round_logits and vocab_group is None)
+    lib_vp = False
+    if vocab_group is not None:
+        from .dist import library_comm_matches
+        lib_vp = _lib.load().dpa_comm_world() > 1 and library_comm_matches(vocab_group)
+    if backward == "fused" and (not round_logits or (vocab_group is not None and not lib_vp)):
+        raise ValueError("backward='fused' needs round_logits=True and, with a vocab_group, the library's own communicator over "
+                         "that group (halva_b200.dist.init_library_comm)")
+    fused = backward == "fused" or (backward == "auto" and round_logits and (vocab_group is None or lib_vp))
     loss, align, div, status = DPALossFn.apply(h_pair, h_ref_pol, W, norm_weight, labels_pair, signs_pair, labels_ref, h_ref_frozen,
                                                W_ref, float(alpha), bool(round_logits), bool(need_dW), bool(dense), int(chunk_rows),
                                                vocab_group, int(v_offset), int(vocab_size), fused, norm_weight_ref, float(norm_eps),

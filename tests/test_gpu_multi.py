@@ -64,14 +64,34 @@ def _worker(rank, world, port, out):
         assert part32[2].dtype == torch.float32
         assert abs(part32[0].item() - full32[0].item()) <= 2e-6 * abs(full32[0].item()), (part32[0].item(), full32[0].item())
         assert _rel(part32[2], full32[2]) <= 1e-5 and _rel(part32[3], full32[3]) <= 1e-5 and _rel(part32[4], full32[4][v0:v1]) <= 1e-5
-        # the same with the library's own NCCL communicator: both exchange steps inside the two C calls
+        # the same with the library's own communicator: statistics all-gathered inside the C calls, dH partial sums reduced
+        # through peer memory by the library's own kernels (row counts from device memory, no host read-back)
         from halva_b200 import _lib
         from halva_b200.dist import destroy_library_comm, init_library_comm
         assert init_library_comm(dist.group.WORLD) == world and _lib.load().dpa_comm_world() == world
-        own = run(t["W"][v0:v1].contiguous(), t["W_ref"][v0:v1].contiguous(), vocab_group=dist.group.WORLD, v_offset=v0, vocab_size=shape.V)
-        destroy_library_comm()
+        shard = lambda: (t["W"][v0:v1].contiguous(), t["W_ref"][v0:v1].contiguous())
+        vkw = dict(vocab_group=dist.group.WORLD, v_offset=v0, vocab_size=shape.V)
+        own = run(*shard(), backward="recompute", **vkw)
         assert own[0].item() == part[0].item() and torch.equal(own[4], part[4])
         assert _rel(own[2], part[2]) <= 1e-3 and _rel(own[3], part[3]) <= 1e-3
+        # fused-gradient forward under vocab parallelism (the default once the library owns the communicator): one exchange of
+        # the pair statistics, one per row chunk of the reference-sample rows, dH through peer memory, dW sharded
+        full_f = run(t["W"], t["W_ref"])
+        for kw in (dict(), dict(chunk_rows=256), dict(chunk_rows=512, dense=True)):       # several chunks: both peer buffers cycle
+            fz = run(*shard(), **vkw, **kw)
+            assert abs(fz[0].item() - full_f[0].item()) <= 1e-5 * abs(full_f[0].item()), (kw, fz[0].item(), full_f[0].item())
+            assert abs(fz[1].item() - full_f[1].item()) <= 1e-4 * abs(full_f[1].item()) + 1e-7
+            assert _rel(fz[2], full_f[2]) <= 5e-3 and _rel(fz[3], full_f[3]) <= 5e-3, kw
+            assert _rel(fz[4], full_f[4][v0:v1]) <= 2e-3, kw
+            assert torch.equal(fz[2] == 0, full_f[2] == 0)                                # the same rows carry a gradient
+        other = [torch.empty_like(fz[2]) for _ in range(world)]
+        dist.all_gather(other, fz[2].contiguous())
+        assert all(torch.equal(o, other[0]) for o in other)                               # every rank holds bit-identical dH
+        with torch.no_grad():                                                             # evaluation under vocab parallelism
+            le = dpa_loss(t["h_pair"], t["labels_pair"], t["signs_pair"], t["h_ref_pol"], t["labels_ref"], shard()[0],
+                          h_ref_frozen=t["h_ref_frz"], W_ref=shard()[1], alpha=t["alpha"], **vkw)[0]
+        assert abs(le.item() - full_f[0].item()) <= 1e-5 * abs(full_f[0].item())
+        destroy_library_comm()
         # ---- data parallel: pairs split over ranks, lm_head gradient averaged
         B = shape.B
         mine = list(dp_shard(B, world, rank))
