@@ -27,6 +27,12 @@ def vocab_shard_bounds(vocab: int, world: int, rank: int, multiple: int = 8) -> 
     return min(lo, vocab), min(hi, vocab)
 
 
+def peer_slice(rows: int, rank: int, world: int) -> Tuple[int, int]:
+    """[r0, r1) of the `rows` packed dH rows of a chunk that `rank` sums in the library's peer-memory all-reduce
+    (csrc/dpa_peer.cuh: peer_reduce_rows_kernel uses the same split): contiguous, every row owned by exactly one rank."""
+    return rows * rank // world, rows * (rank + 1) // world
+
+
 def dp_shard(n_samples: int, world: int, rank: int) -> range:
     """Sample pairs (and their reference samples) owned by `rank`: contiguous, as even as possible."""
     lo = (n_samples * rank) // world

@@ -10,7 +10,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from dpa_testutil import load_golden
-from halva_b200.dist import (average_gradients, dp_shard, merge_row_stats, row_stats_record_floats, vocab_shard_bounds)
+from halva_b200.dist import (average_gradients, dp_shard, library_comm_matches, merge_row_stats, peer_slice, row_stats_record_floats,
+                             shard_offsets, vocab_shard_bounds)
 from oracle import dpa_oracle
 
 IGNORE = -100
@@ -31,6 +32,16 @@ def test_dp_shard_partitions():
     for n, G in ((16, 8), (5, 2), (3, 4)):
         got = [i for r in range(G) for i in dp_shard(n, G, r)]
         assert got == list(range(n))
+
+
+def test_peer_slices_partition_the_rows():
+    """Rows a rank reduces in the peer-memory all-reduce of the packed dH rows (csrc/dpa_peer.cuh): every row exactly once."""
+    for rows in (0, 1, 7, 256, 24832, 32768):
+        for G in (2, 3, 4, 8):
+            cuts = [peer_slice(rows, r, G) for r in range(G)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == rows
+            assert all(b == c for (_, b), (c, _) in zip(cuts, cuts[1:]))
+            assert max(b - a for a, b in cuts) - min(b - a for a, b in cuts) <= 1
 
 
 def _free_port():
@@ -99,6 +110,28 @@ def _worker(rank, world, port, out):
         kl = (ref[:, 4] / ref[:, 3] - ((ref[:, 2] - ref[:, 0]) + torch.log(ref[:, 3] / ref[:, 1]))).numpy()
         act = full["active_ref"].reshape(-1)
         assert np.allclose(kl * act, full["kl_rows"].reshape(-1), rtol=2e-3, atol=2e-6)
+        # ---- fused-gradient forward under vocab parallelism: with the GLOBAL log-sum-exps known after the exchange, every shard
+        #      sums q (z_r - z_p) over its own columns; the row's KL is the sum of the shards' parts minus (LSE_r - LSE_p) once
+        #      (rank 0 subtracts it), and the divergence one scalar all-reduce of the shards' sums
+        f64 = lambda k: np.asarray(g[k], np.float64)
+        zp = f64("h_ref_pol")[:, :-1].reshape(-1, f64("W").shape[1]) @ f64("W")[v0:v1].T
+        zr = f64("h_ref_frz")[:, :-1].reshape(-1, f64("W").shape[1]) @ f64("W_ref")[v0:v1].T
+        lse_p = (ref[:, 0] + torch.log(ref[:, 1])).double().numpy()
+        lse_r = (ref[:, 2] + torch.log(ref[:, 3])).double().numpy()
+        t_local = (np.exp(zr - lse_r[:, None]) * (zr - zp)).sum(-1)
+        part = torch.from_numpy((t_local - (lse_r - lse_p if rank == 0 else 0.0)) * act)
+        tot = part.clone()
+        dist.all_reduce(tot)
+        assert np.allclose(tot.numpy(), full["kl_rows"].reshape(-1), rtol=2e-3, atol=2e-6)
+        div = torch.tensor([part.sum().item()], dtype=torch.float64)
+        dist.all_reduce(div)
+        assert abs(div.item() / g["h_ref_pol"].shape[0] - full["div"]) <= 2e-3 * abs(full["div"]) + 1e-7
+        # ---- shard offsets from the shard sizes of all ranks (uneven shards allowed), and the communicator / group match
+        sizes = [5, 11][:world]
+        off, total = shard_offsets(sizes[rank], None, "cpu")
+        assert (off, total) == (sum(sizes[:rank]), sum(sizes))
+        assert shard_offsets(sizes[rank], None, "cpu") == (off, total)       # cached: no second collective needed
+        assert library_comm_matches(None) is False                           # no library communicator was created here
         out[rank] = 1
     finally:
         dist.destroy_process_group()

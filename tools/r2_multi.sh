@@ -3,7 +3,7 @@
 N=${1:-2}
 mkdir -p gpurun_out
 export DPA_VERBOSE=1
-echo "== multi-GPU tests"; timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -x -q 2>&1 | tail -25 | tee gpurun_out/r2_pytest_multi_$N.log
+echo "== multi-GPU tests"; timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -x -q > gpurun_out/r2_pytest_multi_$N.log 2>&1; grep -v "co-resident" gpurun_out/r2_pytest_multi_$N.log | tail -60
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533"
 echo "== bench --gpus $N"; timeout 900 $TR bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r2_bench_${N}gpu.json 2> gpurun_out/r2_bench_${N}gpu.err; tail -c 2500 gpurun_out/r2_bench_${N}gpu.json; tail -5 gpurun_out/r2_bench_${N}gpu.err
 for mode in "" "--vp-backward recompute" "--vp-torch-exchange"; do
