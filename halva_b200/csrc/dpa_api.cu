@@ -286,7 +286,8 @@ struct Layout {
   size_t b_Hp, b_Hf, b_dz, b_dW32, b_dHp, bwd_total;
   // fp32 inputs (split-bf16 operands): Hp / Hf / dz hold three parts (hi, mid, lo) one after the other, and the lm_head
   // weights are split into scratch as well (three parts each)
-  struct Split { size_t W3, Wr3; } f_split, b_split;
+  struct Split { size_t W3, Wr3; } f_split, b_split, u_split;
+  size_t u_zp32;    // fp32 inputs, fused-gradient forward: kept fp32 policy logits of the chunk (u_zr then holds fp32 too)
   bool split;
   // fused-gradient forward scratch offsets (DPA_FLAG_FUSED_GRAD)
   size_t u_Hp, u_Hf, u_part_pair, u_part_ref, u_part_u, u_dz, u_zr, u_dW32, u_gather, fused_total;
@@ -301,8 +302,8 @@ int make_layout(const dpa_shape_t& s, Layout& L) {
   if (s.v_offset < 0 || s.v_offset + s.V_local > s.V) return fail(DPA_ERR_BAD_SHAPE, "vocab shard [%d,%d) outside V=%d", s.v_offset, s.v_offset + s.V_local, s.V);
   if (s.dtype != DPA_BF16 && s.dtype != DPA_F32) return fail(DPA_ERR_DTYPE, "hidden states / weights must be bf16 or fp32");
   L.split = s.dtype == DPA_F32;
-  if (L.split && (s.flags & (DPA_FLAG_ROUND_LOGITS | DPA_FLAG_FUSED_GRAD | DPA_FLAG_FUSED_NORM)))
-    return fail(DPA_ERR_ARG, "fp32 inputs: DPA_FLAG_ROUND_LOGITS / FUSED_GRAD / FUSED_NORM describe the bf16 execution and are not available");
+  if (L.split && (s.flags & (DPA_FLAG_ROUND_LOGITS | DPA_FLAG_FUSED_NORM)))
+    return fail(DPA_ERR_ARG, "fp32 inputs: DPA_FLAG_ROUND_LOGITS / FUSED_NORM describe the bf16 execution and are not available");
   if (L.split && comm_world > 1 && s.V_local < s.V) return fail(DPA_ERR_ARG, "fp32 inputs are not available with the library-side vocab-parallel exchange");
   if (s.index_dtype != DPA_I64 && s.index_dtype != DPA_I32) return fail(DPA_ERR_DTYPE, "labels/signs must be int64 or int32");
   if ((long long)2 * s.B * s.T >= (1ll << 31) / 2 || 2 * s.B >= 32768) return fail(DPA_ERR_BAD_SHAPE, "batch too large for 32-bit row ids");
@@ -315,7 +316,8 @@ int make_layout(const dpa_shape_t& s, Layout& L) {
   L.ng_pair = ((s.V_local + kBnPair - 1) / kBnPair + kTpuPair - 1) / kTpuPair;
   L.ng_ref = ((s.V_local + kBnRef - 1) / kBnRef + kTpuRef - 1) / kTpuRef;
   L.ldz = round_up_i(s.V_local, 64);
-  L.chunk_rows = s.chunk_rows > 0 ? s.chunk_rows : kDefaultChunkRows;
+  // (fp32 inputs keep 14 B per logit of a chunk -- two fp32 logit buffers and a split-bf16 dLogits triple -- so their default chunk is smaller)
+  L.chunk_rows = s.chunk_rows > 0 ? s.chunk_rows : (L.split ? kDefaultChunkRows / 4 : kDefaultChunkRows);
   if (L.chunk_rows % kRowPad) return fail(DPA_ERR_BAD_SHAPE, "chunk_rows=%d must be a multiple of %d", L.chunk_rows, kRowPad);
   const int cap_tot = L.cap_pair + L.cap_ref;
   L.chunk_rows = std::min(L.chunk_rows, cap_tot);
@@ -370,19 +372,21 @@ int make_layout(const dpa_shape_t& s, Layout& L) {
   L.bwd_total = o;
 
   o = 0;
-  L.u_Hp = take((size_t)cap_tot * s.H * 2);
-  L.u_Hf = take((size_t)L.cap_ref * s.H * 2);
+  L.u_Hp = take(parts * cap_tot * s.H * 2);
+  L.u_Hf = take(parts * L.cap_ref * s.H * 2);
   L.u_part_pair = take((size_t)L.ng_pair * L.cap_pair * 16);
   L.u_part_ref = take((size_t)L.ng_ref * L.cap_ref * 16);
   L.u_part_u = take((size_t)L.ng_ref * L.cap_ref * 4);
   // Kept bf16 logits: chunk c < n_slots owns slot c (its pair rows' logits are written by the statistics GEMM and turned into
   // dLogits in place, never recomputed); chunks past the pair segment reuse slot 0.  One slot unless every position is
   // processed (DPA_FLAG_DENSE: the pair segment then spans several chunks and all of them are kept -- 180 GB of HBM).
-  L.n_slots = (s.flags & DPA_FLAG_DENSE) ? std::max(1, (L.cap_pair + L.chunk_rows - 1) / L.chunk_rows) : 1;
+  L.n_slots = ((s.flags & DPA_FLAG_DENSE) && !L.split) ? std::max(1, (L.cap_pair + L.chunk_rows - 1) / L.chunk_rows) : 1;
   L.n_slots = std::min(L.n_slots, L.n_chunks);
-  L.u_dz = take((size_t)L.n_slots * L.chunk_rows * L.ldz * 2);
-  L.u_zr = take((size_t)L.chunk_rows * L.ldz * 2);
-  L.u_dW32 = (s.flags & DPA_FLAG_NEED_DW) ? take((size_t)s.V_local * s.H * 4) : o;
+  L.u_dz = take(parts * L.n_slots * L.chunk_rows * L.ldz * 2);
+  L.u_zr = take((size_t)L.chunk_rows * L.ldz * (L.split ? 4 : 2));
+  L.u_zp32 = L.split ? take((size_t)L.chunk_rows * L.ldz * 4) : o;
+  L.u_dW32 = ((s.flags & DPA_FLAG_NEED_DW) && !L.split) ? take((size_t)s.V_local * s.H * 4) : o;
+  take_split(L.u_split);
   L.u_gather = o;                       // statistics records of all vocab shards (library-side exchange)
   if (comm_world > 1 && s.V_local < s.V) take((size_t)comm_world * L.row_stats_bytes);
   L.fused_total = o;
@@ -758,6 +762,7 @@ struct Plan {
   const dpa_shape_t& s;
   const DpaMeta* meta;
   __nv_bfloat16* dz = nullptr; __nv_bfloat16* zr = nullptr; float* dW32 = nullptr;
+  float* zp32 = nullptr; float* zr32 = nullptr;      // fp32 inputs, fused-gradient forward: the chunk's kept fp32 logits
   int n_slots = 1;                        // kept-logit slots behind `dz` (fused-gradient forward; 1 elsewhere)
   int slot_of(int ch) const { return ch < n_slots ? ch : 0; }
   __nv_bfloat16* dz_of(int ch) const { return dz + (size_t)slot_of(ch) * L.chunk_rows * L.ldz; }
@@ -769,7 +774,7 @@ struct Plan {
   // communicator's own stream while this stream goes on with dW and the next chunk (joined before the final scatter)
   const Layout::Split* split = nullptr;
   size_t dz_part = 0;                      // elements between the hi / mid / lo copies of dz
-  CUtensorMap tmHpS[2], tmHfS[2], tmW128S[2], tmW64S[2], tmWr64S[2], tmDzKS[2], tmWmnS[2], tmDzMNS[2], tmHpMNS[2];
+  CUtensorMap tmHpS[2], tmHfS[2], tmW128S[2], tmW64S[2], tmWr128S[2], tmWr64S[2], tmDzKS[2], tmWmnS[2], tmDzMNS[2], tmHpMNS[2];
   CUtensorMap tmW32, tmWr32, tmW32S[2], tmWr32S[2];       // 32-row boxes: each CTA's half of a 64-column dual tile (CTA pairs)
 
   Plan(const dpa_args_t* a_, const Layout& L_, const DeviceInfo* d_, cudaStream_t st_)
@@ -825,6 +830,7 @@ struct Plan {
         if ((rc = make_operand_tmap(d, &tmW128S[p], WP, KMAJOR, s.V_local, s.H, s.H, 128))) return rc;
         if ((rc = make_operand_tmap(d, &tmW64S[p], WP, KMAJOR, s.V_local, s.H, s.H, 64))) return rc;
         if ((rc = make_operand_tmap(d, &tmWr64S[p], Wr3 + (p + 1) * w_part, KMAJOR, s.V_local, s.H, s.H, 64))) return rc;
+        if ((rc = make_operand_tmap(d, &tmWr128S[p], Wr3 + (p + 1) * w_part, KMAJOR, s.V_local, s.H, s.H, 128))) return rc;
         if ((rc = make_operand_tmap(d, &tmW32S[p], WP, KMAJOR, s.V_local, s.H, s.H, 32))) return rc;
         if ((rc = make_operand_tmap(d, &tmWr32S[p], Wr3 + (p + 1) * w_part, KMAJOR, s.V_local, s.H, s.H, 32))) return rc;
         if (dz) {
@@ -888,9 +894,9 @@ struct Plan {
     ProfScope ps(PK_FWD_PAIR, 1, st);
     if constexpr (!ROUND) {
       if (split) {
-        using EpiS = EpiStatsPair<kBnSplit, false>;
+        using EpiS = EpiStatsPair<kBnSplit, false, float>;
         GemmWork ws = w; ws.tiles_per_unit = kTpuSplit;
-        typename EpiS::Params eps{ep.labels, ep.part, ep.row_cap, ep.v_local, ep.v_offset, nullptr, L.ldz, 0};
+        typename EpiS::Params eps{ep.labels, ep.part, ep.row_cap, ep.v_local, ep.v_offset, store_rows > 0 ? zp32 : nullptr, L.ldz, store_rows};
         return launch_split<KMAJOR, KMAJOR, EpiS>(tmHp, tmHpS, tmW128, tmW128S, tmW64, tmW64S, ws, eps, "fwd_pair[split]");
       }
     }
@@ -951,6 +957,17 @@ struct Plan {
     using Epi = EpiStatsStore<256>;
     float2* part2 = reinterpret_cast<float2*>(part_ref);
     const bool given = a->ref_logits != nullptr;
+    if (split) {              // fp32 inputs: the same two GEMMs on split-bf16 operands, fp32 logits kept
+      using EpiS = EpiStatsStore<kBnSplit, float>;
+      ProfScope ps(PK_STASH_REF, 2, st);
+      GemmWork wp{meta, KIND_STASH_POL, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuSplit, super_m().stats};
+      typename EpiS::Params epp{meta, part2, zp32, L.cap_ref, s.V_local, L.ldz, ch * L.chunk_rows, 0};
+      int rc = launch_split<KMAJOR, KMAJOR, EpiS>(tmHp, tmHpS, tmW128, tmW128S, tmW64, tmW64S, wp, epp, "stash_pol[split]");
+      if (rc) return rc;
+      GemmWork wf{meta, KIND_STASH_FRZ, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuSplit, super_m().stats};
+      typename EpiS::Params epf{meta, part2, zr32, L.cap_ref, s.V_local, L.ldz, ch * L.chunk_rows, 1};
+      return launch_split<KMAJOR, KMAJOR, EpiS>(tmHf, tmHfS, tmWr128, tmWr128S, tmWr64, tmWr64S, wf, epf, "stash_frz[split]");
+    }
     {
       ProfScope ps(PK_STASH_REF, given ? 1 : 2, st);
       GemmWork wp{meta, KIND_STASH_POL, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair, super_m().stats, hint_stats().a, hint_stats().b};
@@ -1135,7 +1152,9 @@ int forward_fused_impl(const dpa_args_t* a, cudaStream_t st) {
   int rc = check_common(a, L, &d);
   if (rc) return rc;
   const dpa_shape_t& s = a->shape;
-  if (!(s.flags & DPA_FLAG_ROUND_LOGITS)) return fail(DPA_ERR_ARG, "DPA_FLAG_FUSED_GRAD needs DPA_FLAG_ROUND_LOGITS (the kept logits are bf16)");
+  // the kept logits are the ones the reference's softmax sees: bf16-rounded for a bf16 model (DPA_FLAG_ROUND_LOGITS), fp32 for fp32 inputs
+  if (!L.split && !(s.flags & DPA_FLAG_ROUND_LOGITS)) return fail(DPA_ERR_ARG, "DPA_FLAG_FUSED_GRAD needs DPA_FLAG_ROUND_LOGITS (the kept logits are bf16)");
+  if (L.split && a->ref_logits) return fail(DPA_ERR_ARG, "fp32 inputs: ref_logits belongs to the bf16 execution");
   if (!a->scratch || a->scratch_bytes < L.fused_total) return fail(DPA_ERR_WORKSPACE, "fused scratch: need %zu bytes, got %zu", L.fused_total, a->scratch_bytes);
   if (!a->losses || !a->status) return fail(DPA_ERR_ARG, "losses/status is NULL");
   const bool loss_only = (s.flags & DPA_FLAG_LOSS_ONLY) != 0;      // evaluation: same chunked pass, no gradient GEMMs
@@ -1157,17 +1176,21 @@ int forward_fused_impl(const dpa_args_t* a, cudaStream_t st) {
     return run_merge(a, L, d, reinterpret_cast<const float4*>(g), reinterpret_cast<const float4*>(g + (L.stats_ref - L.stats_pair)), nullptr,
                      G, G, rec / 16, rec / 16, rec / 4, st, rr, finish);
   };
+  const Layout::Split* sp = L.split ? &L.u_split : nullptr;
   if ((rc = p.init(L.u_Hp, L.u_Hf, L.u_part_pair, L.u_part_ref, L.u_part_u, true, at<__nv_bfloat16>(a->scratch, L.u_dz),
                    at<__nv_bfloat16>(a->scratch, L.u_zr),
-                   ((s.flags & DPA_FLAG_NEED_DW) && !loss_only) ? at<float>(a->scratch, L.u_dW32) : nullptr, nullptr, L.n_slots))) return rc;
+                   ((s.flags & DPA_FLAG_NEED_DW) && !loss_only && !sp) ? at<float>(a->scratch, L.u_dW32) : nullptr, sp, L.n_slots))) return rc;
+  if (sp) { p.zp32 = at<float>(a->scratch, L.u_zp32); p.zr32 = at<float>(a->scratch, L.u_zr); }
 
   if ((rc = run_meta(a, L, d, st))) return rc;
   if ((rc = run_gather(a, L, d, a->scratch, L.u_Hp, L.u_Hf, st))) return rc;
+  if (sp && (rc = run_split_weights(a, L, d, *sp, st))) return rc;
   if (!loss_only && (rc = p.zero_grad_outputs())) return rc;
 
   // ---- alignment half: statistics of every pair row -> P, N -> sigma, alignment loss -> row coefficients
   // (the statistics GEMM keeps the logits of the pair rows of every slot; nothing else touches a slot until its chunk's turn)
-  if ((rc = p.fwd_pair<true>(loss_only ? 0 : L.n_slots * L.chunk_rows))) return rc;
+  const int keep_rows = loss_only ? 0 : L.n_slots * L.chunk_rows;
+  if ((rc = sp ? p.fwd_pair<false>(keep_rows) : p.fwd_pair<true>(keep_rows))) return rc;
   if ((rc = p.merge(RowRange{SEG_PAIR, 0, 0}, true, vp ? MERGE_ONLY : MERGE_FINISH))) return rc;
   if (vp && (rc = exchange_stats(RowRange{SEG_PAIR, 0, 0}, MERGE_FINISH))) return rc;
   if ((rc = run_losses(a, L, st, LOSS_ALIGN, 0))) return rc;
@@ -1179,6 +1202,12 @@ int forward_fused_impl(const dpa_args_t* a, cudaStream_t st) {
       // no dz of the pair rows is needed
     } else if ((long long)ch * L.chunk_rows >= L.cap_pair) {
       // past the pair segment
+    } else if (ch < L.n_slots && sp) {                            // kept fp32 logits -> split-bf16 dLogits
+      DzPairElemF32Args e{p.meta, ch * L.chunk_rows, (ch + 1) * L.chunk_rows, p.zp32, p.dz, p.dz_part, L.ldz, s.V_local, s.v_offset,
+                          at<int>(a->state, L.lab_pair), at<float>(a->state, L.lse_pair), at<float>(a->state, L.coef_pair)};
+      ProfScope ps(PK_DZ_ELEM, 1, st);
+      dz_pair_elem_f32_kernel<<<d->sms * 8, 256, 0, st>>>(e);
+      LAUNCH_CHECK("dz_pair_elem_f32");
     } else if (ch < L.n_slots) {                                  // kept logits -> dLogits in place
       DzPairElemArgs e{p.meta, ch * L.chunk_rows, (ch + 1) * L.chunk_rows, p.dz, L.ldz, s.V_local, s.v_offset, at<int>(a->state, L.lab_pair),
                        at<float>(a->state, L.lse_pair), at<float>(a->state, L.coef_pair)};
@@ -1186,13 +1215,19 @@ int forward_fused_impl(const dpa_args_t* a, cudaStream_t st) {
       dz_pair_elem_kernel<<<d->sms * 8, 256, 0, st>>>(e);
       LAUNCH_CHECK("dz_pair_elem");
     } else {                                                       // pair rows beyond the kept slots (if any): recompute
-      if ((rc = p.dz_pair<true>(ch))) return rc;
+      if ((rc = sp ? p.dz_pair<false>(ch) : p.dz_pair<true>(ch))) return rc;
     }
     if ((rc = p.stash_ref(ch))) return rc;
     const RowRange rr{SEG_REF_CHUNK, ch, L.chunk_rows};
     if ((rc = p.merge(rr, false, vp ? MERGE_ONLY : MERGE_FINISH_KL_LATER))) return rc;
     if (vp && (rc = exchange_stats(rr, MERGE_FINISH_KL_LATER))) return rc;
-    {
+    if (sp) {
+      DzElemF32Args e{p.meta, ch, L.chunk_rows, p.zp32, p.zr32, p.dz, p.dz_part, L.ldz, s.V_local, at<float>(a->state, L.lse_ref_p),
+                      at<float>(a->state, L.lse_ref_r), at<float>(a->state, L.coef_ref), at<int>(a->state, L.act_ref), at<float>(a->state, L.kl_row)};
+      ProfScope ps(PK_DZ_ELEM, 1, st);
+      dz_kl_elem_f32_kernel<<<d->sms * 8, 256, 0, st>>>(e);
+      LAUNCH_CHECK("dz_kl_elem_f32");
+    } else {
       DzElemArgs e{p.meta, ch, L.chunk_rows, p.dz_of(ch), p.zr, L.ldz, s.V_local, at<float>(a->state, L.lse_ref_p), at<float>(a->state, L.lse_ref_r),
                    at<float>(a->state, L.coef_ref), at<int>(a->state, L.act_ref), at<float>(a->state, L.kl_row),
                    (!vp || g_comm.rank == 0) ? 1 : 0};
@@ -1223,6 +1258,13 @@ int backward_scale_impl(const dpa_args_t* a, cudaStream_t st) {
   if (!a->d_loss) return DPA_OK;                                 // NULL = 1
   const dpa_shape_t& s = a->shape;
   ProfScope ps(PK_SCALE, 3, st);
+  if (L.split) {
+    scale_f32_kernel<<<d->sms * 8, 256, 0, st>>>(static_cast<float*>(a->dH_pair), (size_t)2 * s.B * s.T * s.H, a->d_loss);
+    scale_f32_kernel<<<d->sms * 8, 256, 0, st>>>(static_cast<float*>(a->dH_ref), (size_t)s.B_ref * s.T_ref * s.H, a->d_loss);
+    if (s.flags & DPA_FLAG_NEED_DW) scale_f32_kernel<<<d->sms * 8, 256, 0, st>>>(static_cast<float*>(a->dW), (size_t)s.V_local * s.H, a->d_loss);
+    LAUNCH_CHECK("scale_grads[fp32]");
+    return DPA_OK;
+  }
   scale_bf16_kernel<<<d->sms * 8, 256, 0, st>>>(static_cast<__nv_bfloat16*>(a->dH_pair), (size_t)2 * s.B * s.T * s.H, a->d_loss);
   scale_bf16_kernel<<<d->sms * 8, 256, 0, st>>>(static_cast<__nv_bfloat16*>(a->dH_ref), (size_t)s.B_ref * s.T_ref * s.H, a->d_loss);
   if (s.flags & DPA_FLAG_NEED_DW)

@@ -492,19 +492,21 @@ __device__ __forceinline__ float online_update(const float (&v)[32], int nvalid,
 }
 
 __device__ __forceinline__ void store_bf16_chunk(__nv_bfloat16* dst, const float (&d)[32]);
+__device__ __forceinline__ void store_out_chunk(__nv_bfloat16* dst, const float (&v)[32]);
+__device__ __forceinline__ void store_out_chunk(float* dst, const float (&v)[32]);
 
 // ---- forward statistics, pair rows: per (row, column group) partial {max, sum-exp, target logit}.
 //      Fused-gradient forward: rows below `store_rows` (the pair rows of row chunk 0) also keep their bf16 logits in the
 //      chunk's dz buffer, so that dz = c (onehot - p) is an elementwise pass instead of a recompute GEMM.
-template <int BN, bool ROUND>
+template <int BN, bool ROUND, class ZT = __nv_bfloat16>      // ZT = float: the fp32 path keeps fp32 logits
 struct EpiStatsPair {
   struct Params {
     const int* labels;     // packed row -> target id (global vocab id)
     float4* part;          // [n_groups][row_cap]
     int row_cap, v_local, v_offset;
-    __nv_bfloat16* z; int ldz, store_rows;     // z == nullptr: statistics only
+    ZT* z; int ldz, store_rows;                // z == nullptr: statistics only
   };
-  struct State { float m, s, zy; int yloc; int row; __nv_bfloat16* out; };
+  struct State { float m, s, zy; int yloc; int row; ZT* out; };
   __device__ static void unit_begin(const Params& p, State& s, int erow, int) {
     s.m = -INFINITY; s.s = 0.f; s.zy = 0.f; s.row = erow;
     s.yloc = p.labels[erow] - p.v_offset;
@@ -518,7 +520,7 @@ struct EpiStatsPair {
       float v[32], e[32];
       load_chunk(taddr + c * 32, v);
       round_chunk<ROUND>(v);
-      if (s.out) store_bf16_chunk(s.out + cbase, v);
+      if (s.out) store_out_chunk(s.out + cbase, v);
       online_update(v, p.v_local - cbase, s.m, s.s, e);
       if ((unsigned)(s.yloc - cbase) < 32u) {
         const int j = s.yloc - cbase;
@@ -596,15 +598,15 @@ __device__ __forceinline__ void store_split_chunk(__nv_bfloat16* hi, size_t part
 //      that dz = c (p - q) and the KL row are one elementwise pass once the chunk's log-sum-exps are known, instead of a
 //      second pair of GEMMs.  Only valid in reference-bf16 numerics (the logits ARE bf16 there,
 //      modeling_llama.py:1028), hence always rounded.
-template <int BN>
+template <int BN, class ZT = __nv_bfloat16>      // ZT = float (fp32 inputs): the kept logits are the promoted fp32 sums, unrounded
 struct EpiStatsStore {
   struct Params {
     const DpaMeta* meta;
     float2* part;            // [n_groups][row_cap][2]: {m, s} of the policy (which = 0) / frozen (which = 1) logits
-    __nv_bfloat16* z;        // [chunk_rows][ldz]
+    ZT* z;                   // [chunk_rows][ldz]
     int row_cap, v_local, ldz, chunk_row0, which;
   };
-  struct State { float m, s; int row; __nv_bfloat16* out; };
+  struct State { float m, s; int row; ZT* out; };
   __device__ static void unit_begin(const Params& p, State& s, int erow, int) {
     s.m = -INFINITY; s.s = 0.f;
     s.row = erow - p.meta->p0;                                   // reference-sample row id
@@ -617,8 +619,8 @@ struct EpiStatsStore {
       if (cbase >= p.v_local) break;
       float v[32], e[32];
       load_chunk(taddr + c * 32, v);
-      round_chunk<true>(v);
-      store_bf16_chunk(s.out + cbase, v);                        // a partial last chunk still stores 32 columns (ldz % 64 == 0)
+      round_chunk<sizeof(ZT) == 2>(v);
+      store_out_chunk(s.out + cbase, v);                         // a partial last chunk still stores 32 columns (ldz % 64 == 0)
       online_update(v, p.v_local - cbase, s.m, s.s, e);
     }
   }

@@ -745,6 +745,97 @@ __global__ void __launch_bounds__(256) dz_pair_elem_kernel(DzPairElemArgs a) {
   }
 }
 
+// ---- fp32 inputs, fused-gradient forward: the kept logits are fp32 (the promoted sums of the split-bf16 GEMMs), the dLogits
+//      leave as split-bf16 triples (hi, mid, lo `part` elements apart) for the split gradient GEMMs: 4-8 B read + 6 B written
+//      per logit.  Same formulas as the bf16 kernels above and as the recompute epilogues (EpiDzPair / EpiDzRef, SPLIT).
+struct DzPairElemF32Args {
+  const DpaMeta* meta; int row_lo, row_hi;
+  const float* z; __nv_bfloat16* dz; size_t part; int ldz, v_local, v_offset;
+  const int* labels; const float* lse; const float* coef;
+};
+__global__ void __launch_bounds__(256) dz_pair_elem_f32_kernel(DzPairElemF32Args a) {
+  const int hi = min(a.meta->p0, a.row_hi);
+  const int nvec = (a.v_local + 7) >> 3;
+  for (int r = a.row_lo + blockIdx.x; r < hi; r += gridDim.x) {
+    const float4* pz = reinterpret_cast<const float4*>(a.z + (size_t)(r - a.row_lo) * a.ldz);
+    uint4* po = reinterpret_cast<uint4*>(a.dz + (size_t)(r - a.row_lo) * a.ldz);
+    const size_t pv = a.part >> 3;
+    const float c = a.coef[r];
+    if (c == 0.f) {
+      for (int v = threadIdx.x; v < nvec; v += blockDim.x) { po[v] = make_uint4(0, 0, 0, 0); po[v + pv] = make_uint4(0, 0, 0, 0); po[v + 2 * pv] = make_uint4(0, 0, 0, 0); }
+      continue;
+    }
+    const float nl = -a.lse[r] * kLog2e;
+    const int y = a.labels[r] - a.v_offset;
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+      const float4 z0 = pz[2 * v], z1 = pz[2 * v + 1];
+      float z[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+      const int col = v * 8;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { z[k] = -c * fast_exp2(fmaf(z[k], kLog2e, nl)); z[k] += (col + k == y) ? c : 0.f; }
+      uint4 o[3];
+      split8(make_float4(z[0], z[1], z[2], z[3]), make_float4(z[4], z[5], z[6], z[7]), o);
+      po[v] = o[0]; po[v + pv] = o[1]; po[v + 2 * pv] = o[2];
+    }
+  }
+}
+struct DzElemF32Args {
+  const DpaMeta* meta; int chunk, chunk_rows;
+  const float* zp; const float* zr; __nv_bfloat16* dz; size_t part; int ldz, v_local;
+  const float* lse_p; const float* lse_r; const float* coef; const int* act;
+  float* kl_row;
+};
+__global__ void __launch_bounds__(256) dz_kl_elem_f32_kernel(DzElemF32Args a) {
+  __shared__ float sh[32];
+  const int p0 = a.meta->p0, n_tot = a.meta->n_tot;
+  const int c_lo = a.chunk * a.chunk_rows;
+  const int lo = max(c_lo, p0), hi = min(c_lo + a.chunk_rows, n_tot);
+  const int nvec = (a.v_local + 7) >> 3;
+  const size_t pv = a.part >> 3;
+  for (int r = lo + blockIdx.x; r < hi; r += gridDim.x) {
+    const int j = r - p0;
+    const float4* pp = reinterpret_cast<const float4*>(a.zp + (size_t)(r - c_lo) * a.ldz);
+    const float4* pr = reinterpret_cast<const float4*>(a.zr + (size_t)(r - c_lo) * a.ldz);
+    uint4* po = reinterpret_cast<uint4*>(a.dz + (size_t)(r - c_lo) * a.ldz);
+    if (!a.act[j]) {
+      for (int v = threadIdx.x; v < nvec; v += blockDim.x) { po[v] = make_uint4(0, 0, 0, 0); po[v + pv] = make_uint4(0, 0, 0, 0); po[v + 2 * pv] = make_uint4(0, 0, 0, 0); }
+      if (threadIdx.x == 0) a.kl_row[j] = 0.f;
+      continue;
+    }
+    const float c = a.coef[j];
+    const float nlp = -a.lse_p[j] * kLog2e, nlr = -a.lse_r[j] * kLog2e;
+    float t = 0.f;
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+      const float4 a0 = pp[2 * v], a1 = pp[2 * v + 1], b0 = __ldg(pr + 2 * v), b1 = __ldg(pr + 2 * v + 1);
+      const float zp[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, zr[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float d[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const bool in = v * 8 + k < a.v_local;          // columns past v_local hold logits of zero-filled weight rows
+        const float q = in ? fast_exp2(fmaf(zr[k], kLog2e, nlr)) : 0.f;
+        t = fmaf(q, zr[k] - zp[k], t);
+        d[k] = in ? c * (fast_exp2(fmaf(zp[k], kLog2e, nlp)) - q) : 0.f;
+      }
+      uint4 o[3];
+      split8(make_float4(d[0], d[1], d[2], d[3]), make_float4(d[4], d[5], d[6], d[7]), o);
+      po[v] = o[0]; po[v + pv] = o[1]; po[v + 2 * pv] = o[2];
+    }
+    const float tot = block_sum(t, sh);
+    if (threadIdx.x == 0) a.kl_row[j] = tot - a.kl_row[j];
+  }
+}
+__global__ void scale_f32_kernel(float* x, size_t n, const float* __restrict__ d_loss) {
+  const float go = *d_loss;
+  if (go == 1.f) return;
+  float4* p = reinterpret_cast<float4*>(x);
+  const size_t nv = n >> 2, stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+    float4 v = p[i];
+    v.x *= go; v.y *= go; v.z *= go; v.w *= go;
+    p[i] = v;
+  }
+}
+
 // ---- fused-gradient backward: the gradients were formed for d_loss = 1 during the forward; scale them by the
 //      upstream gradient (a device scalar) unless it is exactly 1
 __global__ void scale_bf16_kernel(__nv_bfloat16* x, size_t n, const float* __restrict__ d_loss) {

@@ -270,7 +270,8 @@ def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.
                                    the reference's CPU-runnable configuration): every operand goes to the tensor cores as a
                                    split-bf16 triple (hi + mid + lo, six K segments per GEMM with the accumulator promoted
                                    to fp32 registers every K = 256), logits and dLogits stay fp32-accurate, gradients come
-                                   back in fp32.  round_logits is ignored (an fp32 nn.Linear does not round).
+                                   back in fp32.  round_logits is ignored (an fp32 nn.Linear does not round).  The chunked
+                                   ("fused") pass keeps fp32 logits, so it too runs the algorithmic GEMM count.
     need_dW                        default W.requires_grad (False under the shipped LoRA recipe: lm_head frozen)
     dense                          process every fed position instead of compacting to rows with a non-zero
                                    contribution (what the reference executes; benchmarking only)
@@ -306,8 +307,8 @@ def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.
             norm_weight_ref = norm_weight
     else:
         W_ref = W if W_ref is None else W_ref
-    if h_pair.dtype == torch.float32 and (ref_logits is not None or norm_weight is not None or backward == "fused"):
-        raise ValueError("fp32 inputs: ref_logits, norm_weight and backward='fused' belong to the bf16 execution")
+    if h_pair.dtype == torch.float32 and (ref_logits is not None or norm_weight is not None):
+        raise ValueError("fp32 inputs: ref_logits and norm_weight belong to the bf16 execution")
     _check_inputs(h_pair, labels_pair, signs_pair, h_ref_pol, h_ref_frozen, labels_ref, W, W_ref, ref_logits,
                   extra=(("norm_weight", norm_weight), ("norm_weight_ref", norm_weight_ref)))
     if need_dW is None:
@@ -331,18 +332,21 @@ def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.
                 raise TypeError(f"{name} must be a CUDA bf16 tensor of H elements")
     if backward not in ("auto", "recompute", "fused"):
         raise ValueError("backward must be 'auto', 'recompute' or 'fused'")
-    if h_pair.dtype == torch.float32:
-        # fp32 model (BASELINE configs[0]): nn.Linear emits fp32 logits, so there is no bf16 rounding point to reproduce and
-        # no bf16 logits to keep -- statistics forward + recompute backward on split-bf16 operands, fp32 dLogits (hi + lo)
-        round_logits, backward = False, "recompute"
+    fp32 = h_pair.dtype == torch.float32
+    if fp32:
+        # fp32 model (BASELINE configs[0]): nn.Linear emits fp32 logits, so there is no bf16 rounding point to reproduce; the
+        # chunked pass keeps fp32 logits (the promoted sums of the split-bf16 GEMMs) and emits split-bf16 dLogits
+        round_logits = False
+        if vocab_group is not None and backward == "auto":
+            backward = "recompute"
     lib_vp = False
     if vocab_group is not None:
         from .dist import library_comm_matches
         lib_vp = _lib.load().dpa_comm_world() > 1 and library_comm_matches(vocab_group)
-    if backward == "fused" and (not round_logits or (vocab_group is not None and not lib_vp)):
-        raise ValueError("backward='fused' needs round_logits=True and, with a vocab_group, the library's own communicator over "
-                         "that group (halva_b200.dist.init_library_comm)")
-    fused = backward == "fused" or (backward == "auto" and round_logits and (vocab_group is None or lib_vp))
+    if backward == "fused" and ((not round_logits and not fp32) or (vocab_group is not None and (not lib_vp or fp32))):
+        raise ValueError("backward='fused' needs round_logits=True (or fp32 inputs) and, with a vocab_group, bf16 inputs and the "
+                         "library's own communicator over that group (halva_b200.dist.init_library_comm)")
+    fused = backward == "fused" or (backward == "auto" and (round_logits or fp32) and (vocab_group is None or lib_vp))
     loss, align, div, status = DPALossFn.apply(h_pair, h_ref_pol, W, norm_weight, labels_pair, signs_pair, labels_ref, h_ref_frozen,
                                                W_ref, float(alpha), bool(round_logits), bool(need_dW), bool(dense), int(chunk_rows),
                                                vocab_group, int(v_offset), int(vocab_size), fused, norm_weight_ref, float(norm_eps),

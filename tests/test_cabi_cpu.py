@@ -75,6 +75,9 @@ def test_workspace_query_fp32_inputs_and_flag_conflicts():
     assert w32.state_bytes == w16.state_bytes
     assert w32.fwd_bytes >= w16.fwd_bytes + 2 * 3 * 32000 * 4096 * 2          # W and W_ref as three bf16 parts each
     assert w32.bwd_bytes > w16.bwd_bytes
+    wf = Workspace()
+    assert lib.dpa_query_workspace(C.byref(Shape(dtype=1, flags=FLAG_NEED_DW | FLAG_FUSED_GRAD, **kw)), C.byref(wf)) == 0
+    assert wf.fused_bytes > 3 * 32000 * 4096 * 2                              # fused fp32 pass: split weights + kept fp32 logits
     for bad in (FLAG_ROUND_LOGITS, FLAG_FUSED_GRAD | FLAG_ROUND_LOGITS):
         assert lib.dpa_query_workspace(C.byref(Shape(dtype=1, flags=bad, **kw)), C.byref(w32)) == -7
         assert b"fp32 inputs" in lib.dpa_last_error()
@@ -99,7 +102,7 @@ def test_python_op_argument_validation_without_gpu():
     with pytest.raises(TypeError):                        # mixed precisions
         dpa_loss(h.float(), y, y, h[:1], y[:1], W, h_ref_frozen=h[:1], alpha=0.4)
     with pytest.raises(ValueError, match="fp32 inputs"):
-        dpa_loss(h.float(), y, y, h[:1].float(), y[:1], W.float(), h_ref_frozen=h[:1].float(), alpha=0.4, backward="fused")
+        dpa_loss(h.float(), y, y, h[:1].float(), y[:1], W.float(), h_ref_frozen=h[:1].float(), alpha=0.4, norm_weight=W[0])
 
 
 def test_python_op_refuses_cpu_tensors():

@@ -63,12 +63,14 @@ def _check(c, o, tag, tol_loss=TOL_LOSS):
             assert rel(c[k], o[k]) <= TOL_GRAD, (tag, k, rel(c[k], o[k]))
 
 
+@pytest.mark.parametrize("bwd", ["fused", "recompute"])
 @pytest.mark.parametrize("name", FP32_GOLDEN)
-def test_fp32_golden_vs_reference_and_oracle(name):
-    """The reference's own fp32 execution (inputs NOT rounded to bf16) and the fp64 oracle on the same inputs."""
+def test_fp32_golden_vs_reference_and_oracle(name, bwd):
+    """The reference's own fp32 execution (inputs NOT rounded to bf16) and the fp64 oracle on the same inputs; both gradient
+    strategies (fused: the chunked pass keeps fp32 logits, 4 GEMM units per reference-sample row; recompute: 6)."""
     g = load_golden(name)
     t = _cuda32(g)
-    c = _run(t)
+    c = _run(t, backward=bwd)
     _check(c, _oracle(t), name + "/oracle")
     ref = dict(loss=float(g["ref_loss"]), align=float(g["ref_align"]), dH_pair=g["ref_dH_pair"], dH_ref=g["ref_dH_ref"], dW=g["ref_dW"])
     assert abs(c["loss"] - ref["loss"]) <= TOL_LOSS * abs(ref["loss"]) and abs(c["align"] - ref["align"]) <= TOL_LOSS * abs(ref["align"])
@@ -123,7 +125,11 @@ def test_fp32_beats_the_bf16_cast_and_is_chunk_invariant():
     g32, g16 = rel(c["dW"], o["dW"]), rel(b["dW"], o["dW"])
     assert err32 <= TOL_LOSS and g32 <= TOL_GRAD
     assert g16 > 20 * g32, (g16, g32, err16, err32)
-    for kw in (dict(chunk_rows=256), dict(dense=True)):
+    r = _run(t, backward="recompute")                    # the two gradient strategies agree to fp32 rounding
+    assert abs(r["loss"] - c["loss"]) <= 2e-6 * abs(c["loss"]) and abs(r["div"] - c["div"]) <= 1e-4 * abs(c["div"]) + 5e-7
+    for k in ("dH_pair", "dH_ref", "dW"):
+        assert rel(r[k], c[k]) <= 2e-5, (k, rel(r[k], c[k]))
+    for kw in (dict(chunk_rows=256), dict(dense=True), dict(dense=True, chunk_rows=256)):
         d = _run(t, **kw)
         assert abs(d["loss"] - c["loss"]) <= 2e-6 * abs(c["loss"]), kw
         for k in ("dH_pair", "dH_ref", "dW"):
@@ -139,10 +145,11 @@ def test_fp32_eval_and_argument_checks():
     with torch.no_grad():
         loss, align, div = dpa_loss(t["h_pair"], t["labels_pair"], t["signs_pair"], t["h_ref_pol"], t["labels_ref"], t["W"],
                                     h_ref_frozen=t["h_ref_frz"], alpha=t["alpha"])
-    assert loss.item() == c["loss"] and div.item() == c["div"]
+    # (evaluation runs the statistics-only forward: KL from the online partial sums; training the chunked pass: KL from the kept logits)
+    assert abs(loss.item() - c["loss"]) <= 2e-6 * abs(c["loss"]) and abs(div.item() - c["div"]) <= 1e-4 * abs(c["div"]) + 5e-7
     args = (t["h_pair"], t["labels_pair"], t["signs_pair"], t["h_ref_pol"], t["labels_ref"], t["W"])
     with pytest.raises(ValueError):
-        dpa_loss(*args, h_ref_frozen=t["h_ref_frz"], alpha=0.4, backward="fused")
+        dpa_loss(*args, h_ref_frozen=t["h_ref_frz"], alpha=0.4, norm_weight=t["W"][0])
     with pytest.raises(TypeError):                       # mixed precisions are refused, not silently cast
         dpa_loss(*args, h_ref_frozen=t["h_ref_frz"].to(torch.bfloat16), alpha=0.4)
     with pytest.raises(TypeError):
