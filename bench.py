@@ -484,7 +484,7 @@ def run_ours(args):
     vp = args.parallelism == "vp" and world > 1
     # dp: every rank its own batch (weak scaling);  vp: the SAME rows on every rank, lm_head rows split over the ranks
     if args.fp32:
-        args.backward, args.no_e2e, args.no_variants = "recompute", True, True
+        args.no_e2e, args.no_variants = True, True
     t = make_inputs(shape, seed=1234 + (0 if vp else rank), device=dev, plant=PLANT,
                     dtype=torch.float32 if args.fp32 else torch.bfloat16)
     vp_kw = {}

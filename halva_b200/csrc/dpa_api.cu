@@ -245,8 +245,8 @@ int launch_single(cudaStream_t st, const DeviceInfo* d, const CUtensorMap& tmA, 
 // the long-K gradient GEMMs on 256 x 512 tiles (CTA pairs only; B is MN-major in both, so the 64-column TMA boxes serve)
 template <template <int> class EpiT, int AMAJ, int BMAJ, class Params>
 int launch_grad(cudaStream_t st, const DeviceInfo* d, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmWork& work,
-                const Params& ep, const char* what) {
-  if (cta_group() == 2 && grad_bn() == 512)
+                const Params& ep, const char* what, bool wide = true) {
+  if (wide && cta_group() == 2 && grad_bn() == 512)
     return launch_gemm<GemmCfg<512, false, AMAJ, BMAJ, 2>, EpiT<512>>(st, d->sms, tmA, tmB, tmA, tmB, work, ep, what);
   return launch_single<EpiT<256>, AMAJ, BMAJ>(st, d, tmA, tmB, tmB, work, ep, what);
 }
@@ -318,6 +318,9 @@ int make_layout(const dpa_shape_t& s, Layout& L) {
   L.ldz = round_up_i(s.V_local, 64);
   // (fp32 inputs keep 14 B per logit of a chunk -- two fp32 logit buffers and a split-bf16 dLogits triple -- so their default chunk is smaller)
   L.chunk_rows = s.chunk_rows > 0 ? s.chunk_rows : (L.split ? kDefaultChunkRows / 4 : kDefaultChunkRows);
+  // a vocabulary shard keeps V_local / V of the logits per row: the same scratch holds proportionally more rows per chunk
+  // (8 shards of cfg-3: every row in one chunk -- one statistics exchange per segment, no empty chunk launches)
+  if (s.chunk_rows <= 0 && s.V_local < s.V) L.chunk_rows = (int)std::min<long long>((long long)L.chunk_rows * (s.V / s.V_local), 1 << 20);
   if (L.chunk_rows % kRowPad) return fail(DPA_ERR_BAD_SHAPE, "chunk_rows=%d must be a multiple of %d", L.chunk_rows, kRowPad);
   const int cap_tot = L.cap_pair + L.cap_ref;
   L.chunk_rows = std::min(L.chunk_rows, cap_tot);
@@ -387,8 +390,7 @@ int make_layout(const dpa_shape_t& s, Layout& L) {
   L.u_zp32 = L.split ? take((size_t)L.chunk_rows * L.ldz * 4) : o;
   L.u_dW32 = ((s.flags & DPA_FLAG_NEED_DW) && !L.split) ? take((size_t)s.V_local * s.H * 4) : o;
   take_split(L.u_split);
-  L.u_gather = o;                       // statistics records of all vocab shards (library-side exchange)
-  if (comm_world > 1 && s.V_local < s.V) take((size_t)comm_world * L.row_stats_bytes);
+  L.u_gather = o;                       // (library-side exchange: the shards' statistics records meet in peer memory)
   L.fused_total = o;
   return DPA_OK;
 }
@@ -513,7 +515,7 @@ int run_norm_backward(const dpa_args_t* a, const Layout& L, const DeviceInfo* d,
 enum : int { MERGE_ONLY = 0, MERGE_FINISH = 1, MERGE_FINISH_KL_LATER = 2 };
 int run_merge(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, const float4* part_pair, const float4* part_ref,
               const float* part_u, int n_pair, int n_ref, size_t stride_pair, size_t stride_ref, size_t stride_u, cudaStream_t st,
-              RowRange rr = RowRange{SEG_ALL, 0, 0}, int finish = MERGE_ONLY);
+              RowRange rr = RowRange{SEG_ALL, 0, 0}, int finish = MERGE_ONLY, const PeerView* push = nullptr, size_t push_off = 0);
 
 }  // namespace
 
@@ -530,7 +532,16 @@ struct MergeStrided {
   int finish, kl_from_stats;
   const int* act_ref;
   float* lse_pair; float* logp_pair; float* lse_ref_p; float* lse_ref_r; float* kl_row;
+  // vocab-parallel, library-side exchange: push the merged rows of THIS shard into slot `rank` of the statistics gather
+  // region of every peer (pv.world == 0: no push).  Record layout = [stats_pair | stats_ref | stats_u] of this state.
+  PeerView pv; size_t push_off, rec_bytes, ref_off;
 };
+__device__ __forceinline__ void push_float4(const PeerView& pv, size_t off, const float4& v) {
+  const uint4 u = make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
+#pragma unroll
+  for (int r = 0; r < kPeerMax; ++r)
+    if (r < pv.world) st_peer_v4(reinterpret_cast<uint4*>(pv.base[r] + off), u);
+}
 __global__ void merge_strided_kernel(MergeStrided a) {
   const int p0 = a.meta->p0;
   int lo, hi; row_range(a.meta, a.rr, lo, hi);
@@ -544,6 +555,7 @@ __global__ void merge_strided_kernel(MergeStrided a) {
         s += p.y * expf(p.x - m); zy += p.z;
       }
       a.stats_pair[r] = make_float4(m, s, zy, 0.f);
+      if (a.pv.world) push_float4(a.pv, a.push_off + (size_t)a.pv.rank * a.rec_bytes + (size_t)r * 16, make_float4(m, s, zy, 0.f));
       if (a.finish) {
         const float lse = m + logf(s);
         a.lse_pair[r] = lse; a.logp_pair[r] = zy - lse;          // z[y] - LSE (halva_trainer.py:407)
@@ -564,6 +576,7 @@ __global__ void merge_strided_kernel(MergeStrided a) {
       }
       a.stats_ref[j] = make_float4(mp, sp, mr, sr);
       if (a.part_u) a.stats_u[j] = u;
+      if (a.pv.world) push_float4(a.pv, a.push_off + (size_t)a.pv.rank * a.rec_bytes + a.ref_off + (size_t)j * 16, make_float4(mp, sp, mr, sr));
       if (a.finish) {                                  // same maths as finish_rows_kernel (dpa_kernels.cuh)
         a.lse_ref_p[j] = mp + logf(sp); a.lse_ref_r[j] = mr + logf(sr);
         const float dlse = (mr - mp) + logf(sr / sp);
@@ -572,6 +585,21 @@ __global__ void merge_strided_kernel(MergeStrided a) {
       }
     }
   }
+  if (a.pv.world) __threadfence_system();        // the pushed rows are ordered before the barrier that follows
+}
+// every shard's part of the divergence -> all peers (slot = rank); summed in fixed order by finish_div_kernel
+__global__ void push_div_kernel(PeerView pv, const float* losses) {
+  if (threadIdx.x < pv.world)
+    *reinterpret_cast<volatile float*>(pv.base[threadIdx.x] + kPeerLossOff + 4 * pv.rank) = losses[2];
+  __threadfence_system();
+}
+__global__ void finish_div_kernel(PeerView pv, float* losses, float alpha) {
+  if (threadIdx.x == 0) {
+    const float* part = reinterpret_cast<const float*>(pv.base[pv.rank] + kPeerLossOff);
+    float div = 0.f;
+    for (int r = 0; r < pv.world; ++r) div += __ldcg(part + r);
+    losses[2] = div; losses[0] = losses[1] + alpha * div;
+  }
 }
 }  // namespace dpa
 
@@ -579,12 +607,12 @@ namespace {
 
 int run_merge(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, const float4* part_pair, const float4* part_ref,
               const float* part_u, int n_pair, int n_ref, size_t stride_pair, size_t stride_ref, size_t stride_u, cudaStream_t st,
-              RowRange rr, int finish) {
+              RowRange rr, int finish, const PeerView* push, size_t push_off) {
   MergeStrided m{at<DpaMeta>(a->state, L.meta), rr, part_pair, part_ref, part_u, n_pair, n_ref, stride_pair, stride_ref, stride_u,
                  at<float4>(a->state, L.stats_pair), at<float4>(a->state, L.stats_ref), at<float>(a->state, L.stats_u),
                  finish != MERGE_ONLY, finish == MERGE_FINISH, at<int>(a->state, L.act_ref), at<float>(a->state, L.lse_pair),
                  at<float>(a->state, L.logp_pair), at<float>(a->state, L.lse_ref_p), at<float>(a->state, L.lse_ref_r),
-                 at<float>(a->state, L.kl_row)};
+                 at<float>(a->state, L.kl_row), push ? *push : PeerView{}, push_off, L.row_stats_bytes, L.stats_ref - L.stats_pair};
   ProfScope ps(PK_REDUCE, 1, st);
   merge_strided_kernel<<<d->sms * 2, 256, 0, st>>>(m);
   LAUNCH_CHECK("merge_partials");
@@ -662,7 +690,6 @@ struct NcclApi {
   int (*CommInitRank)(NcclComm*, int, NcclId, int) = nullptr;
   int (*CommDestroy)(NcclComm) = nullptr;
   int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;
-  int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
 NcclApi g_nccl;
@@ -676,7 +703,7 @@ struct PeerMem {
 struct Comm { NcclComm comm = nullptr; int rank = 0, world = 1, device = -1; cudaStream_t stream = nullptr; PeerMem pm; };   // stream: the
 // exchange of the backward runs beside the caller's stream (fork / join with events) so that it overlaps the remaining GEMMs
 Comm g_comm;
-constexpr int kNcclUint8 = 1, kNcclFloat32 = 7, kNcclBfloat16 = 9, kNcclSum = 0;
+constexpr int kNcclUint8 = 1;
 
 int nccl_bind() {
   if (g_nccl.lib) return DPA_OK;
@@ -687,7 +714,7 @@ int nccl_bind() {
 #define BIND(field, sym) do { *reinterpret_cast<void**>(&g_nccl.field) = dlsym(h, sym); \
     if (!g_nccl.field) return fail(DPA_ERR_NCCL, "libnccl: symbol %s missing", sym); } while (0)
   BIND(GetUniqueId, "ncclGetUniqueId"); BIND(CommInitRank, "ncclCommInitRank"); BIND(CommDestroy, "ncclCommDestroy");
-  BIND(AllGather, "ncclAllGather"); BIND(AllReduce, "ncclAllReduce"); BIND(GetErrorString, "ncclGetErrorString");
+  BIND(AllGather, "ncclAllGather"); BIND(GetErrorString, "ncclGetErrorString");
 #undef BIND
   g_nccl.lib = h;
   return DPA_OK;
@@ -1032,19 +1059,27 @@ struct Plan {
     }
     if (dW32) {
       using P = typename EpiAccumDW<256>::Params;
-      const int wide = (cta_group() == 2 && grad_bn() == 512) ? 1 : 0;
+      // 512-wide tiles unless their wave count over the CTA pairs is clearly worse (a vocabulary shard: few row units of dW)
+      auto waves = [&](int bn) { const long long t = (long long)((s.V_local + 255) / 256) * ((s.H + bn - 1) / bn); const int p = std::max(1, d->sms / 2);
+                                 return (double)((t + p - 1) / p) * (bn / 256); };
+      const int wide = (cta_group() == 2 && grad_bn() == 512 && waves(512) <= 1.08 * waves(256)) ? 1 : 0;
       GemmWork w{meta, KIND_DW, ch, L.chunk_rows, s.V_local, s.H, 0, 1, super_m().dw ? super_m().dw : (wide ? 9 : 0), hint_dw().a, hint_dw().b,
                  slot_of(ch) * L.chunk_rows};
       P ep{meta, ch, L.chunk_rows, dW32, static_cast<__nv_bfloat16*>(a->dW), s.H, s.V_local, s.H};
       ProfScope ps(PK_DW, 1, st);
-      return launch_grad<EpiAccumDW, MNMAJOR, MNMAJOR>(st, d, tmDzMN, tmHpMN, w, ep, "dW");
+      return launch_grad<EpiAccumDW, MNMAJOR, MNMAJOR>(st, d, tmDzMN, tmHpMN, w, ep, "dW", wide != 0);
     }
     return DPA_OK;
   }
   // ---- vocab-parallel with the library's communicator: this rank's dH partial sums of chunk ch (packed rows, written by the
   //      dH GEMM into peer-memory buffer ch & 1) are all-reduced in place over NVLink and scattered, on the communicator's
   //      stream, while this stream goes on with dW and the next chunk.  Row ranges come from DpaMeta: no host count.
-  size_t peer_buf_off(int ch) const { return kPeerCtrlBytes + (size_t)(ch & 1) * L.chunk_rows * s.H * 2; }
+  size_t peer_stats_off() const { return kPeerCtrlBytes; }
+  size_t peer_buf_off(int ch) const {
+    return kPeerCtrlBytes + align_up((size_t)g_comm.world * L.row_stats_bytes, 256) + (size_t)(ch & 1) * L.chunk_rows * s.H * 2;
+  }
+  // DPA_PEER_OVERLAP=0: run the dH reduction on the caller's stream (serialised) instead of beside the dW GEMM
+  static bool peer_overlap() { static const bool v = env_int("DPA_PEER_OVERLAP", 1) != 0; return v; }
   cudaEvent_t buf_free[2] = {nullptr, nullptr};      // recorded on the communicator's stream after chunk's scatter
   int before_dH_chunk(int ch) {                      // buffer ch & 1 must have been scattered (chunk ch - 2) before it is rewritten
     cudaEvent_t& e = buf_free[ch & 1];
@@ -1055,12 +1090,16 @@ struct Plan {
     return DPA_OK;
   }
   int exchange_dH_chunk(int ch) {
-    cudaEvent_t e;
-    CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    CUDA_TRY(cudaEventRecord(e, st));
-    CUDA_TRY(cudaStreamWaitEvent(g_comm.stream, e, 0));
-    CUDA_TRY(cudaEventDestroy(e));              // released once it has completed
-    cudaStream_t cs = g_comm.stream;
+    const bool overlap = peer_overlap();
+    cudaStream_t cs = overlap ? g_comm.stream : st;
+    if (overlap) {
+      cudaEvent_t e;
+      CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      CUDA_TRY(cudaEventRecord(e, st));
+      CUDA_TRY(cudaStreamWaitEvent(g_comm.stream, e, 0));
+      CUDA_TRY(cudaEventDestroy(e));              // released once it has completed
+    }
+    ProfScope ps(PK_MISC, 4, cs);
     const PeerView v = peer_view();
     peer_barrier_kernel<<<1, 32, 0, cs>>>(v, 2 * (ch & 3));
     PeerReduceArgs ra{v, meta, ch, L.chunk_rows, s.H, peer_buf_off(ch)};
@@ -1071,11 +1110,37 @@ struct Plan {
                         static_cast<__nv_bfloat16*>(a->dH_pair), static_cast<__nv_bfloat16*>(a->dH_ref), s.H};
     scatter_chunk_rows_kernel<<<d->sms * 4, 256, 0, cs>>>(sc);
     LAUNCH_CHECK("peer exchange");
+    if (!overlap) return DPA_OK;
     CUDA_TRY(cudaEventCreateWithFlags(&buf_free[ch & 1], cudaEventDisableTiming));
     CUDA_TRY(cudaEventRecord(buf_free[ch & 1], cs));
     return DPA_OK;
   }
+  // the forward's exchange: this shard's merged statistics rows of `rr` were pushed into every peer by merge(..., push);
+  // wait for all shards, then merge the G records (+ per-row results)
+  int exchange_stats(RowRange rr, int finish, int slot) {
+    const PeerView v = peer_view();
+    {
+      ProfScope ps(PK_MISC, 1, st);
+      peer_barrier_kernel<<<1, 32, 0, st>>>(v, 8 + (slot & 3));
+      LAUNCH_CHECK("peer barrier");
+    }
+    const char* g = g_comm.pm.base + peer_stats_off();
+    const size_t rec = L.row_stats_bytes;
+    const int G = g_comm.world;
+    return run_merge(a, L, d, reinterpret_cast<const float4*>(g), reinterpret_cast<const float4*>(g + (L.stats_ref - L.stats_pair)), nullptr,
+                     G, G, rec / 16, rec / 16, rec / 4, st, rr, finish);
+  }
+  int exchange_div() {          // the divergence is the sum of the shards' parts
+    const PeerView v = peer_view();
+    ProfScope ps(PK_REDUCE, 3, st);
+    push_div_kernel<<<1, 32, 0, st>>>(v, a->losses);
+    peer_barrier_kernel<<<1, 32, 0, st>>>(v, 12);
+    finish_div_kernel<<<1, 32, 0, st>>>(v, a->losses, a->alpha);
+    LAUNCH_CHECK("exchange_div");
+    return DPA_OK;
+  }
   int join_exchange() {                          // the caller's stream waits for everything queued on the communicator's stream
+    if (!peer_overlap()) return DPA_OK;
     for (int i = 0; i < 2; ++i)
       if (buf_free[i]) { CUDA_TRY(cudaEventDestroy(buf_free[i])); buf_free[i] = nullptr; }
     cudaEvent_t e;
@@ -1086,8 +1151,9 @@ struct Plan {
     return DPA_OK;
   }
   // collective part of enabling the library-side exchange for this call (peer memory sized for two chunk buffers)
-  int enable_peer_exchange() {
-    int rc = ensure_peer_mem((size_t)2 * L.chunk_rows * s.H * 2);
+  int enable_peer_exchange(bool with_dH = true) {
+    const int bufs = L.n_chunks > 1 ? 2 : 1;
+    int rc = ensure_peer_mem(align_up((size_t)g_comm.world * L.row_stats_bytes, 256) + (with_dH ? (size_t)bufs * L.chunk_rows * s.H * 2 : 0));
     if (rc) return rc;
     dH_packed = reinterpret_cast<__nv_bfloat16*>(g_comm.pm.base);     // (per-chunk buffer: see grad_gemms)
     return DPA_OK;
@@ -1116,8 +1182,10 @@ struct Plan {
     LAUNCH_CHECK("coef");
     return DPA_OK;
   }
-  int merge(RowRange rr, bool with_u, int finish = MERGE_ONLY) {
-    return run_merge(a, L, d, part_pair, part_ref, with_u ? part_u : nullptr, L.ng_pair, L.ng_ref, L.cap_pair, L.cap_ref, L.cap_ref, st, rr, finish);
+  int merge(RowRange rr, bool with_u, int finish = MERGE_ONLY, bool push = false) {
+    const PeerView v = push ? peer_view() : PeerView{};
+    return run_merge(a, L, d, part_pair, part_ref, with_u ? part_u : nullptr, L.ng_pair, L.ng_ref, L.cap_pair, L.cap_ref, L.cap_ref, st, rr, finish,
+                     push ? &v : nullptr, peer_stats_off());
   }
 };
 
@@ -1167,15 +1235,8 @@ int forward_fused_impl(const dpa_args_t* a, cudaStream_t st) {
   if (vp && (s.flags & DPA_FLAG_FUSED_NORM)) return fail(DPA_ERR_ARG, "DPA_FLAG_FUSED_NORM is not available with a vocab-sharded lm_head");
   if (vp && a->ref_logits) return fail(DPA_ERR_ARG, "ref_logits is not available with a vocab-sharded lm_head");
   Plan p(a, L, d, st);
-  if (vp && !loss_only && (rc = p.enable_peer_exchange())) return rc;
-  auto exchange_stats = [&](RowRange rr, int finish) -> int {      // all shards' records -> every rank -> merge (+ per-row results)
-    char* g = at<char>(a->scratch, L.u_gather);
-    const size_t rec = L.row_stats_bytes;
-    NCCL_TRY(g_nccl.AllGather(at<char>(a->state, L.stats_pair), g, rec, kNcclUint8, g_comm.comm, st));
-    const int G = g_comm.world;
-    return run_merge(a, L, d, reinterpret_cast<const float4*>(g), reinterpret_cast<const float4*>(g + (L.stats_ref - L.stats_pair)), nullptr,
-                     G, G, rec / 16, rec / 16, rec / 4, st, rr, finish);
-  };
+  if (vp && (rc = p.enable_peer_exchange(!loss_only))) return rc;
+  int n_exchange = 0;
   const Layout::Split* sp = L.split ? &L.u_split : nullptr;
   if ((rc = p.init(L.u_Hp, L.u_Hf, L.u_part_pair, L.u_part_ref, L.u_part_u, true, at<__nv_bfloat16>(a->scratch, L.u_dz),
                    at<__nv_bfloat16>(a->scratch, L.u_zr),
@@ -1191,8 +1252,8 @@ int forward_fused_impl(const dpa_args_t* a, cudaStream_t st) {
   // (the statistics GEMM keeps the logits of the pair rows of every slot; nothing else touches a slot until its chunk's turn)
   const int keep_rows = loss_only ? 0 : L.n_slots * L.chunk_rows;
   if ((rc = sp ? p.fwd_pair<false>(keep_rows) : p.fwd_pair<true>(keep_rows))) return rc;
-  if ((rc = p.merge(RowRange{SEG_PAIR, 0, 0}, true, vp ? MERGE_ONLY : MERGE_FINISH))) return rc;
-  if (vp && (rc = exchange_stats(RowRange{SEG_PAIR, 0, 0}, MERGE_FINISH))) return rc;
+  if ((rc = p.merge(RowRange{SEG_PAIR, 0, 0}, true, vp ? MERGE_ONLY : MERGE_FINISH, vp))) return rc;
+  if (vp && (rc = p.exchange_stats(RowRange{SEG_PAIR, 0, 0}, MERGE_FINISH, n_exchange++))) return rc;
   if ((rc = run_losses(a, L, st, LOSS_ALIGN, 0))) return rc;
   if ((rc = p.coef(nullptr /* d_loss = 1 */))) return rc;
 
@@ -1219,8 +1280,8 @@ int forward_fused_impl(const dpa_args_t* a, cudaStream_t st) {
     }
     if ((rc = p.stash_ref(ch))) return rc;
     const RowRange rr{SEG_REF_CHUNK, ch, L.chunk_rows};
-    if ((rc = p.merge(rr, false, vp ? MERGE_ONLY : MERGE_FINISH_KL_LATER))) return rc;
-    if (vp && (rc = exchange_stats(rr, MERGE_FINISH_KL_LATER))) return rc;
+    if ((rc = p.merge(rr, false, vp ? MERGE_ONLY : MERGE_FINISH_KL_LATER, vp))) return rc;
+    if (vp && (rc = p.exchange_stats(rr, MERGE_FINISH_KL_LATER, n_exchange++))) return rc;
     if (sp) {
       DzElemF32Args e{p.meta, ch, L.chunk_rows, p.zp32, p.zr32, p.dz, p.dz_part, L.ldz, s.V_local, at<float>(a->state, L.lse_ref_p),
                       at<float>(a->state, L.lse_ref_r), at<float>(a->state, L.coef_ref), at<int>(a->state, L.act_ref), at<float>(a->state, L.kl_row)};
@@ -1238,10 +1299,7 @@ int forward_fused_impl(const dpa_args_t* a, cudaStream_t st) {
     if (!loss_only && (rc = p.grad_gemms(ch))) return rc;
   }
   if ((rc = run_losses(a, L, st, LOSS_TOTAL, 1))) return rc;
-  if (vp) {                      // the divergence is the sum of the shards' parts: one float over the communicator
-    NCCL_TRY(g_nccl.AllReduce(a->losses + 2, a->losses + 2, 1, kNcclFloat32, kNcclSum, g_comm.comm, st));
-    if ((rc = run_losses(a, L, st, LOSS_FINAL, 2))) return rc;
-  }
+  if (vp && (rc = p.exchange_div())) return rc;
   if (loss_only) return DPA_OK;
   if (vp && (rc = p.join_exchange())) return rc;
   if ((rc = run_norm_backward(a, L, d, st))) return rc;

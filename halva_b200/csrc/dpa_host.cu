@@ -97,10 +97,9 @@ int dpa_stage_host_batch(const dpa_host_batch_t* b, void* stream, dpa_stage_info
     bytes += (long long)n;
     return cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, st);
   };
-  cudaError_t e = cudaSuccess;
-  if ((e = copy(b->d_labels_pair, b->labels_pair, (size_t)S * b->T * isz)) != cudaSuccess) return DPA_ERR_CUDA;
-  if ((e = copy(b->d_signs_pair, b->signs_pair, (size_t)S * b->T * isz)) != cudaSuccess) return DPA_ERR_CUDA;
-  if ((e = copy(b->d_labels_ref, b->labels_ref, (size_t)b->B_ref * b->T_ref * isz)) != cudaSuccess) return DPA_ERR_CUDA;
+  if (copy(b->d_labels_pair, b->labels_pair, (size_t)S * b->T * isz) != cudaSuccess) return DPA_ERR_CUDA;
+  if (copy(b->d_signs_pair, b->signs_pair, (size_t)S * b->T * isz) != cudaSuccess) return DPA_ERR_CUDA;
+  if (copy(b->d_labels_ref, b->labels_ref, (size_t)b->B_ref * b->T_ref * isz) != cudaSuccess) return DPA_ERR_CUDA;
   if (b->dense) {
     if (copy(b->d_h_pair, b->h_pair, (size_t)S * b->T * row_bytes) != cudaSuccess) return DPA_ERR_CUDA;
     if (copy(b->d_h_ref_pol, b->h_ref_pol, (size_t)b->B_ref * b->T_ref * row_bytes) != cudaSuccess) return DPA_ERR_CUDA;

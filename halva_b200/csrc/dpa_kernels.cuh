@@ -442,7 +442,7 @@ __global__ void finish_rows_kernel(FinishArgs a) {
 // ---- P[b,k], N[b,k] and the loss assembly in ONE launch: one block per sequence computes its row of P / N (one warp per
 //      phrase column round-robin, fixed summation order); the last block to finish (ticket in DpaMeta) assembles
 //      align = mean log(1+exp(N-P)), sigma for the backward and / or div = sum(kl)/B_ref and the total.
-enum : int { LOSS_ALIGN = 1, LOSS_TOTAL = 2, LOSS_FINAL = 4 };
+enum : int { LOSS_ALIGN = 1, LOSS_TOTAL = 2 };
 struct LossArgs {
   DpaMeta* meta;
   const int* src_pair; const int* col_pair; const float* logp_pair;
@@ -532,8 +532,6 @@ __global__ void __launch_bounds__(256) loss_kernel(LossArgs a) {
       a.losses[0] = align + a.alpha * div; a.losses[2] = div; a.losses[3] = 0.f;
     }
   }
-  // vocab-parallel: losses[2] held this shard's part of the divergence and has just been summed over the shards
-  if ((a.phases & LOSS_FINAL) && threadIdx.x == 0) a.losses[0] = a.losses[1] + a.alpha * a.losses[2];
 }
 
 // ---- backward row coefficients (incl. the upstream gradient): dz = coef (onehot - p) / coef (p - q)

@@ -8,8 +8,10 @@
 // in a fixed order in fp32 (every rank ends up with bit-identical rows), and runs beside the chunk's dW GEMM.
 //
 // Layout of one rank's symmetric allocation (cudaMalloc by dpa_comm's first use, mapped into every peer with CUDA IPC):
-//   [0, 4096)   control: uint32 flag[kPeerSlots][8] (written by the peers), uint32 epoch[kPeerSlots] (local)
-//   [4096, ..)  two chunk buffers [chunk_rows][H] bf16: the dH GEMM of chunk c writes its partial sums into buffer c & 1
+//   [0, 4096)   control: uint32 flag[kPeerSlots][8] (written by the peers), uint32 epoch[kPeerSlots] (local), float kl_part[8]
+//   [4096, ..)  statistics gather region [G][record]: rank r pushes its per-row statistics record rows into slot r of
+//               every peer (the forward's exchange: 36 B/row, only the rows of the segment / chunk being finished)
+//   [.., ..)    two chunk buffers [chunk_rows][H] bf16: the dH GEMM of chunk c writes its partial sums into buffer c & 1
 // Protocol per chunk, on the communicator's stream (forked from the caller's stream after the chunk's dH GEMM):
 //   barrier(slot A)  -- every rank's partial sums of the chunk are complete
 //   reduce           -- rank r sums rows slice r of all G buffers (peer loads) and writes the result back into slice r of
@@ -25,6 +27,7 @@ constexpr int kPeerMax = 8;                 // ranks of one NVSwitch box
 constexpr int kPeerSlots = 16;              // barrier slots (flag rows) in the control block
 constexpr size_t kPeerCtrlBytes = 4096;
 constexpr int kPeerFlagWords = kPeerSlots * kPeerMax;      // epoch[] follows
+constexpr size_t kPeerLossOff = 1024;       // float kl_part[8] inside the control block: every shard's part of the divergence
 
 struct PeerView {
   char* base[kPeerMax];                     // base[r]: rank r's symmetric allocation as mapped in THIS process

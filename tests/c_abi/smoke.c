@@ -97,6 +97,6 @@ int main(int argc, char** argv) {
   CK(cudaMemcpy(status, a.status, 32, cudaMemcpyDeviceToHost));
   printf("status %d K %d rows %d %d\n", status[0], status[1], status[2], status[3]);
   printf("loss %.9g align %.9g div %.9g\n", losses[0], losses[1], losses[2]);
-  printf("dH_pair %.9g dH_ref %.9g dW %.9g\n", bf16_abs_sum(a.dH_pair, n_hp), bf16_abs_sum(a.dH_ref, n_hr), bf16_abs_sum(a.dW, n_w));
+  printf("dH_pair %.17g dH_ref %.17g dW %.17g\n", bf16_abs_sum(a.dH_pair, n_hp), bf16_abs_sum(a.dH_ref, n_hr), bf16_abs_sum(a.dW, n_w));
   return 0;
 }
