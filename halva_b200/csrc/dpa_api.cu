@@ -1103,7 +1103,7 @@ struct Plan {
     const PeerView v = peer_view();
     peer_barrier_kernel<<<1, 32, 0, cs>>>(v, 2 * (ch & 3));
     PeerReduceArgs ra{v, meta, ch, L.chunk_rows, s.H, peer_buf_off(ch)};
-    peer_reduce_rows_kernel<<<d->sms * 2, 256, 0, cs>>>(ra);
+    CUDA_TRY(launch_peer_reduce(ra, d->sms * 2, cs));
     peer_barrier_kernel<<<1, 32, 0, cs>>>(v, 2 * (ch & 3) + 1);
     ScatterChunkArgs sc{meta, ch, L.chunk_rows, at<int>(a->state, L.src_pair), at<int>(a->state, L.src_ref),
                         reinterpret_cast<const __nv_bfloat16*>(g_comm.pm.base + peer_buf_off(ch)),

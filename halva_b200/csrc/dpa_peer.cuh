@@ -77,33 +77,55 @@ struct PeerReduceArgs {
   size_t buf_off;                           // byte offset of this chunk's buffer inside every rank's allocation
 };
 // In-place all-reduce of the chunk's packed dH rows [c_lo, min(c_hi, n_tot)): this rank owns slice `rank` of the rows.
-__global__ void __launch_bounds__(256) peer_reduce_rows_kernel(PeerReduceArgs a) {
+// G = ranks (compile-time: the G peer loads of a vector are independent and U = 16 / G vectors are in flight per thread).
+template <int G>
+__global__ void __launch_bounds__(256, 2) peer_reduce_rows_kernel(PeerReduceArgs a) {
   const int c_lo = a.chunk * a.chunk_rows;
   const int rows = max(min(c_lo + a.chunk_rows, a.meta->n_tot) - c_lo, 0);
-  const int G = a.v.world;
   const long long vec_row = a.H / 8;                                    // uint4 per row
   const long long v0 = (long long)rows * a.v.rank / G * vec_row, v1 = (long long)rows * (a.v.rank + 1) / G * vec_row;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = v0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < v1; i += stride) {
-    uint4 in[kPeerMax];
+  constexpr int U = G >= 16 ? 1 : 16 / G;
+  for (long long i0 = v0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < v1; i0 += U * stride) {
+    uint4 in[U][G];
 #pragma unroll
-    for (int r = 0; r < kPeerMax; ++r)
-      if (r < G) in[r] = ld_peer_v4(reinterpret_cast<const uint4*>(a.v.base[r] + a.buf_off) + i);
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
 #pragma unroll
-    for (int r = 0; r < kPeerMax; ++r) {                                // fixed order: identical result on every rank
-      if (r < G) {
-        const uint32_t w[4] = {in[r].x, in[r].y, in[r].z, in[r].w};
+      for (int r = 0; r < G; ++r)
+        if (i < v1) in[u][r] = ld_peer_v4(reinterpret_cast<const uint4*>(a.v.base[r] + a.buf_off) + i);
+    }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { const float2 f = bf2_to_f2(w[k]); acc[2 * k] += f.x; acc[2 * k + 1] += f.y; }
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < v1) {
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int r = 0; r < G; ++r) {                                   // fixed order: identical result on every rank
+          const uint32_t w[4] = {in[u][r].x, in[u][r].y, in[u][r].z, in[u][r].w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { const float2 f = bf2_to_f2(w[k]); acc[2 * k] += f.x; acc[2 * k + 1] += f.y; }
+        }
+        const uint4 out = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+#pragma unroll
+        for (int r = 0; r < G; ++r) st_peer_v4(reinterpret_cast<uint4*>(a.v.base[r] + a.buf_off) + i, out);
       }
     }
-    const uint4 out = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
-#pragma unroll
-    for (int r = 0; r < kPeerMax; ++r)
-      if (r < G) st_peer_v4(reinterpret_cast<uint4*>(a.v.base[r] + a.buf_off) + i, out);
   }
   __threadfence_system();                   // this thread's peer stores are ordered before the barrier that follows
+}
+inline cudaError_t launch_peer_reduce(const PeerReduceArgs& a, int blocks, cudaStream_t st) {
+  switch (a.v.world) {
+    case 2: peer_reduce_rows_kernel<2><<<blocks, 256, 0, st>>>(a); break;
+    case 3: peer_reduce_rows_kernel<3><<<blocks, 256, 0, st>>>(a); break;
+    case 4: peer_reduce_rows_kernel<4><<<blocks, 256, 0, st>>>(a); break;
+    case 5: peer_reduce_rows_kernel<5><<<blocks, 256, 0, st>>>(a); break;
+    case 6: peer_reduce_rows_kernel<6><<<blocks, 256, 0, st>>>(a); break;
+    case 7: peer_reduce_rows_kernel<7><<<blocks, 256, 0, st>>>(a); break;
+    case 8: peer_reduce_rows_kernel<8><<<blocks, 256, 0, st>>>(a); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
 }
 
 // packed rows of one chunk (already reduced, local buffer) -> their [s, t] positions; one warp per row
