@@ -42,13 +42,16 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ uint4 ld_peer_v4(const uint4* p) {        // never through L1: the line may be a peer's, rewritten every step
+// Bulk data moves with weak (non-coherent-scope) accesses -- system-scope relaxed accesses measured 4x below the NVLink
+// rate -- ordered by the fences / flag barriers around them: loads bypass L1 (.cg; L1 is invalidated at kernel start anyway
+// and peer memory is never cached in this GPU's L2), stores are followed by __threadfence_system() before the next barrier.
+__device__ __forceinline__ uint4 ld_peer_v4(const uint4* p) {
   uint4 v;
-  asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void st_peer_v4(uint4* p, const uint4& v) {
-  asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  asm volatile("st.global.cg.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 // One warp: lane r signals rank r (epoch of this slot, kept in the local control block, so a CUDA-graph replay advances it
