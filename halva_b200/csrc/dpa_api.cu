@@ -1315,20 +1315,15 @@ int backward_scale_impl(const dpa_args_t* a, cudaStream_t st) {
   if ((rc = check_grad_outputs(a))) return rc;
   if (!a->d_loss) return DPA_OK;                                 // NULL = 1
   const dpa_shape_t& s = a->shape;
-  ProfScope ps(PK_SCALE, 3, st);
-  if (L.split) {
-    scale_f32_kernel<<<d->sms * 8, 256, 0, st>>>(static_cast<float*>(a->dH_pair), (size_t)2 * s.B * s.T * s.H, a->d_loss);
-    scale_f32_kernel<<<d->sms * 8, 256, 0, st>>>(static_cast<float*>(a->dH_ref), (size_t)s.B_ref * s.T_ref * s.H, a->d_loss);
-    if (s.flags & DPA_FLAG_NEED_DW) scale_f32_kernel<<<d->sms * 8, 256, 0, st>>>(static_cast<float*>(a->dW), (size_t)s.V_local * s.H, a->d_loss);
-    LAUNCH_CHECK("scale_grads[fp32]");
-    return DPA_OK;
-  }
-  scale_bf16_kernel<<<d->sms * 8, 256, 0, st>>>(static_cast<__nv_bfloat16*>(a->dH_pair), (size_t)2 * s.B * s.T * s.H, a->d_loss);
-  scale_bf16_kernel<<<d->sms * 8, 256, 0, st>>>(static_cast<__nv_bfloat16*>(a->dH_ref), (size_t)s.B_ref * s.T_ref * s.H, a->d_loss);
-  if (s.flags & DPA_FLAG_NEED_DW)
-    scale_bf16_kernel<<<d->sms * 8, 256, 0, st>>>(static_cast<__nv_bfloat16*>(a->dW), (size_t)s.V_local * s.H, a->d_loss);
-  if ((s.flags & DPA_FLAG_FUSED_NORM) && a->d_norm_w)
-    scale_bf16_kernel<<<1, 256, 0, st>>>(static_cast<__nv_bfloat16*>(a->d_norm_w), (size_t)s.H, a->d_loss);
+  ProfScope ps(PK_SCALE, 1, st);
+  ScaleSegs sg{};
+  auto add = [&](void* p, size_t n) { sg.p[sg.count] = p; sg.n[sg.count] = n; ++sg.count; };
+  add(a->dH_pair, (size_t)2 * s.B * s.T * s.H);
+  add(a->dH_ref, (size_t)s.B_ref * s.T_ref * s.H);
+  if (s.flags & DPA_FLAG_NEED_DW) add(a->dW, (size_t)s.V_local * s.H);
+  if ((s.flags & DPA_FLAG_FUSED_NORM) && a->d_norm_w) add(a->d_norm_w, (size_t)s.H);
+  if (L.split) scale_grads_kernel<float><<<d->sms * 8, 256, 0, st>>>(sg, a->d_loss);
+  else scale_grads_kernel<__nv_bfloat16><<<d->sms * 8, 256, 0, st>>>(sg, a->d_loss);
   LAUNCH_CHECK("scale_grads");
   return DPA_OK;
 }

@@ -822,34 +822,32 @@ __global__ void __launch_bounds__(256) dz_kl_elem_f32_kernel(DzElemF32Args a) {
     if (threadIdx.x == 0) a.kl_row[j] = tot - a.kl_row[j];
   }
 }
-__global__ void scale_f32_kernel(float* x, size_t n, const float* __restrict__ d_loss) {
-  const float go = *d_loss;
-  if (go == 1.f) return;
-  float4* p = reinterpret_cast<float4*>(x);
-  const size_t nv = n >> 2, stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
-    float4 v = p[i];
-    v.x *= go; v.y *= go; v.z *= go; v.w *= go;
-    p[i] = v;
-  }
-}
-
 // ---- fused-gradient backward: the gradients were formed for d_loss = 1 during the forward; scale them by the
 //      upstream gradient (a device scalar) unless it is exactly 1
-__global__ void scale_bf16_kernel(__nv_bfloat16* x, size_t n, const float* __restrict__ d_loss) {
+struct ScaleSegs { void* p[4]; size_t n[4]; int count; };       // up to four gradient tensors, one launch
+template <class T>
+__global__ void scale_grads_kernel(ScaleSegs sg, const float* __restrict__ d_loss) {
   const float go = *d_loss;
   if (go == 1.f) return;
-  uint4* p = reinterpret_cast<uint4*>(x);
-  const size_t nv = n >> 3, stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
-    uint4 v = p[i];
-    uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+  const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int k = 0; k < sg.count; ++k) {
+    uint4* p = reinterpret_cast<uint4*>(sg.p[k]);
+    const size_t nv = sg.n[k] * sizeof(T) / 16;
+    for (size_t i = t0; i < nv; i += stride) {
+      uint4 v = p[i];
+      uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+      if constexpr (sizeof(T) == 2) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
-      w[k] = pack_bf16x2(f.x * go, f.y * go);
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+          w[j] = pack_bf16x2(f.x * go, f.y * go);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w[j] = __float_as_uint(__uint_as_float(w[j]) * go);
+      }
+      p[i] = v;
     }
-    p[i] = v;
   }
 }
 
