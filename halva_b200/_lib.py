@@ -15,7 +15,7 @@ STATUS_BAD_SIGN, STATUS_K_MISMATCH, STATUS_K_ZERO, STATUS_BAD_LABEL = 1, 2, 4, 8
 EXPORTS = ["dpa_version", "dpa_last_error", "dpa_query_workspace", "dpa_struct_sizes", "dpa_forward", "dpa_backward",
            "dpa_forward_stats", "dpa_forward_finish", "dpa_row_stats_view", "dpa_debug_gemm",
            "dpa_profile_enable", "dpa_profile_collect", "dpa_profile_kind_name", "dpa_set_cta_group",
-           "dpa_comm_unique_id", "dpa_comm_init", "dpa_comm_destroy", "dpa_comm_world", "dpa_tmap_cache_stats", "dpa_plan_host_spans", "dpa_stage_host_batch"]
+           "dpa_comm_unique_id", "dpa_comm_init", "dpa_comm_destroy", "dpa_comm_world", "dpa_tmap_cache_stats", "dpa_plan_host_spans", "dpa_stage_host_batch", "dpa_debug_max_clusters"]
 
 
 class Shape(C.Structure):

@@ -1493,6 +1493,30 @@ int dpa_set_cta_group(int cg) {
   return DPA_OK;
 }
 
+// Probe (profiles/): how many clusters of `cluster_size` CTAs of the 256-wide GEMM kernel (225 KB of shared memory per CTA)
+// can be co-resident on this device -- the cost side of a multicast design with clusters of 4.
+int dpa_debug_max_clusters(int cluster_size) {
+  DeviceInfo* d = nullptr;
+  int rc = device_info(&d);
+  if (rc) return rc;
+  using Cfg = GemmCfg<256, false, KMAJOR, KMAJOR, 2>;
+  auto kern = dpa_gemm_kernel<Cfg, EpiAccumF32<256>>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  if (cluster_size > 8) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(d->sms / cluster_size * cluster_size));
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster_size; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int n = 0;
+  cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+  if (e != cudaSuccess) return fail(DPA_ERR_CUDA, "cudaOccupancyMaxActiveClusters: %s", cudaGetErrorString(e));
+  return n;
+}
+
 int dpa_tmap_cache_stats(long long* hits, long long* misses) {
   if (hits) *hits = g_tmap_hits.load();
   if (misses) *misses = g_tmap_misses.load();

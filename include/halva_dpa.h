@@ -15,7 +15,7 @@
  * Conventions
  *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated otherwise
  *   - the caller owns all memory (inputs, outputs, workspaces); the library allocates nothing persistent
- *   - all calls are asynchronous on `stream` and never synchronise the device on the success path
+ *   - all calls are asynchronous on `stream` and never synchronise the stream or the device on the step path
  *   - return value 0 = OK, negative = dpa_status_t; message via dpa_last_error() (thread local)
  *   - data-dependent errors (bad phrase ids, K_pos != K_neg, K == 0) cannot be seen by the host without a
  *     sync: they are reported in status[0] (device) and turn the losses into NaN, which is also what the
@@ -149,11 +149,18 @@ int dpa_forward_finish(const dpa_args_t* args, const void* gathered_stats, int n
 /* byte size and device address of this rank's merged per-row statistics inside `state` */
 int dpa_row_stats_view(const dpa_args_t* args, void** ptr, size_t* bytes);
 
-/* Optional NCCL communicator for vocab-parallel lm_head (V_local < V).  Once initialised, dpa_forward (statistics path)
- * all-gathers the per-row statistics record of every shard and merges them, and dpa_backward all-reduces the dH partial
- * sums, both on the caller's stream -- one call each way, no caller-side exchange.  NCCL is bound at run time (the copy
- * already loaded in the process, else libnccl.so.2).  Not thread-safe: call once per process at start-up, before
- * dpa_query_workspace (the forward scratch grows by world * record bytes).
+/* Optional communicator for vocab-parallel lm_head (V_local < V): one call each way, no caller-side exchange.
+ *   dpa_forward under DPA_FLAG_FUSED_GRAD: every rank runs the chunked pass on the same rows and its own lm_head rows; the
+ *     per-row statistics of the shards (36 B/row) are pushed into CUDA-IPC peer memory and merged once for the pair segment
+ *     and once per row chunk, the dH partial sums of a chunk are all-reduced in place through peer memory by the library's
+ *     own kernels (packed rows only, row counts read from device memory: no host read-back, no stream synchronisation) and
+ *     scattered; dW stays sharded.  No NCCL call on the step path.
+ *   dpa_forward without DPA_FLAG_FUSED_GRAD (statistics forward + recompute dpa_backward): the statistics record is
+ *     all-gathered with NCCL on the caller's stream, the backward's dH exchange is the same peer-memory one.
+ * NCCL (bound at run time: the copy already loaded in the process, else libnccl.so.2) bootstraps the communicator and the
+ * exchange of the IPC handles.  The symmetric peer buffer (statistics region + one or two dH chunk buffers) is allocated
+ * collectively at first use and when a larger shape arrives -- the only moment the communicator synchronises the device.
+ * Not thread-safe: call once per process at start-up, before dpa_query_workspace.
  *   rank 0:    dpa_comm_unique_id(id)  -> broadcast the 128 bytes by any means ->  every rank: dpa_comm_init(rank, world, id) */
 int dpa_comm_unique_id(void* out_128_bytes);
 int dpa_comm_init(int rank, int world, const void* unique_id_128_bytes);
@@ -197,6 +204,10 @@ int dpa_stage_host_batch(const dpa_host_batch_t* batch, void* cuda_stream, dpa_s
 int dpa_profile_enable(int on);
 int dpa_profile_collect(double* ms, int* launches, int n);
 const char* dpa_profile_kind_name(int k);
+
+/* Probe: co-resident clusters of `cluster_size` CTAs of the 256-wide GEMM kernel on the current device (>= 0), or a negative
+ * dpa_status_t. */
+int dpa_debug_max_clusters(int cluster_size);
 
 /* Encoded TMA descriptors are cached per (device, pointer, dims, stride, box); cumulative hit / miss counts (tests). */
 int dpa_tmap_cache_stats(long long* hits, long long* misses);
