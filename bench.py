@@ -575,13 +575,14 @@ def run_ours(args):
     tokens_step = shape.tokens * (1 if vp else world)
     tps = lambda ms_: round(tokens_step / (ms_ * 1e-3))
 
-    if do_var and need_dw:
+    diag = do_var and world == 1           # single-GPU diagnostics; at N > 1 the line's tail belongs to the multi-GPU variants
+    if diag and need_dw:
         # lm_head frozen (the shipped LoRA recipe, /root/reference/llava/train/train_halva.py:167-168): no dW
         Wf = W.detach()
         step_f = make_step(t, shape, Wf, False, **kw)
         ms_v = cx.time_steps(lambda: step_f(), K)
         variants["lm_head_frozen"] = dict(ms_per_step=round(ms_v, 4), value=tps(ms_v), note="LoRA recipe: no dW GEMM")
-    if do_var and args.backward != "recompute":
+    if diag and args.backward != "recompute":
         # the frozen model's logits GIVEN (dpa_loss(ref_logits=...)): 3 instead of 4 lm_head GEMMs per reference-sample row
         with torch.no_grad():
             zr = torch.empty(shape.B_ref, shape.T_ref, shape.V, dtype=torch.bfloat16, device=dev)
@@ -599,7 +600,7 @@ def run_ours(args):
         variants["ref_logits_given"] = dict(ms_per_step=round(ms_v, 4), value=tps(ms_v), loss=out["l"].item(),
                                             note="frozen logits handed over (cached): 3 instead of 4 lm_head GEMMs per reference row")
         del zr, out
-    if do_var and shape.B % 4 == 0 and shape.B_ref == shape.B and shape.B >= 8:
+    if diag and shape.B % 4 == 0 and shape.B_ref == shape.B and shape.B >= 8:
         # the reference recipe's form of the same 16 pairs: 4 micro-batches of 4 pairs, gradients accumulated
         # (per_device_train_batch_size 4 x gradient_accumulation_steps 4, /root/reference/src/hallava_7b.sh:21-22)
         mb = shape.B // 4
@@ -641,15 +642,29 @@ def run_ours(args):
     if do_var and world == 1:
         variants["fp32_cfg1"] = variant_fp32_cfg1(cx, K, peaks)
     if do_var and world > 1:
-        ms1 = None
+        def guarded(name, fn):
+            # a variant that fails the same way on every rank (e.g. peer memory unavailable) must not cost the whole line
+            try:
+                variants[name] = fn()
+            except Exception as e:  # noqa: BLE001
+                variants[name] = dict(error=repr(e)[:300])
+                torch.cuda.synchronize()
         # rank 0's headline batch IS the fixed batch (seed 1234): its single-GPU time is this run's ms per step
-        variants["strong"] = variant_strong(cx, K, ms_eager / K)
-        variants["vp_cfg3"] = variant_vp(cx, "cfg3", min(K, 10), peaks, args)
-        try:
-            variants["multi_gpu_parity"] = variant_parity(cx)
-        except Exception as e:  # noqa: BLE001
-            variants["multi_gpu_parity"] = dict(ok=False, error=repr(e)[:300])
-        variants["dp_cfg4"] = variant_dp_config(cx, "cfg4", min(K, 10), peaks)
+        guarded("strong", lambda: variant_strong(cx, K, ms_eager / K))
+        guarded("vp_cfg3", lambda: variant_vp(cx, "cfg3", min(K, 10), peaks, args))
+        if "error" in variants["vp_cfg3"] and not args.vp_torch_exchange:
+            # the library-side exchange is unavailable here: the portable form (torch.distributed around the C calls)
+            from halva_b200.dist import destroy_library_comm
+            try:
+                destroy_library_comm()
+            except Exception:  # noqa: BLE001
+                pass
+            args.vp_torch_exchange = True
+            err = variants["vp_cfg3"]["error"]
+            guarded("vp_cfg3", lambda: variant_vp(cx, "cfg3", min(K, 10), peaks, args))
+            variants["vp_cfg3"]["library_exchange_error"] = err
+        guarded("multi_gpu_parity", lambda: variant_parity(cx))
+        guarded("dp_cfg4", lambda: variant_dp_config(cx, "cfg4", min(K, 10), peaks))
 
     if rank != 0:
         if world > 1:

@@ -87,13 +87,18 @@ def test_cfg2_pair_permutation(cfg2):
     assert _rel(b["dW"], a["dW"]) <= 1e-3
 
 
-@pytest.mark.parametrize("cfg,pairs", [("cfg3", 4), ("cfg4", 2)])
+@pytest.mark.parametrize("cfg,pairs", [("cfg3", 4), ("cfg4", 2), ("cfg3", 16), ("cfg4", 8)])
 def test_13b_shapes_vs_reference_op_chain(cfg, pairs):
-    """BASELINE configs[2]/[3] shapes (H 5120; T 4096 with the 196-token VILA image prefix) at a reduced pair count:
-    loss and gradients against the reference's ATen sequence on the same GPU."""
+    """BASELINE configs[2]/[3] shapes (H 5120; T 4096 with the 196-token VILA image prefix): loss and gradients against the
+    reference's ATen sequence on the same GPU -- at a reduced pair count, at cfg-3's FULL batch (16 pairs, 98 K positions)
+    and at half of cfg-4's (8 pairs of T 4096: the same 98 K positions; the op chain's fp32 logits of the full 196 K
+    positions do not fit beside their autograd copies)."""
     from halva_b200 import dpa_loss, read_status
     from halva_b200.synth import CONFIGS, make_inputs
     from oracle import dpa_port
+    torch.cuda.empty_cache()
+    if pairs >= 8 and torch.cuda.mem_get_info()[0] < 100e9:
+        pytest.skip("needs ~100 GB free for the reference op chain at this size")
     shape = dataclasses.replace(CONFIGS[cfg], B=pairs, B_ref=pairs)
     t = make_inputs(shape, seed=99, device="cuda", plant=5.0)
 
@@ -110,6 +115,12 @@ def test_13b_shapes_vs_reference_op_chain(cfg, pairs):
     assert read_status(ours[0])["status"] == 0
     ref = grads(lambda hp, hr, W: dpa_port.dpa_loss_torch(hp, t["labels_pair"], t["signs_pair"], hr, t["h_ref_frz"], t["labels_ref"], W,
                                                           W.detach(), shape.alpha)[0])
-    assert np.isfinite(ref[0].item()) and abs(ours[0].item() - ref[0].item()) <= 1e-3 * abs(ref[0].item())
+    if not np.isfinite(ref[0].item()):
+        # a long phrase overflowed the reference's literal log(1 + exp(N - P)): ours must overflow the same way
+        assert pairs >= 8 and ours[0].item() == ref[0].item(), (ours[0].item(), ref[0].item())
+        return
+    assert abs(ours[0].item() - ref[0].item()) <= 1e-3 * abs(ref[0].item())
     for a, b, name in zip(ours[1:], ref[1:], ("dH_pair", "dH_ref", "dW")):
         assert _rel(a, b) <= 1e-2, (cfg, name, _rel(a, b))
+    del ours, ref
+    torch.cuda.empty_cache()
