@@ -221,6 +221,8 @@ Hints hints_of(const char* name, int dflt) {
 const Hints& hint_stats() { static const Hints h = hints_of("DPA_HINT_STATS", 0); return h; }
 const Hints& hint_dh() { static const Hints h = hints_of("DPA_HINT_DH", 0); return h; }
 const Hints& hint_dw() { static const Hints h = hints_of("DPA_HINT_DW", 0); return h; }
+// K-lockstep interval (k-blocks) of the gradient GEMMs' CTA groups; 0 = off.  DPA_KSYNC overrides.
+int ksync() { static const int v = env_int("DPA_KSYNC", 0); return v; }
 // cta_group of the single-accumulator GEMMs: 2 = CTA pairs on 256 x 256 tiles (default), 1 = one CTA per 128 x 256 tile.
 // Both are compiled; dpa_set_cta_group() / DPA_CTA_GROUP pick one (A/B measurements, bring-up).
 std::atomic<int> g_cta_group{0};
@@ -277,7 +279,7 @@ struct Layout {
   int n_pos_pair, n_pos_ref, cap_pair, cap_ref, nblk_pair, nblk_ref, ng_pair, ng_ref, ldz, chunk_rows, n_chunks;
   int n_slots;      // fused-gradient forward: row chunks whose pair-row logits are KEPT (slot c = chunk c); later chunks reuse slot 0
   // state offsets
-  size_t meta, bitmap, block_counts, src_pair, lab_pair, col_pair, src_ref, act_ref, stats_pair, stats_ref, stats_u,
+  size_t meta, bitmap, sync_ctr, block_counts, src_pair, lab_pair, col_pair, src_ref, act_ref, stats_pair, stats_ref, stats_u,
       lse_pair, logp_pair, lse_ref_p, lse_ref_r, kl_row, PN, sigma, coef_pair, coef_ref, rinv, dnw32, state_total;
   size_t row_stats_bytes;
   // forward scratch offsets
@@ -330,6 +332,7 @@ int make_layout(const dpa_shape_t& s, Layout& L) {
   auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
   L.meta = take(sizeof(DpaMeta));
   L.bitmap = take(16 * 4);
+  L.sync_ctr = take((size_t)2 * L.n_chunks * 4);       // K-lockstep counters of the dH / dW launches (zeroed with DpaMeta)
   L.block_counts = take((size_t)(L.nblk_pair + L.nblk_ref) * 4);
   L.src_pair = take((size_t)L.cap_pair * 4); L.lab_pair = take((size_t)L.cap_pair * 4); L.col_pair = take((size_t)L.cap_pair * 4);
   L.src_ref = take((size_t)L.cap_ref * 4); L.act_ref = take((size_t)L.cap_ref * 4);
@@ -1045,7 +1048,7 @@ struct Plan {
       const int wide = (cta_group() == 2 && grad_bn() == 512) ? 1 : 0;
       // 512-wide tiles: a super-block of 9 row units x all column tiles is one wave of the 74 CTA pairs
       GemmWork w{meta, KIND_DH, ch, L.chunk_rows, 0, s.H, s.V_local, 1, super_m().dh ? super_m().dh : (wide ? 9 : 0), hint_dh().a, hint_dh().b,
-                 slot_of(ch) * L.chunk_rows};
+                 slot_of(ch) * L.chunk_rows, ksync(), at<unsigned>(a->state, L.sync_ctr) + ch};
       if (dH_packed) { int rc = before_dH_chunk(ch); if (rc) return rc; }
       P ep{meta, at<int>(a->state, L.src_pair), at<int>(a->state, L.src_ref),
            static_cast<__nv_bfloat16*>(a->dH_pair), static_cast<__nv_bfloat16*>(a->dH_ref), s.H,
@@ -1064,7 +1067,7 @@ struct Plan {
                                  return (double)((t + p - 1) / p) * (bn / 256); };
       const int wide = (cta_group() == 2 && grad_bn() == 512 && waves(512) <= 1.08 * waves(256)) ? 1 : 0;
       GemmWork w{meta, KIND_DW, ch, L.chunk_rows, s.V_local, s.H, 0, 1, super_m().dw ? super_m().dw : (wide ? 9 : 0), hint_dw().a, hint_dw().b,
-                 slot_of(ch) * L.chunk_rows};
+                 slot_of(ch) * L.chunk_rows, ksync(), at<unsigned>(a->state, L.sync_ctr) + L.n_chunks + ch};
       P ep{meta, ch, L.chunk_rows, dW32, static_cast<__nv_bfloat16*>(a->dW), s.H, s.V_local, s.H};
       ProfScope ps(PK_DW, 1, st);
       return launch_grad<EpiAccumDW, MNMAJOR, MNMAJOR>(st, d, tmDzMN, tmHpMN, w, ep, "dW", wide != 0);
@@ -1343,6 +1346,7 @@ int run_backward(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, cuda
   // peer memory (dpa_peer.cuh; row counts read from DpaMeta on the device, nothing is read back) and scattered.
   const bool vp = comm_active(s);
   if (vp && (rc = p.enable_peer_exchange())) return rc;
+  if (ksync() > 0) CUDA_TRY(cudaMemsetAsync(at<char>(a->state, L.sync_ctr), 0, (size_t)2 * L.n_chunks * 4, st));
   if ((rc = p.coef(a->d_loss))) return rc;
   if ((rc = run_gather(a, L, d, a->scratch, L.b_Hp, L.b_Hf, st))) return rc;
   if (sp && (rc = run_split_weights(a, L, d, *sp, st))) return rc;

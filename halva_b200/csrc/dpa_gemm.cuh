@@ -78,6 +78,12 @@ struct GemmWork {
   int super_m;         // row-tile units per L2 super-block of the unit order (0 = kSuperM)
   int hint_a, hint_b;  // L2 eviction priority of the A / B operand loads: 0 = none, 1 = evict_first, 2 = evict_last
   int dz_row0;         // KIND_DH / KIND_DW: first row of this chunk's slot inside the kept-logits / dz buffer the dz map spans
+  // K-lockstep of the CTA groups of a launch (0 = off): before the producer loads k-block kb with kb % sync_every == 0 it
+  // waits until every group that runs a tile in the same round has reached that k-block.  The groups of a round share
+  // operand panels; held within sync_every (+ the smem ring) k-blocks of each other, the panels' k-slices stay L2-resident
+  // between the first and the last consumer instead of being re-read from DRAM.
+  int sync_every;
+  unsigned* sync_ctr;  // one zero-initialised counter per launch
 };
 
 struct TileRange {
@@ -284,6 +290,26 @@ __device__ __forceinline__ void dpa_gemm_body(const CUtensorMap& tmA, const CUte
           if (pb) { mB = &sm->B[pb - 1]; mB2 = &sm->B2[pb - 1]; }
         }
         for (int kb = 0; kb < tr.k_blocks; ++kb) {
+          if constexpr (NSEG == 1) {
+            if (work.sync_every > 0 && kb % work.sync_every == 0) {
+              // A cumulative-counter barrier over the groups of this round (one tile per unit: tiles_per_unit == 1 launches
+              // only).  Every round before this one was full (static striding), the groups of round r are those with a unit in
+              // it; each leader adds 1 per sync point on arrival and nobody passes point j before all have arrived at it.
+              const int spt = (tr.k_blocks + work.sync_every - 1) / work.sync_every;      // sync points per tile
+              const int round = (u - group_id) / n_cta_groups;
+              const long long target = (long long)round * n_cta_groups * spt +
+                                       (long long)(kb / work.sync_every + 1) * min(n_cta_groups, n_units - round * n_cta_groups);
+              if (elect_one()) {
+                if (leader) atomicAdd(work.sync_ctr, 1u);
+                unsigned spins = 0;
+                while ((long long)*reinterpret_cast<volatile unsigned*>(work.sync_ctr) < target) {
+                  __nanosleep(32);
+                  if (++spins > (1u << 26)) __trap();
+                }
+              }
+              __syncwarp();
+            }
+          }
           mbar_wait(&empty[st], ph ^ 1);
           if (elect_one()) {
             if constexpr (CG == 1) mbar_arrive_expect_tx(&full[st], Cfg::STAGE_BYTES);
