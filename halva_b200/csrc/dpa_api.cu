@@ -221,8 +221,10 @@ Hints hints_of(const char* name, int dflt) {
 const Hints& hint_stats() { static const Hints h = hints_of("DPA_HINT_STATS", 0); return h; }
 const Hints& hint_dh() { static const Hints h = hints_of("DPA_HINT_DH", 0); return h; }
 const Hints& hint_dw() { static const Hints h = hints_of("DPA_HINT_DW", 0); return h; }
-// K-lockstep interval (k-blocks) of the gradient GEMMs' CTA groups; 0 = off.  DPA_KSYNC overrides.
-int ksync() { static const int v = env_int("DPA_KSYNC", 0); return v; }
+// K-lockstep interval (k-blocks) of the CTA groups (GemmWork::sync_every; 0 = off): DPA_KSYNC for the long-K gradient GEMMs,
+// DPA_KSYNC_STATS for the statistics GEMMs (K = H: 64 = once per tile at H 4096).
+int ksync() { static const int v = env_int("DPA_KSYNC", 32); return v; }
+int ksync_stats() { static const int v = env_int("DPA_KSYNC_STATS", 0); return v; }
 // cta_group of the single-accumulator GEMMs: 2 = CTA pairs on 256 x 256 tiles (default), 1 = one CTA per 128 x 256 tile.
 // Both are compiled; dpa_set_cta_group() / DPA_CTA_GROUP pick one (A/B measurements, bring-up).
 std::atomic<int> g_cta_group{0};
@@ -274,6 +276,8 @@ static_assert(kBnPair * kTpuPair == kBnRef * kTpuRef, "both tilings must produce
 // forward).  32768 holds every contributing row of a cfg-2 batch (24.8 K at 10 % phrase density) in ONE chunk: each GEMM class
 // then runs once per step, dW needs no fp32 accumulation pass, and 4 of 6 launch groups of the 16384-row chunking disappear.
 constexpr int kDefaultChunkRows = 32768;
+
+constexpr int kSyncCtrs(int n_chunks) { return 8 * n_chunks + 8; }     // upper bound of GEMM launches per call
 
 struct Layout {
   int n_pos_pair, n_pos_ref, cap_pair, cap_ref, nblk_pair, nblk_ref, ng_pair, ng_ref, ldz, chunk_rows, n_chunks;
@@ -332,7 +336,7 @@ int make_layout(const dpa_shape_t& s, Layout& L) {
   auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
   L.meta = take(sizeof(DpaMeta));
   L.bitmap = take(16 * 4);
-  L.sync_ctr = take((size_t)2 * L.n_chunks * 4);       // K-lockstep counters of the dH / dW launches (zeroed with DpaMeta)
+  L.sync_ctr = take((size_t)kSyncCtrs(L.n_chunks) * 4);   // K-lockstep counters, one per GEMM launch of a call (zeroed with DpaMeta)
   L.block_counts = take((size_t)(L.nblk_pair + L.nblk_ref) * 4);
   L.src_pair = take((size_t)L.cap_pair * 4); L.lab_pair = take((size_t)L.cap_pair * 4); L.col_pair = take((size_t)L.cap_pair * 4);
   L.src_ref = take((size_t)L.cap_ref * 4); L.act_ref = take((size_t)L.cap_ref * 4);
@@ -794,6 +798,13 @@ struct Plan {
   __nv_bfloat16* dz = nullptr; __nv_bfloat16* zr = nullptr; float* dW32 = nullptr;
   float* zp32 = nullptr; float* zr32 = nullptr;      // fp32 inputs, fused-gradient forward: the chunk's kept fp32 logits
   int n_slots = 1;                        // kept-logit slots behind `dz` (fused-gradient forward; 1 elsewhere)
+  int sync_used = 0;                      // K-lockstep counters handed out to this call's GEMM launches
+  unsigned* next_sync() {
+    unsigned* base = at<unsigned>(a->state, L.sync_ctr);
+    const int i = sync_used < kSyncCtrs(L.n_chunks) ? sync_used++ : -1;
+    return i >= 0 ? base + i : nullptr;
+  }
+  void set_sync(GemmWork& w, int every) { w.sync_ctr = every > 0 ? next_sync() : nullptr; w.sync_every = w.sync_ctr ? every : 0; }
   int slot_of(int ch) const { return ch < n_slots ? ch : 0; }
   __nv_bfloat16* dz_of(int ch) const { return dz + (size_t)slot_of(ch) * L.chunk_rows * L.ldz; }
   __nv_bfloat16* dH_packed = nullptr;     // vocab-parallel with the library's communicator: dH rows stay packed until reduced
@@ -919,6 +930,7 @@ struct Plan {
   template <bool ROUND> int fwd_pair(int store_rows) {
     using Epi = EpiStatsPair<kBnPair, ROUND>;
     GemmWork w{meta, KIND_FWD_PAIR, 0, 0, 0, s.V_local, s.H, kTpuPair, super_m().stats, hint_stats().a, hint_stats().b};
+    set_sync(w, ksync_stats());
     typename Epi::Params ep{at<int>(a->state, L.lab_pair), part_pair, L.cap_pair, s.V_local, s.v_offset,
                             store_rows > 0 ? dz : nullptr, L.ldz, store_rows};
     ProfScope ps(PK_FWD_PAIR, 1, st);
@@ -936,6 +948,7 @@ struct Plan {
   template <bool ROUND> int fwd_ref() {
     using Epi = EpiStatsRef<kBnRef, ROUND>;
     GemmWork w{meta, KIND_FWD_REF, 0, 0, 0, s.V_local, s.H, kTpuRef, super_m().stats, hint_stats().a, hint_stats().b};
+    set_sync(w, ksync_stats());
     typename Epi::Params ep{part_ref, part_u, L.cap_ref, s.V_local};
     ProfScope ps(PK_FWD_REF, 1, st);
     if constexpr (!ROUND) {
@@ -952,6 +965,7 @@ struct Plan {
   template <bool ROUND> int dz_pair(int ch) {
     using Epi = EpiDzPair<kBnPair, ROUND>;
     GemmWork w{meta, KIND_DZ_PAIR, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair, super_m().stats, hint_stats().a, hint_stats().b};
+    set_sync(w, ksync_stats());
     typename Epi::Params ep{at<int>(a->state, L.lab_pair), at<float>(a->state, L.lse_pair), at<float>(a->state, L.coef_pair),
                             dz_of(ch), L.ldz, ch * L.chunk_rows, s.V_local, s.v_offset, 0};
     ProfScope ps(PK_DZ_PAIR, 1, st);
@@ -969,6 +983,7 @@ struct Plan {
   template <bool ROUND> int dz_ref(int ch) {
     using Epi = EpiDzRef<kBnRef, ROUND>;
     GemmWork w{meta, KIND_DZ_REF, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuRef, super_m().stats, hint_stats().a, hint_stats().b};
+    set_sync(w, ksync_stats());
     typename Epi::Params ep{meta, at<float>(a->state, L.lse_ref_p), at<float>(a->state, L.lse_ref_r), at<float>(a->state, L.coef_ref),
                             dz, L.ldz, ch * L.chunk_rows, s.V_local, 0};
     ProfScope ps(PK_DZ_REF, 1, st);
@@ -1001,11 +1016,13 @@ struct Plan {
     {
       ProfScope ps(PK_STASH_REF, given ? 1 : 2, st);
       GemmWork wp{meta, KIND_STASH_POL, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair, super_m().stats, hint_stats().a, hint_stats().b};
+    set_sync(wp, ksync_stats());
       typename Epi::Params epp{meta, part2, dz_of(ch), L.cap_ref, s.V_local, L.ldz, ch * L.chunk_rows, 0};
       int rc = launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHp, tmW256, tmW128, wp, epp, "stash_pol");
       if (rc) return rc;
       if (!given) {
         GemmWork wf{meta, KIND_STASH_FRZ, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair, super_m().stats, hint_stats().a, hint_stats().b};
+    set_sync(wf, ksync_stats());
         typename Epi::Params epf{meta, part2, zr, L.cap_ref, s.V_local, L.ldz, ch * L.chunk_rows, 1};
         return launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHf, tmWr256, tmWr128, wf, epf, "stash_frz");
       }
@@ -1048,7 +1065,8 @@ struct Plan {
       const int wide = (cta_group() == 2 && grad_bn() == 512) ? 1 : 0;
       // 512-wide tiles: a super-block of 9 row units x all column tiles is one wave of the 74 CTA pairs
       GemmWork w{meta, KIND_DH, ch, L.chunk_rows, 0, s.H, s.V_local, 1, super_m().dh ? super_m().dh : (wide ? 9 : 0), hint_dh().a, hint_dh().b,
-                 slot_of(ch) * L.chunk_rows, ksync(), at<unsigned>(a->state, L.sync_ctr) + ch};
+                 slot_of(ch) * L.chunk_rows};
+      set_sync(w, ksync());
       if (dH_packed) { int rc = before_dH_chunk(ch); if (rc) return rc; }
       P ep{meta, at<int>(a->state, L.src_pair), at<int>(a->state, L.src_ref),
            static_cast<__nv_bfloat16*>(a->dH_pair), static_cast<__nv_bfloat16*>(a->dH_ref), s.H,
@@ -1067,7 +1085,8 @@ struct Plan {
                                  return (double)((t + p - 1) / p) * (bn / 256); };
       const int wide = (cta_group() == 2 && grad_bn() == 512 && waves(512) <= 1.08 * waves(256)) ? 1 : 0;
       GemmWork w{meta, KIND_DW, ch, L.chunk_rows, s.V_local, s.H, 0, 1, super_m().dw ? super_m().dw : (wide ? 9 : 0), hint_dw().a, hint_dw().b,
-                 slot_of(ch) * L.chunk_rows, ksync(), at<unsigned>(a->state, L.sync_ctr) + L.n_chunks + ch};
+                 slot_of(ch) * L.chunk_rows};
+      set_sync(w, ksync());
       P ep{meta, ch, L.chunk_rows, dW32, static_cast<__nv_bfloat16*>(a->dW), s.H, s.V_local, s.H};
       ProfScope ps(PK_DW, 1, st);
       return launch_grad<EpiAccumDW, MNMAJOR, MNMAJOR>(st, d, tmDzMN, tmHpMN, w, ep, "dW", wide != 0);
@@ -1346,7 +1365,7 @@ int run_backward(const dpa_args_t* a, const Layout& L, const DeviceInfo* d, cuda
   // peer memory (dpa_peer.cuh; row counts read from DpaMeta on the device, nothing is read back) and scattered.
   const bool vp = comm_active(s);
   if (vp && (rc = p.enable_peer_exchange())) return rc;
-  if (ksync() > 0) CUDA_TRY(cudaMemsetAsync(at<char>(a->state, L.sync_ctr), 0, (size_t)2 * L.n_chunks * 4, st));
+  CUDA_TRY(cudaMemsetAsync(at<char>(a->state, L.sync_ctr), 0, (size_t)kSyncCtrs(L.n_chunks) * 4, st));   // (a retained graph may run twice)
   if ((rc = p.coef(a->d_loss))) return rc;
   if ((rc = run_gather(a, L, d, a->scratch, L.b_Hp, L.b_Hf, st))) return rc;
   if (sp && (rc = run_split_weights(a, L, d, *sp, st))) return rc;

@@ -79,9 +79,10 @@ struct GemmWork {
   int hint_a, hint_b;  // L2 eviction priority of the A / B operand loads: 0 = none, 1 = evict_first, 2 = evict_last
   int dz_row0;         // KIND_DH / KIND_DW: first row of this chunk's slot inside the kept-logits / dz buffer the dz map spans
   // K-lockstep of the CTA groups of a launch (0 = off): before the producer loads k-block kb with kb % sync_every == 0 it
-  // waits until every group that runs a tile in the same round has reached that k-block.  The groups of a round share
-  // operand panels; held within sync_every (+ the smem ring) k-blocks of each other, the panels' k-slices stay L2-resident
-  // between the first and the last consumer instead of being re-read from DRAM.
+  // waits until every group that runs a unit in the same round has reached that k-block of that tile.  The groups of a
+  // round share operand panels; held within sync_every (+ the smem ring) k-blocks of each other, a panel's k-slices stay
+  // L2-resident between their first and last consumer instead of being re-read from DRAM -- measured on the long-K gradient
+  // GEMMs: 13.4 -> 5.6 GB read per launch, and the whole (power-bound) step 6 % faster (profiles/r02e_klockstep.md).
   int sync_every;
   unsigned* sync_ctr;  // one zero-initialised counter per launch
 };
@@ -279,8 +280,33 @@ __device__ __forceinline__ void dpa_gemm_body(const CUtensorMap& tmA, const CUte
     for (int u = group_id; u < n_units; u += n_cta_groups) {
       int mu, ng; decode(u, mu, ng);
       const int mt = mu * CG + cta_rank;
-      const int nt_end = min((ng + 1) * tpu, n_tiles);
+      // K-lockstep (GemmWork::sync_every): every unit passes tiles_per_unit x spt sync points -- a unit of the last column
+      // group with fewer tiles still visits the points of its missing tiles -- so a round's barrier arithmetic is uniform.
+      const bool ksync = NSEG == 1 && work.sync_every > 0;
+      const int spt = ksync ? (tr.k_blocks + work.sync_every - 1) / work.sync_every : 0;      // sync points per tile
+      const int round = (u - group_id) / n_cta_groups;
+      const long long sync_base = (long long)round * n_cta_groups * tpu * spt;                 // every earlier round was full
+      const int round_groups = min(n_cta_groups, n_units - round * n_cta_groups);
+      auto k_sync = [&](int point) {
+        // cumulative-counter barrier over the groups of this round: each leader adds 1 per point on arrival, nobody passes
+        // point j before all have arrived at it
+        const long long target = sync_base + (long long)(point + 1) * round_groups;
+        if (elect_one()) {
+          if (leader) atomicAdd(work.sync_ctr, 1u);
+          unsigned spins = 0;
+          while ((long long)*reinterpret_cast<volatile unsigned*>(work.sync_ctr) < target) {
+            __nanosleep(32);
+            if (++spins > (1u << 26)) __trap();
+          }
+        }
+        __syncwarp();
+      };
+      const int nt_end = ksync ? (ng + 1) * tpu : min((ng + 1) * tpu, n_tiles);
       for (int nt = ng * tpu; nt < nt_end; ++nt) {
+       if (nt >= n_tiles) {                         // (ksync only) a missing tile of the last column group: its sync points
+         for (int j = 0; j < spt; ++j) k_sync((nt - ng * tpu) * spt + j);
+         continue;
+       }
 #pragma unroll 1
        for (int seg = 0; seg < NSEG; ++seg) {
         const CUtensorMap* mA = &tmA; const CUtensorMap* mB = &tmB; const CUtensorMap* mA2 = &tmA2; const CUtensorMap* mB2 = &tmB2;
@@ -290,26 +316,7 @@ __device__ __forceinline__ void dpa_gemm_body(const CUtensorMap& tmA, const CUte
           if (pb) { mB = &sm->B[pb - 1]; mB2 = &sm->B2[pb - 1]; }
         }
         for (int kb = 0; kb < tr.k_blocks; ++kb) {
-          if constexpr (NSEG == 1) {
-            if (work.sync_every > 0 && kb % work.sync_every == 0) {
-              // A cumulative-counter barrier over the groups of this round (one tile per unit: tiles_per_unit == 1 launches
-              // only).  Every round before this one was full (static striding), the groups of round r are those with a unit in
-              // it; each leader adds 1 per sync point on arrival and nobody passes point j before all have arrived at it.
-              const int spt = (tr.k_blocks + work.sync_every - 1) / work.sync_every;      // sync points per tile
-              const int round = (u - group_id) / n_cta_groups;
-              const long long target = (long long)round * n_cta_groups * spt +
-                                       (long long)(kb / work.sync_every + 1) * min(n_cta_groups, n_units - round * n_cta_groups);
-              if (elect_one()) {
-                if (leader) atomicAdd(work.sync_ctr, 1u);
-                unsigned spins = 0;
-                while ((long long)*reinterpret_cast<volatile unsigned*>(work.sync_ctr) < target) {
-                  __nanosleep(32);
-                  if (++spins > (1u << 26)) __trap();
-                }
-              }
-              __syncwarp();
-            }
-          }
+          if (ksync && kb % work.sync_every == 0) k_sync((nt - ng * tpu) * spt + kb / work.sync_every);
           mbar_wait(&empty[st], ph ^ 1);
           if (elect_one()) {
             if constexpr (CG == 1) mbar_arrive_expect_tx(&full[st], Cfg::STAGE_BYTES);
