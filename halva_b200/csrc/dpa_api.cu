@@ -804,7 +804,7 @@ struct Plan {
     const int i = sync_used < kSyncCtrs(L.n_chunks) ? sync_used++ : -1;
     return i >= 0 ? base + i : nullptr;
   }
-  void set_sync(GemmWork& w, int every) { w.sync_ctr = every > 0 ? next_sync() : nullptr; w.sync_every = w.sync_ctr ? every : 0; }
+  void set_sync(GemmWork& w, int every) { w.sync_ctr = every != 0 ? next_sync() : nullptr; w.sync_every = w.sync_ctr ? every : 0; }
   int slot_of(int ch) const { return ch < n_slots ? ch : 0; }
   __nv_bfloat16* dz_of(int ch) const { return dz + (size_t)slot_of(ch) * L.chunk_rows * L.ldz; }
   __nv_bfloat16* dH_packed = nullptr;     // vocab-parallel with the library's communicator: dH rows stay packed until reduced

@@ -282,10 +282,12 @@ __device__ __forceinline__ void dpa_gemm_body(const CUtensorMap& tmA, const CUte
       const int mt = mu * CG + cta_rank;
       // K-lockstep (GemmWork::sync_every): every unit passes tiles_per_unit x spt sync points -- a unit of the last column
       // group with fewer tiles still visits the points of its missing tiles -- so a round's barrier arithmetic is uniform.
+      // (sync_every < 0: one sync point per UNIT, at its first k-block -- the cheap form for the short-K statistics GEMMs)
+      const bool usync = NSEG == 1 && work.sync_every < 0;
       const bool ksync = NSEG == 1 && work.sync_every > 0;
       const int spt = ksync ? (tr.k_blocks + work.sync_every - 1) / work.sync_every : 0;      // sync points per tile
       const int round = (u - group_id) / n_cta_groups;
-      const long long sync_base = (long long)round * n_cta_groups * tpu * spt;                 // every earlier round was full
+      const long long sync_base = (long long)round * n_cta_groups * (usync ? 1 : tpu * spt);   // every earlier round was full
       const int round_groups = min(n_cta_groups, n_units - round * n_cta_groups);
       auto k_sync = [&](int point) {
         // cumulative-counter barrier over the groups of this round: each leader adds 1 per point on arrival, nobody passes
@@ -301,6 +303,7 @@ __device__ __forceinline__ void dpa_gemm_body(const CUtensorMap& tmA, const CUte
         }
         __syncwarp();
       };
+      if (usync) k_sync(0);
       const int nt_end = ksync ? (ng + 1) * tpu : min((ng + 1) * tpu, n_tiles);
       for (int nt = ng * tpu; nt < nt_end; ++nt) {
        if (nt >= n_tiles) {                         // (ksync only) a missing tile of the last column group: its sync points
