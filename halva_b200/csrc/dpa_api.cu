@@ -221,10 +221,11 @@ Hints hints_of(const char* name, int dflt) {
 const Hints& hint_stats() { static const Hints h = hints_of("DPA_HINT_STATS", 0); return h; }
 const Hints& hint_dh() { static const Hints h = hints_of("DPA_HINT_DH", 0); return h; }
 const Hints& hint_dw() { static const Hints h = hints_of("DPA_HINT_DW", 0); return h; }
-// K-lockstep interval (k-blocks) of the CTA groups (GemmWork::sync_every; 0 = off): DPA_KSYNC for the long-K gradient GEMMs,
-// DPA_KSYNC_STATS for the statistics GEMMs (K = H: 64 = once per tile at H 4096).
+// K-lockstep of the CTA groups (GemmWork::sync_every; > 0: every so many k-blocks, -1: once per unit, 0: off).  DPA_KSYNC:
+// the long-K gradient GEMMs (32 k-blocks); DPA_KSYNC_STATS: the statistics GEMMs (K = H is only 64 k-blocks per tile: a
+// barrier per tile costs more than it saves, one per five-tile unit pays -- profiles/r02e_klockstep.md).
 int ksync() { static const int v = env_int("DPA_KSYNC", 32); return v; }
-int ksync_stats() { static const int v = env_int("DPA_KSYNC_STATS", 0); return v; }
+int ksync_stats() { static const int v = env_int("DPA_KSYNC_STATS", -1); return v; }
 // cta_group of the single-accumulator GEMMs: 2 = CTA pairs on 256 x 256 tiles (default), 1 = one CTA per 128 x 256 tile.
 // Both are compiled; dpa_set_cta_group() / DPA_CTA_GROUP pick one (A/B measurements, bring-up).
 std::atomic<int> g_cta_group{0};
