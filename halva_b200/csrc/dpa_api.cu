@@ -327,7 +327,10 @@ int make_layout(const dpa_shape_t& s, Layout& L) {
   L.chunk_rows = s.chunk_rows > 0 ? s.chunk_rows : (L.split ? kDefaultChunkRows / 4 : kDefaultChunkRows);
   // a vocabulary shard keeps V_local / V of the logits per row: the same scratch holds proportionally more rows per chunk
   // (8 shards of cfg-3: every row in one chunk -- one statistics exchange per segment, no empty chunk launches)
-  if (s.chunk_rows <= 0 && s.V_local < s.V) L.chunk_rows = (int)std::min<long long>((long long)L.chunk_rows * (s.V / s.V_local), 1 << 20);
+  // (with the library's communicator the factor is the world size: every rank must cut the rows into the SAME chunks even
+  //  when the shards are uneven -- the chunks are the units of the exchanges)
+  if (s.chunk_rows <= 0 && s.V_local < s.V)
+    L.chunk_rows = (int)std::min<long long>((long long)L.chunk_rows * (comm_world > 1 ? comm_world : s.V / s.V_local), 1 << 20);
   if (L.chunk_rows % kRowPad) return fail(DPA_ERR_BAD_SHAPE, "chunk_rows=%d must be a multiple of %d", L.chunk_rows, kRowPad);
   const int cap_tot = L.cap_pair + L.cap_ref;
   L.chunk_rows = std::min(L.chunk_rows, cap_tot);

@@ -87,6 +87,15 @@ def _worker(rank, world, port, out):
         other = [torch.empty_like(fz[2]) for _ in range(world)]
         dist.all_gather(other, fz[2].contiguous())
         assert all(torch.equal(o, other[0]) for o in other)                               # every rank holds bit-identical dH
+        # uneven shards (V = 1016 over 2 ranks: 504 + 512 rows), offsets derived from the shard sizes of all ranks
+        shape_u = dataclasses.replace(shape, V=1016)
+        tu = make_inputs(shape_u, seed=6, device=dev)
+        u0, u1 = vocab_shard_bounds(shape_u.V, world, rank)
+        assert (u1 - u0) != shape_u.V // world or world != 2
+        full_u = run(tu["W"], tu["W"], src=tu)
+        part_u = run(tu["W"][u0:u1].contiguous(), tu["W"][u0:u1].contiguous(), src=tu, vocab_group=dist.group.WORLD)
+        assert abs(part_u[0].item() - full_u[0].item()) <= 1e-5 * abs(full_u[0].item()), (part_u[0].item(), full_u[0].item())
+        assert _rel(part_u[2], full_u[2]) <= 5e-3 and _rel(part_u[3], full_u[3]) <= 5e-3 and _rel(part_u[4], full_u[4][u0:u1]) <= 2e-3
         with torch.no_grad():                                                             # evaluation under vocab parallelism
             le = dpa_loss(t["h_pair"], t["labels_pair"], t["signs_pair"], t["h_ref_pol"], t["labels_ref"], shard()[0],
                           h_ref_frozen=t["h_ref_frz"], W_ref=shard()[1], alpha=t["alpha"], **vkw)[0]
