@@ -364,7 +364,7 @@ def variant_vp(cx, cfg, steps, peaks, args):
     ms = cx.time_steps(lambda: step(), steps)
     f_act = algorithmic_flops(shape, True, st["n_pair_active"], st["n_ref_active"]) / cx.world
     res = dict(config=cfg, ms_per_step=round(ms, 4), value=round(shape.tokens / (ms * 1e-3)), loss=step()[0].item(),
-               tc_frac_active=tc_frac(f_act, ms, peaks), tc_frac_dense=tc_frac(algorithmic_flops(shape, True) / cx.world, ms, peaks),
+               tc_frac_active=tc_frac(f_act, ms, peaks),
                rows=[st["n_pair_active"], st["n_ref_active"]], v_local=v1 - v0,
                exchange="torch.distributed around the C calls" if args.vp_torch_exchange else "library communicator inside the C calls")
     del t, W, step
