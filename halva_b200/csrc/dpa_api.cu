@@ -1129,7 +1129,10 @@ struct Plan {
     const PeerView v = peer_view();
     peer_barrier_kernel<<<1, 32, 0, cs>>>(v, 2 * (ch & 3));
     PeerReduceArgs ra{v, meta, ch, L.chunk_rows, s.H, peer_buf_off(ch)};
-    CUDA_TRY(launch_peer_reduce(ra, d->sms * 2, cs));
+    // blocks of the reduce kernel: it shares the SMs with the dW GEMM's persistent CTAs (registers: 24 K of the GEMM CTA +
+    // 30 K per reduce block of the 64 K of an SM)
+    static const int reduce_blocks = env_int("DPA_PEER_BLOCKS", 0);
+    CUDA_TRY(launch_peer_reduce(ra, reduce_blocks > 0 ? reduce_blocks : d->sms * 2, cs));
     peer_barrier_kernel<<<1, 32, 0, cs>>>(v, 2 * (ch & 3) + 1);
     ScatterChunkArgs sc{meta, ch, L.chunk_rows, at<int>(a->state, L.src_pair), at<int>(a->state, L.src_ref),
                         reinterpret_cast<const __nv_bfloat16*>(g_comm.pm.base + peer_buf_off(ch)),
