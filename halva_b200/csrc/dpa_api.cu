@@ -1129,9 +1129,11 @@ struct Plan {
     const PeerView v = peer_view();
     peer_barrier_kernel<<<1, 32, 0, cs>>>(v, 2 * (ch & 3));
     PeerReduceArgs ra{v, meta, ch, L.chunk_rows, s.H, peer_buf_off(ch)};
-    // blocks of the reduce kernel: it shares the SMs with the dW GEMM's persistent CTAs (registers: 24 K of the GEMM CTA +
-    // 30 K per reduce block of the 64 K of an SM)
-    static const int reduce_blocks = env_int("DPA_PEER_BLOCKS", 0);
+    // Blocks of the reduce kernel: it runs beside the dW GEMM, whose persistent CTAs own every SM -- each reduce block slows
+    // the GEMM CTA it shares an SM with, and the statically scheduled GEMM is as slow as its slowest CTA.  64 blocks saturate
+    // NVLink (the exchange takes the same 1.2 ms with 64, 148 or 296 blocks on 8 GPUs) and cost the GEMM 0.3 ms less
+    // (cfg-3 x 8: step 4.28 -> 4.02 ms; 24 blocks no longer saturate the links).  DPA_PEER_BLOCKS overrides.
+    static const int reduce_blocks = env_int("DPA_PEER_BLOCKS", 64);
     CUDA_TRY(launch_peer_reduce(ra, reduce_blocks > 0 ? reduce_blocks : d->sms * 2, cs));
     peer_barrier_kernel<<<1, 32, 0, cs>>>(v, 2 * (ch & 3) + 1);
     ScatterChunkArgs sc{meta, ch, L.chunk_rows, at<int>(a->state, L.src_pair), at<int>(a->state, L.src_ref),

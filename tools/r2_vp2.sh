@@ -3,7 +3,7 @@
 N=${1:-2}
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533"
-for pb in 0 148 74 32 0 148; do
+for pb in ${PBS:-0 148 74 32 0 148}; do
   timeout 300 env DPA_PEER_BLOCKS=$pb $TR bench.py --gpus $N --config cfg3 --parallelism vp --steps 20 --warmup 5 --no-e2e --no-variants 2>gpurun_out/r2_vp_${N}_pb$pb.err | tail -1 > gpurun_out/r2_vp_${N}_pb$pb.json
   python - <<PY
 import json
