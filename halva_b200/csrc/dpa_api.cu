@@ -226,6 +226,7 @@ const Hints& hint_dw() { static const Hints h = hints_of("DPA_HINT_DW", 0); retu
 // barrier per tile costs more than it saves, one per five-tile unit pays -- profiles/r02e_klockstep.md).
 int ksync() { static const int v = env_int("DPA_KSYNC", 32); return v; }
 int ksync_stats() { static const int v = env_int("DPA_KSYNC_STATS", -1); return v; }
+int ksync_split() { static const int v = env_int("DPA_KSYNC_SPLIT", 0); return v; }     // fp32 inputs: the split gradient GEMMs
 // cta_group of the single-accumulator GEMMs: 2 = CTA pairs on 256 x 256 tiles (default), 1 = one CTA per 128 x 256 tile.
 // Both are compiled; dpa_set_cta_group() / DPA_CTA_GROUP pick one (A/B measurements, bring-up).
 std::atomic<int> g_cta_group{0};
@@ -912,7 +913,8 @@ struct Plan {
   // K-major B operand: bx1 / bx2 = maps whose box holds BN (one CTA) or BN / 2 (CTA pair) rows, with their mid / lo parts
   template <int AMAJ, int BMAJ, class Epi>
   int launch_split(const CUtensorMap& tmA, const CUtensorMap (&tmAS)[2], const CUtensorMap& bx1, const CUtensorMap (&bx1S)[2],
-                   const CUtensorMap& bx2, const CUtensorMap (&bx2S)[2], const GemmWork& w, const typename Epi::Params& ep, const char* what) {
+                   const CUtensorMap& bx2, const CUtensorMap (&bx2S)[2], GemmWork w, const typename Epi::Params& ep, const char* what) {
+    if (ksync_split() == 0) { w.sync_every = 0; w.sync_ctr = nullptr; }      // (K-lockstep of the split kernels: DPA_KSYNC_SPLIT)
     if (split_cg(false) == 2) {
       const SplitMaps sm = split_maps(tmAS, bx2S, tmAS, bx2S);
       return launch_gemm<SplitCfg<AMAJ, BMAJ, 2>, Epi>(st, d->sms, tmA, bx2, tmA, bx2, w, ep, what, &sm);
@@ -921,7 +923,8 @@ struct Plan {
     return launch_gemm<SplitCfg<AMAJ, BMAJ, 1>, Epi>(st, d->sms, tmA, bx1, tmA, bx1, w, ep, what, &sm);
   }
   template <class Epi>
-  int launch_split_dual(const GemmWork& w, const typename Epi::Params& ep, const char* what) {
+  int launch_split_dual(GemmWork w, const typename Epi::Params& ep, const char* what) {
+    if (ksync_split() == 0) { w.sync_every = 0; w.sync_ctr = nullptr; }
     if (split_cg(true) == 2) {
       const SplitMaps sm = split_maps(tmHpS, tmW32S, tmHfS, tmWr32S);
       return launch_gemm<SplitDualCfg<2>, Epi>(st, d->sms, tmHp, tmW32, tmHf, tmWr32, w, ep, what, &sm);
@@ -1049,6 +1052,7 @@ struct Plan {
       {
         using Epi = EpiStoreRows<kBnSplit, float>;
         GemmWork w{meta, KIND_DH, ch, L.chunk_rows, 0, s.H, s.V_local, 1, super_m().dh};
+        set_sync(w, ksync_split());
         typename Epi::Params ep{meta, at<int>(a->state, L.src_pair), at<int>(a->state, L.src_ref),
                                 static_cast<float*>(a->dH_pair), static_cast<float*>(a->dH_ref), s.H, nullptr};
         ProfScope ps(PK_DH, 1, st);
@@ -1058,6 +1062,7 @@ struct Plan {
       if (s.flags & DPA_FLAG_NEED_DW) {
         using Epi = EpiAccumF32<kBnSplit>;
         GemmWork w{meta, KIND_DW, ch, L.chunk_rows, s.V_local, s.H, 0, 1, super_m().dw};
+        set_sync(w, ksync_split());
         typename Epi::Params ep{static_cast<float*>(a->dW), s.H, s.V_local, s.H, ch > 0};
         ProfScope ps(PK_DW, 1, st);
         return launch_split<MNMAJOR, MNMAJOR, Epi>(tmDzMN, tmDzMNS, tmHpMN, tmHpMNS, tmHpMN, tmHpMNS, w, ep, "dW[split]");

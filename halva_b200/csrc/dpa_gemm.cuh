@@ -283,9 +283,10 @@ __device__ __forceinline__ void dpa_gemm_body(const CUtensorMap& tmA, const CUte
       // K-lockstep (GemmWork::sync_every): every unit passes tiles_per_unit x spt sync points -- a unit of the last column
       // group with fewer tiles still visits the points of its missing tiles -- so a round's barrier arithmetic is uniform.
       // (sync_every < 0: one sync point per UNIT, at its first k-block -- the cheap form for the short-K statistics GEMMs)
-      const bool usync = NSEG == 1 && work.sync_every < 0;
-      const bool ksync = NSEG == 1 && work.sync_every > 0;
-      const int spt = ksync ? (tr.k_blocks + work.sync_every - 1) / work.sync_every : 0;      // sync points per tile
+      // (split-bf16 operands: the NSEG K segments of a tile are NSEG passes over the k-blocks, each with its own sync points)
+      const bool usync = work.sync_every < 0;
+      const bool ksync = work.sync_every > 0;
+      const int spt = ksync ? NSEG * ((tr.k_blocks + work.sync_every - 1) / work.sync_every) : 0;   // sync points per tile
       const int round = (u - group_id) / n_cta_groups;
       const long long sync_base = (long long)round * n_cta_groups * (usync ? 1 : tpu * spt);   // every earlier round was full
       const int round_groups = min(n_cta_groups, n_units - round * n_cta_groups);
@@ -319,7 +320,7 @@ __device__ __forceinline__ void dpa_gemm_body(const CUtensorMap& tmA, const CUte
           if (pb) { mB = &sm->B[pb - 1]; mB2 = &sm->B2[pb - 1]; }
         }
         for (int kb = 0; kb < tr.k_blocks; ++kb) {
-          if (ksync && kb % work.sync_every == 0) k_sync((nt - ng * tpu) * spt + kb / work.sync_every);
+          if (ksync && kb % work.sync_every == 0) k_sync((nt - ng * tpu) * spt + seg * (spt / NSEG) + kb / work.sync_every);
           mbar_wait(&empty[st], ph ^ 1);
           if (elect_one()) {
             if constexpr (CG == 1) mbar_arrive_expect_tx(&full[st], Cfg::STAGE_BYTES);
