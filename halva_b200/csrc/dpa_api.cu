@@ -291,14 +291,14 @@ struct Layout {
   // forward scratch offsets
   size_t f_Hp, f_Hf, f_part_pair, f_part_ref, f_part_u, f_gather, fwd_total;
   // backward scratch offsets
-  size_t b_Hp, b_Hf, b_dz, b_dW32, b_dHp, bwd_total;
+  size_t b_Hp, b_Hf, b_dz, b_dW32, bwd_total;
   // fp32 inputs (split-bf16 operands): Hp / Hf / dz hold three parts (hi, mid, lo) one after the other, and the lm_head
   // weights are split into scratch as well (three parts each)
   struct Split { size_t W3, Wr3; } f_split, b_split, u_split;
   size_t u_zp32;    // fp32 inputs, fused-gradient forward: kept fp32 policy logits of the chunk (u_zr then holds fp32 too)
   bool split;
   // fused-gradient forward scratch offsets (DPA_FLAG_FUSED_GRAD)
-  size_t u_Hp, u_Hf, u_part_pair, u_part_ref, u_part_u, u_dz, u_zr, u_dW32, u_gather, fused_total;
+  size_t u_Hp, u_Hf, u_part_pair, u_part_ref, u_part_u, u_dz, u_zr, u_dW32, fused_total;
 };
 
 int g_layout_comm_world = 1;   // set by dpa_comm_init / dpa_comm_destroy (declared before the communicator itself)
@@ -383,7 +383,7 @@ int make_layout(const dpa_shape_t& s, Layout& L) {
   L.b_dz = take(parts * L.chunk_rows * L.ldz * 2);
   L.b_dW32 = ((s.flags & DPA_FLAG_NEED_DW) && !L.split) ? take((size_t)s.V_local * s.H * 4) : o;   // fp32: dW itself accumulates
   take_split(L.b_split);
-  L.b_dHp = o;    // (library-side vocab-parallel exchange: the packed dH partial sums live in the communicator's peer memory)
+  // (library-side vocab-parallel exchange: the packed dH partial sums live in the communicator's peer memory)
   L.bwd_total = o;
 
   o = 0;
@@ -402,7 +402,7 @@ int make_layout(const dpa_shape_t& s, Layout& L) {
   L.u_zp32 = L.split ? take((size_t)L.chunk_rows * L.ldz * 4) : o;
   L.u_dW32 = ((s.flags & DPA_FLAG_NEED_DW) && !L.split) ? take((size_t)s.V_local * s.H * 4) : o;
   take_split(L.u_split);
-  L.u_gather = o;                       // (library-side exchange: the shards' statistics records meet in peer memory)
+  // (library-side exchange: the shards' statistics records meet in peer memory, not in this scratch)
   L.fused_total = o;
   return DPA_OK;
 }
