@@ -225,7 +225,8 @@ const Hints& hint_dw() { static const Hints h = hints_of("DPA_HINT_DW", 0); retu
 // the long-K gradient GEMMs (32 k-blocks); DPA_KSYNC_STATS: the statistics GEMMs (K = H is only 64 k-blocks per tile: a
 // barrier per tile costs more than it saves, one per five-tile unit pays -- profiles/r02e_klockstep.md).
 int ksync() { static const int v = env_int("DPA_KSYNC", 32); return v; }
-int ksync_stats() { static const int v = env_int("DPA_KSYNC_STATS", -1); return v; }
+// (units of a single tile -- small vocabulary shards, see tiles_per_unit() -- would pay that barrier per tile: off there)
+int ksync_stats(int tpu) { static const int v = env_int("DPA_KSYNC_STATS", -2); return v != -2 ? v : (tpu >= 4 ? -1 : 0); }
 int ksync_split() { static const int v = env_int("DPA_KSYNC_SPLIT", 0); return v; }     // fp32 inputs: the split gradient GEMMs
 // cta_group of the single-accumulator GEMMs: 2 = CTA pairs on 256 x 256 tiles (default), 1 = one CTA per 128 x 256 tile.
 // Both are compiled; dpa_set_cta_group() / DPA_CTA_GROUP pick one (A/B measurements, bring-up).
@@ -269,10 +270,18 @@ int launch_dual(cudaStream_t st, const DeviceInfo* d, const CUtensorMap& tmA, co
 }
 
 // ---------------------------------------------------------------------------------- workspace layout
-constexpr int kTpuPair = 5;     // 256-wide column tiles per unit  (V=32000: 125 tiles -> 25 groups)
-constexpr int kTpuRef = 10;     // 128-wide column tiles per unit  (V=32000: 250 tiles -> 25 groups)
+// Column tiles per work unit of the statistics GEMMs.  A unit = (256-row tile, `tpu` consecutive 256-wide column tiles) and
+// leaves one partial-statistics record per row; the units are dealt to the CTA pairs round-robin.  Full vocabulary
+// (V = 32000: 125 tiles): 5 tiles per unit -> 25 column groups, small partial arrays, 24 even rounds.  A vocabulary SHARD
+// has few tiles (V / 8 = 4000: 16): groups of 5 would be 5 + 5 + 5 + 1 tiles and the pair with the most work would run 20
+// tiles against an average of 15.4 (cfg-3 x 8) -- single-tile units deal the same work out to within one tile.
+// The 128-wide (dual) and the split-bf16 tilings use the same column groups (shared partials): 2x / 4x as many tiles.
 constexpr int kBnPair = 256, kBnRef = 128;
-static_assert(kBnPair * kTpuPair == kBnRef * kTpuRef, "both tilings must produce the same column groups (shared partials)");
+int tiles_per_unit(int v_local) {
+  const int forced = env_int("DPA_TPU", 0);             // measurements / tests; read per call so that a test can switch it
+  if (forced > 0) return std::min(forced, 64);
+  return (v_local + kBnPair - 1) / kBnPair <= 40 ? 1 : 5;
+}
 
 // Rows per chunk of the packed row space (kept logits / dLogits scratch = chunk_rows x V x 2 B, twice in the fused-gradient
 // forward).  32768 holds every contributing row of a cfg-2 batch (24.8 K at 10 % phrase density) in ONE chunk: each GEMM class
@@ -283,6 +292,7 @@ constexpr int kSyncCtrs(int n_chunks) { return 8 * n_chunks + 8; }     // upper 
 
 struct Layout {
   int n_pos_pair, n_pos_ref, cap_pair, cap_ref, nblk_pair, nblk_ref, ng_pair, ng_ref, ldz, chunk_rows, n_chunks;
+  int tpu;          // 256-wide column tiles per unit of the statistics GEMMs (tiles_per_unit)
   int n_slots;      // fused-gradient forward: row chunks whose pair-row logits are KEPT (slot c = chunk c); later chunks reuse slot 0
   // state offsets
   size_t meta, bitmap, sync_ctr, block_counts, src_pair, lab_pair, col_pair, src_ref, act_ref, stats_pair, stats_ref, stats_u,
@@ -321,8 +331,9 @@ int make_layout(const dpa_shape_t& s, Layout& L) {
   L.cap_ref = round_up_i(L.n_pos_ref, kRowPad);
   L.nblk_pair = (L.n_pos_pair + kScanBlock - 1) / kScanBlock;
   L.nblk_ref = (L.n_pos_ref + kScanBlock - 1) / kScanBlock;
-  L.ng_pair = ((s.V_local + kBnPair - 1) / kBnPair + kTpuPair - 1) / kTpuPair;
-  L.ng_ref = ((s.V_local + kBnRef - 1) / kBnRef + kTpuRef - 1) / kTpuRef;
+  L.tpu = tiles_per_unit(s.V_local);
+  L.ng_pair = ((s.V_local + kBnPair - 1) / kBnPair + L.tpu - 1) / L.tpu;
+  L.ng_ref = ((s.V_local + kBnRef - 1) / kBnRef + 2 * L.tpu - 1) / (2 * L.tpu);      // == ng_pair: the same column groups
   L.ldz = round_up_i(s.V_local, 64);
   // (fp32 inputs keep 14 B per logit of a chunk -- two fp32 logit buffers and a split-bf16 dLogits triple -- so their default chunk is smaller)
   L.chunk_rows = s.chunk_rows > 0 ? s.chunk_rows : (L.split ? kDefaultChunkRows / 4 : kDefaultChunkRows);
@@ -898,7 +909,10 @@ struct Plan {
   // split-bf16 GEMM configurations (fp32 inputs): 128-column accumulators (the K-chunk promotion keeps them in registers);
   // the column groups of the statistics stay the 1280 columns of the bf16 tilings
   static constexpr int kBnSplit = 128, kBnSplitDual = 64;
-  static constexpr int kTpuSplit = kBnPair * kTpuPair / kBnSplit, kTpuSplitDual = kBnRef * kTpuRef / kBnSplitDual;
+  int tpu_pair() const { return L.tpu; }                                  // tiles per unit of each tiling: the same columns
+  int tpu_ref() const { return L.tpu * (kBnPair / kBnRef); }
+  int tpu_split() const { return L.tpu * (kBnPair / kBnSplit); }
+  int tpu_split_dual() const { return L.tpu * (kBnPair / kBnSplitDual); }
   template <int AMAJ, int BMAJ, int CG> using SplitCfg = GemmCfg<kBnSplit, false, AMAJ, BMAJ, CG, 6>;
   template <int CG> using SplitDualCfg = GemmCfg<kBnSplitDual, true, KMAJOR, KMAJOR, CG, 6>;
   // cta_group of the split kernels: 2 (default) = CTA pairs on 256-row tiles, each CTA staging half of the B tile -- less
@@ -936,15 +950,15 @@ struct Plan {
   // statistics of every pair row; store_rows > 0 also keeps the bf16 logits of the first store_rows packed rows in dz
   template <bool ROUND> int fwd_pair(int store_rows) {
     using Epi = EpiStatsPair<kBnPair, ROUND>;
-    GemmWork w{meta, KIND_FWD_PAIR, 0, 0, 0, s.V_local, s.H, kTpuPair, super_m().stats, hint_stats().a, hint_stats().b};
-    set_sync(w, ksync_stats());
+    GemmWork w{meta, KIND_FWD_PAIR, 0, 0, 0, s.V_local, s.H, tpu_pair(), super_m().stats, hint_stats().a, hint_stats().b};
+    set_sync(w, ksync_stats(L.tpu));
     typename Epi::Params ep{at<int>(a->state, L.lab_pair), part_pair, L.cap_pair, s.V_local, s.v_offset,
                             store_rows > 0 ? dz : nullptr, L.ldz, store_rows};
     ProfScope ps(PK_FWD_PAIR, 1, st);
     if constexpr (!ROUND) {
       if (split) {
         using EpiS = EpiStatsPair<kBnSplit, false, float>;
-        GemmWork ws = w; ws.tiles_per_unit = kTpuSplit;
+        GemmWork ws = w; ws.tiles_per_unit = tpu_split();
         typename EpiS::Params eps{ep.labels, ep.part, ep.row_cap, ep.v_local, ep.v_offset, store_rows > 0 ? zp32 : nullptr, L.ldz, store_rows};
         return launch_split<KMAJOR, KMAJOR, EpiS>(tmHp, tmHpS, tmW128, tmW128S, tmW64, tmW64S, ws, eps, "fwd_pair[split]");
       }
@@ -954,14 +968,14 @@ struct Plan {
   // policy + frozen logits of every reference-sample row side by side: statistics incl. the KL numerator
   template <bool ROUND> int fwd_ref() {
     using Epi = EpiStatsRef<kBnRef, ROUND>;
-    GemmWork w{meta, KIND_FWD_REF, 0, 0, 0, s.V_local, s.H, kTpuRef, super_m().stats, hint_stats().a, hint_stats().b};
-    set_sync(w, ksync_stats());
+    GemmWork w{meta, KIND_FWD_REF, 0, 0, 0, s.V_local, s.H, tpu_ref(), super_m().stats, hint_stats().a, hint_stats().b};
+    set_sync(w, ksync_stats(L.tpu));
     typename Epi::Params ep{part_ref, part_u, L.cap_ref, s.V_local};
     ProfScope ps(PK_FWD_REF, 1, st);
     if constexpr (!ROUND) {
       if (split) {
         using EpiS = EpiStatsRef<kBnSplitDual, false>;
-        GemmWork ws = w; ws.tiles_per_unit = kTpuSplitDual;
+        GemmWork ws = w; ws.tiles_per_unit = tpu_split_dual();
         typename EpiS::Params eps{part_ref, part_u, L.cap_ref, s.V_local};
         return launch_split_dual<EpiS>(ws, eps, "fwd_ref[split]");
       }
@@ -971,15 +985,15 @@ struct Plan {
   // recompute the pair rows of chunk ch -> dz
   template <bool ROUND> int dz_pair(int ch) {
     using Epi = EpiDzPair<kBnPair, ROUND>;
-    GemmWork w{meta, KIND_DZ_PAIR, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair, super_m().stats, hint_stats().a, hint_stats().b};
-    set_sync(w, ksync_stats());
+    GemmWork w{meta, KIND_DZ_PAIR, ch, L.chunk_rows, 0, s.V_local, s.H, tpu_pair(), super_m().stats, hint_stats().a, hint_stats().b};
+    set_sync(w, ksync_stats(L.tpu));
     typename Epi::Params ep{at<int>(a->state, L.lab_pair), at<float>(a->state, L.lse_pair), at<float>(a->state, L.coef_pair),
                             dz_of(ch), L.ldz, ch * L.chunk_rows, s.V_local, s.v_offset, 0};
     ProfScope ps(PK_DZ_PAIR, 1, st);
     if constexpr (!ROUND) {
       if (split) {
         using EpiS = EpiDzPair<kBnSplit, false, true>;
-        GemmWork ws = w; ws.tiles_per_unit = kTpuSplit;
+        GemmWork ws = w; ws.tiles_per_unit = tpu_split();
         typename EpiS::Params eps{ep.labels, ep.lse, ep.coef, dz, L.ldz, ch * L.chunk_rows, s.V_local, s.v_offset, dz_part};
         return launch_split<KMAJOR, KMAJOR, EpiS>(tmHp, tmHpS, tmW128, tmW128S, tmW64, tmW64S, ws, eps, "dz_pair[split]");
       }
@@ -989,15 +1003,15 @@ struct Plan {
   // recompute the reference-sample rows of chunk ch (both models) -> dz
   template <bool ROUND> int dz_ref(int ch) {
     using Epi = EpiDzRef<kBnRef, ROUND>;
-    GemmWork w{meta, KIND_DZ_REF, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuRef, super_m().stats, hint_stats().a, hint_stats().b};
-    set_sync(w, ksync_stats());
+    GemmWork w{meta, KIND_DZ_REF, ch, L.chunk_rows, 0, s.V_local, s.H, tpu_ref(), super_m().stats, hint_stats().a, hint_stats().b};
+    set_sync(w, ksync_stats(L.tpu));
     typename Epi::Params ep{meta, at<float>(a->state, L.lse_ref_p), at<float>(a->state, L.lse_ref_r), at<float>(a->state, L.coef_ref),
                             dz, L.ldz, ch * L.chunk_rows, s.V_local, 0};
     ProfScope ps(PK_DZ_REF, 1, st);
     if constexpr (!ROUND) {
       if (split) {
         using EpiS = EpiDzRef<kBnSplitDual, false, true>;
-        GemmWork ws = w; ws.tiles_per_unit = kTpuSplitDual;
+        GemmWork ws = w; ws.tiles_per_unit = tpu_split_dual();
         typename EpiS::Params eps{meta, ep.lse_p, ep.lse_r, ep.coef, dz, L.ldz, ch * L.chunk_rows, s.V_local, dz_part};
         return launch_split_dual<EpiS>(ws, eps, "dz_ref[split]");
       }
@@ -1012,24 +1026,24 @@ struct Plan {
     if (split) {              // fp32 inputs: the same two GEMMs on split-bf16 operands, fp32 logits kept
       using EpiS = EpiStatsStore<kBnSplit, float>;
       ProfScope ps(PK_STASH_REF, 2, st);
-      GemmWork wp{meta, KIND_STASH_POL, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuSplit, super_m().stats};
+      GemmWork wp{meta, KIND_STASH_POL, ch, L.chunk_rows, 0, s.V_local, s.H, tpu_split(), super_m().stats};
       typename EpiS::Params epp{meta, part2, zp32, L.cap_ref, s.V_local, L.ldz, ch * L.chunk_rows, 0};
       int rc = launch_split<KMAJOR, KMAJOR, EpiS>(tmHp, tmHpS, tmW128, tmW128S, tmW64, tmW64S, wp, epp, "stash_pol[split]");
       if (rc) return rc;
-      GemmWork wf{meta, KIND_STASH_FRZ, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuSplit, super_m().stats};
+      GemmWork wf{meta, KIND_STASH_FRZ, ch, L.chunk_rows, 0, s.V_local, s.H, tpu_split(), super_m().stats};
       typename EpiS::Params epf{meta, part2, zr32, L.cap_ref, s.V_local, L.ldz, ch * L.chunk_rows, 1};
       return launch_split<KMAJOR, KMAJOR, EpiS>(tmHf, tmHfS, tmWr128, tmWr128S, tmWr64, tmWr64S, wf, epf, "stash_frz[split]");
     }
     {
       ProfScope ps(PK_STASH_REF, given ? 1 : 2, st);
-      GemmWork wp{meta, KIND_STASH_POL, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair, super_m().stats, hint_stats().a, hint_stats().b};
-    set_sync(wp, ksync_stats());
+      GemmWork wp{meta, KIND_STASH_POL, ch, L.chunk_rows, 0, s.V_local, s.H, tpu_pair(), super_m().stats, hint_stats().a, hint_stats().b};
+    set_sync(wp, ksync_stats(L.tpu));
       typename Epi::Params epp{meta, part2, dz_of(ch), L.cap_ref, s.V_local, L.ldz, ch * L.chunk_rows, 0};
       int rc = launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHp, tmW256, tmW128, wp, epp, "stash_pol");
       if (rc) return rc;
       if (!given) {
-        GemmWork wf{meta, KIND_STASH_FRZ, ch, L.chunk_rows, 0, s.V_local, s.H, kTpuPair, super_m().stats, hint_stats().a, hint_stats().b};
-    set_sync(wf, ksync_stats());
+        GemmWork wf{meta, KIND_STASH_FRZ, ch, L.chunk_rows, 0, s.V_local, s.H, tpu_pair(), super_m().stats, hint_stats().a, hint_stats().b};
+    set_sync(wf, ksync_stats(L.tpu));
         typename Epi::Params epf{meta, part2, zr, L.cap_ref, s.V_local, L.ldz, ch * L.chunk_rows, 1};
         return launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHf, tmWr256, tmWr128, wf, epf, "stash_frz");
       }
@@ -1039,7 +1053,7 @@ struct Plan {
   // the frozen model's logits are given (dpa_args_t::ref_logits): copy the chunk's rows + their statistics, no GEMM
   int stash_given(int ch, float2* part2) {
     StashGivenArgs g{meta, ch, L.chunk_rows, a->ref_logits, (long long)a->ref_logits_ld, at<int>(a->state, L.src_ref),
-                     at<int>(a->state, L.act_ref), zr, L.ldz, s.V_local, part2, L.cap_ref, L.ng_pair, kBnPair * kTpuPair};
+                     at<int>(a->state, L.act_ref), zr, L.ldz, s.V_local, part2, L.cap_ref, L.ng_pair, kBnPair * L.tpu};
     ProfScope pg(PK_STASH_GIVEN, 1, st);
     if (a->ref_logits_dtype == DPA_F32) stash_given_kernel<true><<<d->sms * 8, 256, 0, st>>>(g);
     else stash_given_kernel<false><<<d->sms * 8, 256, 0, st>>>(g);
@@ -1071,7 +1085,10 @@ struct Plan {
     }
     {
       using P = typename EpiStoreRows<256>::Params;
-      const int wide = (cta_group() == 2 && grad_bn() == 512) ? 1 : 0;
+      // 512-wide tiles have one accumulator stage, so their epilogue is not hidden: they pay for long K only.  K = V_local of a
+      // small vocabulary shard is short (V / 8 = 4000: 63 k-blocks) -- there the double-buffered 256-wide tiles are 6 % faster
+      // (tools/r2_tpu.sh: dH 0.775 -> 0.73 ms at the cfg-3 x 8 shard shape).
+      const int wide = (cta_group() == 2 && grad_bn() == 512 && s.V_local > 8192) ? 1 : 0;
       // 512-wide tiles: a super-block of 9 row units x all column tiles is one wave of the 74 CTA pairs
       GemmWork w{meta, KIND_DH, ch, L.chunk_rows, 0, s.H, s.V_local, 1, super_m().dh ? super_m().dh : (wide ? 9 : 0), hint_dh().a, hint_dh().b,
                  slot_of(ch) * L.chunk_rows};
@@ -1082,7 +1099,7 @@ struct Plan {
            dH_packed ? reinterpret_cast<__nv_bfloat16*>(g_comm.pm.base + peer_buf_off(ch)) : nullptr, ch * L.chunk_rows};
       {
         ProfScope ps(PK_DH, 1, st);
-        int rc = launch_grad<EpiStoreRowsBf16, KMAJOR, MNMAJOR>(st, d, tmDzK, tmWmn, w, ep, "dH");
+        int rc = launch_grad<EpiStoreRowsBf16, KMAJOR, MNMAJOR>(st, d, tmDzK, tmWmn, w, ep, "dH", wide != 0);
         if (rc) return rc;
       }
       if (dH_packed) { int rc = exchange_dH_chunk(ch); if (rc) return rc; }

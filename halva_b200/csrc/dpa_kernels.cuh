@@ -640,7 +640,8 @@ __global__ void __launch_bounds__(256) stash_given_kernel(StashGivenArgs a) {
   const int c_lo = a.chunk * a.chunk_rows;
   const int lo = max(c_lo, p0), hi = min(c_lo + a.chunk_rows, n_tot);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  constexpr int kSteps = 5;                          // 5 x 256 columns = one 1280-column group
+  constexpr int kSteps = 5;                          // up to 5 x 256 columns = one column group of the statistics GEMMs
+  const int steps = a.group_cols / 256;              // (1 for a small vocabulary shard: single-tile units)
   for (int r = lo + blockIdx.x; r < hi; r += gridDim.x) {
     const int j = r - p0;
     if (!a.act_ref[j]) {                             // padding / ignored rows: finite dummies, never used (coef == 0)
@@ -656,6 +657,11 @@ __global__ void __launch_bounds__(256) stash_given_kernel(StashGivenArgs a) {
       for (int i = 0; i < kSteps; ++i) {
         const int col = g * a.group_cols + i * 256 + lane * 8;
         float* x = v + i * 8;
+        if (i >= steps) {                              // past this (narrower) group
+#pragma unroll
+          for (int k = 0; k < 8; ++k) x[k] = -INFINITY;
+          continue;
+        }
         if (col + 8 <= a.v_local) {
           if constexpr (F32) {
             const float4* q = reinterpret_cast<const float4*>(static_cast<const float*>(a.logits) + src + col);

@@ -52,6 +52,8 @@ CONFIGS = {
     "cfg2": DPAShape(B=16, T=2048, H=4096, V=32000, alpha=0.4),
     "cfg3": DPAShape(B=16, T=2048, H=5120, V=32000, alpha=0.5),
     "cfg4": DPAShape(B=16, T=4096, H=5120, V=32000, alpha=0.2, n_img=196),
+    # one rank's GEMM shapes of cfg3 under 8-way vocabulary sharding (V / 8 columns), without the exchange: kernel probes
+    "cfg3_shard8": DPAShape(B=16, T=2048, H=5120, V=4000, alpha=0.5),
     "tiny": DPAShape(B=2, T=48, H=64, V=512, n_sys=3, n_img=8, n_q=3, k_max=3, density=0.2),
     "small": DPAShape(B=2, T=160, H=256, V=1000, n_sys=5, n_img=24, n_q=6, k_max=4, density=0.15),
 }

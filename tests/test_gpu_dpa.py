@@ -123,6 +123,37 @@ def test_synthetic_shapes_vs_oracle(over):
             assert rel(c[k], o[k]) <= TOL_GRAD_BF16, (bwd, k, rel(c[k], o[k]))
 
 
+@pytest.mark.parametrize("tpu", ["1", "2", "5"])
+@pytest.mark.parametrize("over", [dict(V=3001, H=128), dict(V=1288, H=64, T=129, T_ref=77)])
+def test_column_group_width_invariance(over, tpu, monkeypatch):
+    """Work units of the statistics GEMMs: 1 (small vocabulary shards), 2 or 5 (full vocabulary) column tiles per unit -- incl.
+    a ragged last group (V=3001: 12 tiles = 5 + 5 + 2) -- give the same losses and gradients, in every input form."""
+    monkeypatch.setenv("DPA_TPU", tpu)
+    t, shape = _synth(**over)
+    o = _oracle(t, "bf16")
+    for kw in (dict(backward="fused"), dict(backward="recompute"), dict(backward="fused", dense=True, chunk_rows=256)):
+        c = _run_cuda(t, **kw)
+        assert _close(c["loss"], o["loss"], TOL_LOSS_BF16) and _close(c["div"], o["div"], TOL_LOSS_BF16), kw
+        for k in ("dH_pair", "dH_ref", "dW"):
+            assert rel(c[k], o[k]) <= TOL_GRAD_BF16, (kw, k, rel(c[k], o[k]))
+    # frozen logits given: the copy kernel produces the partials of the same column groups
+    from halva_b200 import dpa_loss
+    zr = (t["h_ref_frz"].float() @ t["W_ref"].float().T).to(torch.bfloat16)
+    hp = t["h_pair"].clone().requires_grad_(True)
+    loss, _, div = dpa_loss(hp, t["labels_pair"], t["signs_pair"], t["h_ref_pol"], t["labels_ref"], t["W"], ref_logits=zr, alpha=t["alpha"])
+    loss.backward()
+    assert _close(loss.item(), o["loss"], TOL_LOSS_BF16) and _close(div.item(), o["div"], TOL_LOSS_BF16)
+    assert rel(hp.grad.float().cpu().numpy(), o["dH_pair"]) <= TOL_GRAD_BF16
+    # fp32 inputs: the split-bf16 tilings share the column groups
+    f32 = {k: (v.float() if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in t.items()}
+    hp32 = f32["h_pair"].clone().requires_grad_(True)
+    l32, _, _ = dpa_loss(hp32, f32["labels_pair"], f32["signs_pair"], f32["h_ref_pol"], f32["labels_ref"], f32["W"],
+                         h_ref_frozen=f32["h_ref_frz"], alpha=t["alpha"])
+    l32.backward()
+    o64 = _oracle(t, "fp64")
+    assert _close(l32.item(), o64["loss"], 1e-5) and rel(hp32.grad.cpu().numpy(), o64["dH_pair"]) <= 1e-4
+
+
 def test_no_reference_labels_and_single_position():
     """Every reference-sample label ignored -> divergence exactly 0 and no reference-sample gradient (the reference sums an
     all-masked tensor); T = 2 leaves one predicting position per sequence."""
