@@ -704,7 +704,7 @@ def run_ours(args):
     # launches of the dominant class that had rows to process: the library launches every row chunk of the (host-known)
     # capacity, the chunks past the (device-known) active row count return at once (~5 us each)
     pad = lambda n: -(-n // 256) * 256
-    chunk_rows = args.chunk_rows or _lib.default_chunk_rows()
+    chunk_rows = args.chunk_rows or _lib.default_chunk_rows(2 * shape.B * (shape.T - 1), shape.B_ref * (shape.T_ref - 1))
     chunks_active = max(1, -(-(pad(n_p) + pad(n_r)) // chunk_rows))
     per_chunk = {"stash_ref": 2}.get(dom, 1)
     n_launch_dom = float(per_chunk * (1 if dom in ("fwd_pair", "fwd_ref") else chunks_active))

@@ -111,9 +111,12 @@ def check(rc: int, what: str):
 DEFAULT_CHUNK_ROWS = 32768
 
 
-def default_chunk_rows() -> int:
-    """Rows per chunk of the packed row space when dpa_shape_t::chunk_rows is 0 (include/halva_dpa.h)."""
-    return DEFAULT_CHUNK_ROWS
+def default_chunk_rows(n_pos_pair: int = 0, n_pos_ref: int = 0) -> int:
+    """Rows per chunk of the packed row space when dpa_shape_t::chunk_rows is 0 (include/halva_dpa.h) for a bf16 batch with
+    `n_pos_pair` = 2B(T-1) and `n_pos_ref` = B_ref(T_ref-1) predicting positions: twice the default beyond four default
+    chunks of positions (the rule of make_layout in csrc/dpa_api.cu)."""
+    pad = lambda n: -(-n // 256) * 256
+    return DEFAULT_CHUNK_ROWS * (2 if pad(n_pos_pair) + pad(n_pos_ref) > 4 * DEFAULT_CHUNK_ROWS else 1)
 
 
 def set_cta_group(cg: int):

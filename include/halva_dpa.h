@@ -81,7 +81,8 @@ typedef struct {
   int32_t dtype;      /* dpa_dtype_t of h_*, W, W_ref, dH_*, dW */
   int32_t index_dtype;/* dpa_index_t of labels / signs */
   int32_t flags;      /* DPA_FLAG_* */
-  int32_t chunk_rows; /* row chunk of the packed row space (multiple of 256); 0 = default (32768) */
+  int32_t chunk_rows; /* row chunk of the packed row space (multiple of 256); 0 = default (32768; 65536 for batches
+                         of more than 131072 positions; fp32 inputs 8192; times V / V_local for a vocabulary shard) */
 } dpa_shape_t;
 
 typedef struct {
