@@ -619,10 +619,10 @@ def run_ours(args):
                 m["h_ref_pol"].grad = None
                 l, _, _ = dpa_loss(m["h_pair"], m["labels_pair"], m["signs_pair"], m["h_ref_pol"], m["labels_ref"], W,
                                    h_ref_frozen=m["h_ref_frz"], alpha=shape.alpha, dense=args.dense, chunk_rows=args.chunk_rows,
-                                   backward=args.backward)
+                                   backward=args.backward, grad_scale_hint=0.25)
                 (l / 4).backward()                       # W.grad accumulates over the micro-batches, as under grad accumulation
         ms_v = cx.time_steps(step_micro, K)
-        variants["micro_4x4"] = dict(ms_per_step=round(ms_v, 4), value=tps(ms_v), note="4 micro-batches of B/4 pairs, dW accumulated (the recipe's 4 x 4)")
+        variants["micro_4x4"] = dict(ms_per_step=round(ms_v, 4), value=tps(ms_v), note="4 micro-batches of B/4 pairs, dW accumulated (the recipe's 4 x 4); loss / 4 before each backward, announced as grad_scale_hint")
         del micro
     if do_var and not args.dense:
         # dense convention (SURVEY 8d primary figure for cfg-1..4): every fed position through every GEMM, no row compaction

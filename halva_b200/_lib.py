@@ -9,7 +9,7 @@ LIB_PATH = os.environ.get("HALVA_DPA_LIB") or os.path.join(HERE, "libhalva_dpa.s
 
 DPA_BF16, DPA_F32 = 0, 1
 DPA_I64, DPA_I32 = 0, 1
-FLAG_ROUND_LOGITS, FLAG_NEED_DW, FLAG_DENSE, FLAG_FUSED_GRAD, FLAG_FUSED_NORM, FLAG_LOSS_ONLY = 1, 2, 4, 8, 16, 32
+FLAG_ROUND_LOGITS, FLAG_NEED_DW, FLAG_DENSE, FLAG_FUSED_GRAD, FLAG_FUSED_NORM, FLAG_LOSS_ONLY, FLAG_GRAD_HINT = 1, 2, 4, 8, 16, 32, 64
 ABI_VERSION = 5
 STATUS_BAD_SIGN, STATUS_K_MISMATCH, STATUS_K_ZERO, STATUS_BAD_LABEL = 1, 2, 4, 8
 EXPORTS = ["dpa_version", "dpa_last_error", "dpa_query_workspace", "dpa_struct_sizes", "dpa_forward", "dpa_backward",

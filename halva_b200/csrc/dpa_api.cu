@@ -296,7 +296,7 @@ struct Layout {
   int n_slots;      // fused-gradient forward: row chunks whose pair-row logits are KEPT (slot c = chunk c); later chunks reuse slot 0
   // state offsets
   size_t meta, bitmap, sync_ctr, block_counts, src_pair, lab_pair, col_pair, src_ref, act_ref, stats_pair, stats_ref, stats_u,
-      lse_pair, logp_pair, lse_ref_p, lse_ref_r, kl_row, PN, sigma, coef_pair, coef_ref, rinv, dnw32, state_total;
+      lse_pair, logp_pair, lse_ref_p, lse_ref_r, kl_row, PN, sigma, coef_pair, coef_ref, rinv, dnw32, formed_for, state_total;
   size_t row_stats_bytes;
   // forward scratch offsets
   size_t f_Hp, f_Hf, f_part_pair, f_part_ref, f_part_u, f_gather, fwd_total;
@@ -372,6 +372,7 @@ int make_layout(const dpa_shape_t& s, Layout& L) {
   L.coef_pair = take((size_t)L.cap_pair * 4); L.coef_ref = take((size_t)L.cap_ref * 4);
   L.rinv = take((size_t)cap_tot * 4);             // DPA_FLAG_FUSED_NORM: rsqrt(var + eps) of the packed policy rows
   L.dnw32 = take((size_t)s.H * 4);                //                      fp32 accumulator of d_norm_w
+  L.formed_for = take(4);                         // DPA_FLAG_FUSED_GRAD: the upstream gradient the forward formed the gradients for
   L.state_total = o;
 
   const size_t parts = L.split ? 3 : 1;
@@ -1230,9 +1231,10 @@ struct Plan {
     LAUNCH_CHECK("dW zero-if-empty");
     return DPA_OK;
   }
-  int coef(const float* d_loss) {
+  int coef(const float* d_loss, bool remember = false) {
     CoefArgs c{meta, at<int>(a->state, L.col_pair), at<int>(a->state, L.act_ref), at<float>(a->state, L.sigma), d_loss,
-               at<float>(a->state, L.coef_pair), at<float>(a->state, L.coef_ref), s.B, s.B_ref, a->alpha};
+               at<float>(a->state, L.coef_pair), at<float>(a->state, L.coef_ref), s.B, s.B_ref, a->alpha,
+               remember ? at<float>(a->state, L.formed_for) : nullptr};
     ProfScope ps(PK_COEF, 1, st);
     coef_kernel<<<d->sms * 2, 256, 0, st>>>(c);
     LAUNCH_CHECK("coef");
@@ -1311,7 +1313,10 @@ int forward_fused_impl(const dpa_args_t* a, cudaStream_t st) {
   if ((rc = p.merge(RowRange{SEG_PAIR, 0, 0}, true, vp ? MERGE_ONLY : MERGE_FINISH, vp))) return rc;
   if (vp && (rc = p.exchange_stats(RowRange{SEG_PAIR, 0, 0}, MERGE_FINISH, n_exchange++))) return rc;
   if ((rc = run_losses(a, L, st, LOSS_ALIGN, 0))) return rc;
-  if ((rc = p.coef(nullptr /* d_loss = 1 */))) return rc;
+  // gradients are formed for d_loss = 1, or for the caller's hint of the upstream gradient (DPA_FLAG_GRAD_HINT: *d_loss now)
+  const float* hint = (s.flags & DPA_FLAG_GRAD_HINT) ? a->d_loss : nullptr;
+  if ((s.flags & DPA_FLAG_GRAD_HINT) && !hint) return fail(DPA_ERR_ARG, "DPA_FLAG_GRAD_HINT set but d_loss is NULL at dpa_forward");
+  if ((rc = p.coef(hint, true))) return rc;
 
   // ---- row chunks of the packed space [pair rows | reference-sample rows]
   for (int ch = 0; ch < L.n_chunks; ++ch) {
@@ -1369,8 +1374,9 @@ int backward_scale_impl(const dpa_args_t* a, cudaStream_t st) {
   if (rc) return rc;
   if (a->shape.flags & DPA_FLAG_LOSS_ONLY) return fail(DPA_ERR_ARG, "DPA_FLAG_LOSS_ONLY: the forward formed no gradients");
   if ((rc = check_grad_outputs(a))) return rc;
-  if (!a->d_loss) return DPA_OK;                                 // NULL = 1
   const dpa_shape_t& s = a->shape;
+  if (!a->d_loss && !(s.flags & DPA_FLAG_GRAD_HINT)) return DPA_OK;       // NULL = 1, and they were formed for 1
+  if (!a->d_loss) return fail(DPA_ERR_ARG, "DPA_FLAG_GRAD_HINT: dpa_backward needs the actual d_loss");
   ProfScope ps(PK_SCALE, 1, st);
   ScaleSegs sg{};
   auto add = [&](void* p, size_t n) { sg.p[sg.count] = p; sg.n[sg.count] = n; ++sg.count; };
@@ -1378,8 +1384,9 @@ int backward_scale_impl(const dpa_args_t* a, cudaStream_t st) {
   add(a->dH_ref, (size_t)s.B_ref * s.T_ref * s.H);
   if (s.flags & DPA_FLAG_NEED_DW) add(a->dW, (size_t)s.V_local * s.H);
   if ((s.flags & DPA_FLAG_FUSED_NORM) && a->d_norm_w) add(a->d_norm_w, (size_t)s.H);
-  if (L.split) scale_grads_kernel<float><<<d->sms * 8, 256, 0, st>>>(sg, a->d_loss);
-  else scale_grads_kernel<__nv_bfloat16><<<d->sms * 8, 256, 0, st>>>(sg, a->d_loss);
+  const float* formed_for = at<float>(a->state, L.formed_for);
+  if (L.split) scale_grads_kernel<float><<<d->sms * 8, 256, 0, st>>>(sg, a->d_loss, formed_for);
+  else scale_grads_kernel<__nv_bfloat16><<<d->sms * 8, 256, 0, st>>>(sg, a->d_loss, formed_for);
   LAUNCH_CHECK("scale_grads");
   return DPA_OK;
 }

@@ -540,10 +540,12 @@ struct CoefArgs {
   const int* col_pair; const int* act_ref; const float* sigma; const float* d_loss;
   float* coef_pair; float* coef_ref;
   int B, B_ref; float alpha;
+  float* formed_for;     // fused-gradient forward: remembers the upstream gradient the gradients are being formed for
 };
 __global__ void coef_kernel(CoefArgs a) {
   const int p0 = a.meta->p0, nr_pad = a.meta->n_tot - p0;
   float go = a.d_loss ? *a.d_loss : 1.f;
+  if (a.formed_for && blockIdx.x == 0 && threadIdx.x == 0) *a.formed_for = go;
   // Ill-formed phrase ids / labels: the reference raises (halva_trainer.py:567) or returns NaN; the device cannot raise,
   // so the gradients are poisoned the same way loss_kernel poisons the loss -- finite-but-wrong dH / dW must never reach
   // the optimiser.
@@ -828,13 +830,14 @@ __global__ void __launch_bounds__(256) dz_kl_elem_f32_kernel(DzElemF32Args a) {
     if (threadIdx.x == 0) a.kl_row[j] = tot - a.kl_row[j];
   }
 }
-// ---- fused-gradient backward: the gradients were formed for d_loss = 1 during the forward; scale them by the
-//      upstream gradient (a device scalar) unless it is exactly 1
+// ---- fused-gradient backward: the gradients were formed during the forward for d_loss = 1 (or the caller's hint); scale them by the
+//      upstream gradient (a device scalar) unless they were formed for exactly that value (1, or the caller's hint)
 struct ScaleSegs { void* p[4]; size_t n[4]; int count; };       // up to four gradient tensors, one launch
 template <class T>
-__global__ void scale_grads_kernel(ScaleSegs sg, const float* __restrict__ d_loss) {
-  const float go = *d_loss;
-  if (go == 1.f) return;
+__global__ void scale_grads_kernel(ScaleSegs sg, const float* __restrict__ d_loss, const float* __restrict__ formed_for) {
+  const float want = *d_loss, have = *formed_for;
+  if (want == have) return;
+  const float go = want / have;          // (have == 0 with want != 0: the zero gradients cannot be rescaled -> NaN, loudly)
   const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   for (int k = 0; k < sg.count; ++k) {
     uint4* p = reinterpret_cast<uint4*>(sg.p[k]);

@@ -74,7 +74,7 @@ class _Call:
 
     def __init__(self, h_pair, labels_pair, signs_pair, h_ref_pol, h_ref_frozen, labels_ref, W, W_ref, alpha,
                  round_logits, need_dW, dense, chunk_rows, v_offset, V_global, fused, norm=None, ref_logits=None,
-                 loss_only=False):
+                 loss_only=False, grad_hint=1.0):
         lib = _lib.load()
         self.lib = lib
         dev = h_pair.device
@@ -95,6 +95,12 @@ class _Call:
         flags = (_lib.FLAG_ROUND_LOGITS if round_logits else 0) | (_lib.FLAG_NEED_DW if need_dW else 0) | \
                 (_lib.FLAG_DENSE if dense else 0) | (_lib.FLAG_FUSED_GRAD if fused else 0) | \
                 (_lib.FLAG_FUSED_NORM if norm is not None else 0) | (_lib.FLAG_LOSS_ONLY if loss_only else 0)
+        # the upstream gradient the caller expects (1 / gradient-accumulation steps): the fused forward forms the gradients
+        # for it, and the backward rescales them only if the actual d_loss differs
+        self.hint = None
+        if fused and not loss_only and float(grad_hint) != 1.0:
+            self.hint = torch.full((1,), float(grad_hint), dtype=torch.float32, device=dev)
+            flags |= _lib.FLAG_GRAD_HINT
         self.loss_only = loss_only
         self.fused = fused
         self.lib_comm = False
@@ -118,7 +124,7 @@ class _Call:
                          h_pair=_ptr(hp), labels_pair=_ptr(lp), signs_pair=_ptr(sp), h_ref_pol=_ptr(hr), h_ref_frz=_ptr(hf),
                          labels_ref=_ptr(lr), W=_ptr(w), W_ref=_ptr(wr),
                          state=_ptr(self.state), state_bytes=ws.state_bytes, scratch=None, scratch_bytes=0,
-                         losses=_ptr(self.losses), status=_ptr(self.status), d_loss=None, dH_pair=None, dH_ref=None, dW=None,
+                         losses=_ptr(self.losses), status=_ptr(self.status), d_loss=_ptr(self.hint), dH_pair=None, dH_ref=None, dW=None,
                          norm_w=_ptr(self.norm[0]) if self.norm else None, norm_w_ref=_ptr(self.norm[1]) if self.norm else None,
                          d_norm_w=None, norm_eps=self.norm[2] if self.norm else 0.0,
                          ref_logits=_ptr(ref_logits), ref_logits_ld=0 if ref_logits is None else ref_logits.stride(1),
@@ -201,7 +207,7 @@ class DPALossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, h_pair, h_ref_pol, W, norm_w, labels_pair, signs_pair, labels_ref, h_ref_frozen, W_ref, alpha, round_logits,
-                need_dW, dense, chunk_rows, vocab_group, v_offset, V_global, fused, norm_w_ref, norm_eps, ref_logits):
+                need_dW, dense, chunk_rows, vocab_group, v_offset, V_global, fused, norm_w_ref, norm_eps, ref_logits, grad_hint=1.0):
         want_grad = any(ctx.needs_input_grad[:4])
         loss_only = ref_logits is not None and not want_grad        # given logits live on the chunked (fused) forward only
         fused = bool(fused and (want_grad or loss_only))            # no gradient wanted (eval): statistics only
@@ -209,7 +215,7 @@ class DPALossFn(torch.autograd.Function):
         det = lambda t: None if t is None else t.detach()
         call = _Call(h_pair.detach(), labels_pair, signs_pair, h_ref_pol.detach(), det(h_ref_frozen), labels_ref,
                      W.detach(), det(W_ref), alpha, round_logits, need_dW and not loss_only, dense, chunk_rows, v_offset, V_global,
-                     fused, norm, det(ref_logits), loss_only)
+                     fused, norm, det(ref_logits), loss_only, grad_hint)
         call.forward(vocab_group)
         ctx.call = call
         ctx.status_t = call.status
@@ -235,7 +241,7 @@ class DPALossFn(torch.autograd.Function):
             dist.all_reduce(dH_ref, group=ctx.vocab_group)
         if call.fused:
             ctx.call = None                         # recompute mode keeps its O(rows) state: a retained graph can run again
-        return (dH_pair, dH_ref, dW, dnw) + (None,) * 17
+        return (dH_pair, dH_ref, dW, dnw) + (None,) * 18
 
 
 def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.Tensor,
@@ -246,7 +252,7 @@ def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.
              vocab_group=None, v_offset: Optional[int] = None, vocab_size: Optional[int] = None,
              backward: str = "auto", norm_weight: Optional[torch.Tensor] = None,
              norm_weight_ref: Optional[torch.Tensor] = None, norm_eps: float = 1e-6, strict: bool = False,
-             ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+             grad_scale_hint: float = 1.0) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """Fused DPA loss.  Returns (loss, alignment_loss, divergence) as 0-dim fp32 CUDA tensors; `loss` carries grad.
 
     h_pair       [2B, T, H] bf16   final hidden states; first B sequences "pos" (correct), last B "neg"
@@ -288,6 +294,11 @@ def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.
                                    backward only scales by d_loss;  "auto" = "fused" when round_logits is on, a gradient
                                    is needed and there is no vocab_group (or the library's own communicator spans it:
                                    halva_b200.dist.init_library_comm), else "recompute".
+    grad_scale_hint                the upstream gradient `loss.backward()` is EXPECTED to deliver (HF Trainer / DeepSpeed divide
+                                   the loss by gradient_accumulation_steps before the backward: 1 / steps).  The "fused" pass
+                                   forms its gradients for that value during the forward, so that the backward has nothing
+                                   to rescale (otherwise one pass over dH / dW); a wrong hint only costs that pass, the
+                                   gradients are the same.  Ignored by the "recompute" strategy (it sees the real value).
     Ill-formed phrase ids (K_pos != K_neg, K == 0, id > 255) or labels make the losses AND every gradient NaN and set
     bits in `read_status(loss)["status"]` / `loss.dpa_status`; the reference raises / returns NaN there (SURVEY.md
     section 3.2) -- a truncated batch can never reach the optimiser as finite-but-wrong gradients.
@@ -330,6 +341,8 @@ def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.
         for name, t in (("norm_weight", norm_weight), ("norm_weight_ref", norm_weight_ref)):
             if not t.is_cuda or t.dtype != torch.bfloat16 or t.numel() != h_pair.shape[2]:
                 raise TypeError(f"{name} must be a CUDA bf16 tensor of H elements")
+    if not (grad_scale_hint == grad_scale_hint and abs(grad_scale_hint) != float("inf")) or grad_scale_hint == 0:
+        raise ValueError("grad_scale_hint must be a finite, non-zero number (the expected upstream gradient of the loss)")
     if backward not in ("auto", "recompute", "fused"):
         raise ValueError("backward must be 'auto', 'recompute' or 'fused'")
     fp32 = h_pair.dtype == torch.float32
@@ -350,7 +363,7 @@ def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.
     loss, align, div, status = DPALossFn.apply(h_pair, h_ref_pol, W, norm_weight, labels_pair, signs_pair, labels_ref, h_ref_frozen,
                                                W_ref, float(alpha), bool(round_logits), bool(need_dW), bool(dense), int(chunk_rows),
                                                vocab_group, int(v_offset), int(vocab_size), fused, norm_weight_ref, float(norm_eps),
-                                               ref_logits)
+                                               ref_logits, float(grad_scale_hint))
     loss.dpa_status = status                 # device int32[8]: status bits, K, active rows ... (read_status(loss) decodes it)
     out = (loss, align, div)
     if strict:

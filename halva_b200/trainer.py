@@ -143,7 +143,7 @@ def final_hidden_states(model, input_ids, images, labels, attention_mask, signs=
 # ----------------------------------------------------------------------------------------------- the override
 def fused_compute_loss(trainer, model, inputs, return_outputs: bool = False, num_items_in_batch: Optional[int] = None,
                        *, round_logits: bool = True, backward: str = "auto", sync_logging: bool = False,
-                       fuse_final_norm: bool = False, strict: bool = False):
+                       fuse_final_norm: bool = False, strict: bool = False, grad_scale_hint: Optional[float] = None):
     """Same contract as ``HalvaTrainer.compute_loss(model, inputs)``: returns the 0-dim fp32 loss (with grad).
 
     The LLaVA flavour of the reference ignores its ``model`` argument and calls ``self.model``
@@ -153,6 +153,9 @@ def fused_compute_loss(trainer, model, inputs, return_outputs: bool = False, num
     ``num_items_in_batch`` (newer transformers) is accepted and ignored, as the reference would.
     ``fuse_final_norm``: run the decoders without their final RMSNorm and let dpa_loss apply it (and its backward) to
     the contributing rows only.
+    ``grad_scale_hint``: the upstream gradient the trainer's backward will deliver; default 1 / ``trainer.args.
+    gradient_accumulation_steps`` (``Trainer.training_step`` / the DeepSpeed engine divide the loss by it before the backward),
+    so that the gradients formed during the forward need no rescaling pass.  Only a hint: a different actual value is honoured.
     ``strict``: read the op's status word back after the forward (one host sync per step) and raise where the reference
     raises -- ``RuntimeError`` for K_pos != K_neg (llava halva_trainer.py:567), ``ValueError`` for phrase ids above 255 /
     labels outside the vocabulary.  Off by default: an ill-formed batch then yields a NaN loss and NaN gradients (never
@@ -205,9 +208,13 @@ def fused_compute_loss(trainer, model, inputs, return_outputs: bool = False, num
         else:
             W_op, W_ref_op = W, (None if shared else W_ref.detach())
         frozen_kw = dict(h_ref_frozen=h_ref_frz, W_ref=W_ref_op) if ref_logits is None else dict(ref_logits=ref_logits)
+        if grad_scale_hint is None:
+            gas = getattr(getattr(trainer, "args", None), "gradient_accumulation_steps", 1)
+            grad_scale_hint = 1.0 / gas if isinstance(gas, int) and gas > 1 else 1.0
         loss, align, div = _dpa_loss_mod.dpa_loss(
             h_pair, labels_pair, signs_pair, h_ref_pol, labels_ref, W_op, alpha=alpha, round_logits=round_logits,
-            need_dW=bool(W.requires_grad), backward=backward, strict=strict, **frozen_kw, **norm_kw)
+            need_dW=bool(W.requires_grad), backward=backward, strict=strict, grad_scale_hint=grad_scale_hint,
+            **frozen_kw, **norm_kw)
 
     holder = getattr(trainer, "loss_holder", None)
     if isinstance(holder, dict) and all(k in holder for k in ("contrastive_loss", "divergence", "loss")):

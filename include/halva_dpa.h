@@ -69,6 +69,12 @@ typedef enum { DPA_I64 = 0, DPA_I32 = 1 } dpa_index_t;
 #define DPA_FLAG_LOSS_ONLY    32  /* with DPA_FLAG_FUSED_GRAD: run the chunked forward for the losses only (evaluation,
                                      torch.no_grad()): no gradient buffers needed, no gradient GEMMs */
 
+#define DPA_FLAG_GRAD_HINT    64  /* with DPA_FLAG_FUSED_GRAD: `d_loss` is already valid at dpa_forward and holds the upstream
+                                     gradient the caller EXPECTS (1 / gradient-accumulation steps under HF Trainer /
+                                     DeepSpeed).  The gradients are formed for that value, and dpa_backward -- given the
+                                     actual *d_loss -- rescales them only if the two differ: with a correct hint the
+                                     backward touches no gradient byte.  Without the flag they are formed for 1. */
+
 typedef struct {
   int32_t B;          /* sample pairs; h_pair holds 2B sequences, first B "pos"(correct), last B "neg"(hallucinated) */
   int32_t T;          /* pair sequence length (post image splice) */
@@ -111,7 +117,8 @@ typedef struct {
   float* losses;               /* [4]: loss, align, div, reserved */
   int32_t* status;             /* [8]: status bits, K, n_pair_active, n_ref_active, ... */
   /* backward */
-  const float* d_loss;         /* device scalar: upstream gradient of `loss` */
+  const float* d_loss;         /* device scalar: upstream gradient of `loss` (read by dpa_backward; NULL = 1.  Under
+                                  DPA_FLAG_GRAD_HINT also read by dpa_forward, as the expected value) */
   void* dH_pair;               /* [2B, T, H]  (fully written, zeros for inactive rows) */
   void* dH_ref;                /* [B_ref, T_ref, H] */
   void* dW;                    /* [V_local, H] or NULL */

@@ -229,6 +229,45 @@ def test_grad_output_scaling_and_determinism(bwd):
     assert rel(s["dH_pair"], 0.25 * a["dH_pair"]) <= 5e-3 and rel(s["dW"], 0.25 * a["dW"]) <= 5e-3
 
 
+def test_grad_scale_hint():
+    """dpa_loss(grad_scale_hint=g): the fused forward forms the gradients for the announced upstream gradient; the backward
+    rescales only when the actual one differs.  Right hint, wrong hint and no hint give the same gradients (to the bf16
+    rounding of dLogits), all equal to the oracle's for that grad_output; the recompute strategy ignores the hint."""
+    t, _ = _synth()
+    f = lambda x: x.float().cpu().numpy()
+    o = dpa_oracle.dpa_loss(f(t["h_pair"]), t["labels_pair"].cpu().numpy(), t["signs_pair"].cpu().numpy(), f(t["h_ref_pol"]),
+                            f(t["h_ref_frz"]), t["labels_ref"].cpu().numpy(), f(t["W"]), f(t["W_ref"]), t["alpha"], mode="bf16",
+                            grad_output=0.25)
+    runs = dict(none=_run_cuda(t, grad_out=0.25, backward="fused"),
+                right=_run_cuda(t, grad_out=0.25, backward="fused", grad_scale_hint=0.25),
+                wrong=_run_cuda(t, grad_out=0.25, backward="fused", grad_scale_hint=-3.0),
+                recompute=_run_cuda(t, grad_out=0.25, backward="recompute", grad_scale_hint=0.25),
+                chunked=_run_cuda(t, grad_out=0.25, backward="fused", grad_scale_hint=0.25, chunk_rows=256, dense=True))
+    for name, c in runs.items():
+        assert c["loss"] == runs["none"]["loss"], name
+        for k in ("dH_pair", "dH_ref", "dW"):
+            assert rel(c[k], o[k]) <= TOL_GRAD_BF16, (name, k, rel(c[k], o[k]))
+            assert rel(c[k], runs["none"][k]) <= 6e-3, (name, k)
+    # the right hint IS the reference's order of operations (the upstream gradient enters before dLogits are rounded to bf16)
+    assert np.array_equal(runs["right"]["dH_pair"], runs["recompute"]["dH_pair"]) or \
+        rel(runs["right"]["dH_pair"], runs["recompute"]["dH_pair"]) <= 2e-3
+    # fp32 inputs take the hint too
+    from halva_b200 import dpa_loss
+    t32 = {k: (v.float() if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in t.items()}
+    out = {}
+    for name, kw in (("none", {}), ("right", dict(grad_scale_hint=0.25)), ("wrong", dict(grad_scale_hint=2.0))):
+        hp = t32["h_pair"].clone().requires_grad_(True)
+        W = t32["W"].clone().requires_grad_(True)
+        loss, _, _ = dpa_loss(hp, t32["labels_pair"], t32["signs_pair"], t32["h_ref_pol"], t32["labels_ref"], W,
+                              h_ref_frozen=t32["h_ref_frz"], alpha=t32["alpha"], **kw)
+        (loss * 0.25).backward()
+        out[name] = (hp.grad.cpu().numpy(), W.grad.cpu().numpy())
+    for name in ("right", "wrong"):
+        assert rel(out[name][0], out["none"][0]) <= 1e-5 and rel(out[name][1], out["none"][1]) <= 1e-5, name
+    with pytest.raises(ValueError):
+        _run_cuda(t, grad_scale_hint=0.0)
+
+
 def test_quirks_match_reference():
     """K == 0 -> NaN (as the reference); K_pos != K_neg -> NaN + status bit (the reference raises RuntimeError)."""
     from halva_b200 import dpa_loss, read_status

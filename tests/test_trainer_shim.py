@@ -253,6 +253,28 @@ def test_shim_takes_cached_frozen_logits_from_the_batch(monkeypatch):
         shim.fused_compute_loss(tr, pol, dict(inputs, ref_logits=cached[:, :-1]))
 
 
+def test_shim_announces_the_gradient_accumulation_scale(monkeypatch):
+    """Trainer.training_step / the DeepSpeed engine divide the loss by gradient_accumulation_steps before the backward: the
+    shim tells the op, so that the gradients formed during the forward need no rescaling pass.  An explicit value wins."""
+    from halva_b200 import trainer as shim
+    seen = []
+
+    def op(*a, grad_scale_hint=None, **kw):
+        seen.append(grad_scale_hint)
+        return _port_as_op(*a, **kw)
+    monkeypatch.setattr(shim._dpa_loss_mod, "dpa_loss", op)
+    pol, frz = _models()
+    inputs = make_inputs()
+    tr = _trainer(pol, frz)
+    shim.fused_compute_loss(tr, pol, inputs)                                   # no TrainingArguments at all
+    tr.args = types.SimpleNamespace(gradient_accumulation_steps=4)             # the reference recipe (src/hallava_7b.sh:22)
+    shim.fused_compute_loss(tr, pol, inputs)
+    shim.fused_compute_loss(tr, pol, inputs, grad_scale_hint=0.5)
+    tr.args.gradient_accumulation_steps = 1
+    shim.fused_compute_loss(tr, pol, inputs)
+    assert seen == [1.0, 0.25, 0.5, 1.0]
+
+
 def test_stack_pair_batch_pad_values():
     from halva_b200.trainer import stack_pair_batch
     inputs = make_inputs(Tp=9, Tn=13)
