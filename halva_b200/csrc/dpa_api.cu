@@ -1218,10 +1218,18 @@ struct Plan {
   // (Tried: the fill on a side stream, hidden behind the statistics GEMM -- the GEMM slows down by what the fill costs,
   //  the step is bound by power / HBM energy, not by idle tensor cores.  profiles/r02a.)
   int zero_grad_outputs() {
-    ProfScope ps(PK_MISC, 0, st);
     const size_t es = split ? 4 : 2;
-    CUDA_TRY(cudaMemsetAsync(a->dH_pair, 0, (size_t)2 * s.B * s.T * s.H * es, st));
-    CUDA_TRY(cudaMemsetAsync(a->dH_ref, 0, (size_t)s.B_ref * s.T_ref * s.H * es, st));
+    const size_t n_pair = (size_t)2 * s.B * s.T * s.H * es, n_ref = (size_t)s.B_ref * s.T_ref * s.H * es;   // (H % 64 == 0: 16-byte multiples)
+    static const bool use_kernel = env_int("DPA_ZERO_KERNEL", 1) != 0;        // 0: cudaMemsetAsync (A/B)
+    ProfScope ps(PK_MISC, use_kernel ? 1 : 0, st);
+    if (use_kernel) {
+      ZeroSegs z{{a->dH_pair, a->dH_ref}, {n_pair, n_ref}};
+      zero_fill_kernel<<<d->sms * 4, 512, 0, st>>>(z);
+      LAUNCH_CHECK("zero_fill");
+      return DPA_OK;
+    }
+    CUDA_TRY(cudaMemsetAsync(a->dH_pair, 0, n_pair, st));
+    CUDA_TRY(cudaMemsetAsync(a->dH_ref, 0, n_ref, st));
     return DPA_OK;      // (the dW accumulator needs no memset: the first chunk's epilogue overwrites it)
   }
   int finish_dW() {

@@ -868,6 +868,24 @@ __global__ void zero_if_no_rows_kernel(const DpaMeta* meta, void* out, size_t by
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) p[i] = make_uint4(0, 0, 0, 0);
 }
 
+// dense gradient outputs -> 0 before the dH epilogues scatter the contributing rows into them (two tensors, one launch;
+// 16-byte streaming stores, four in flight per thread)
+struct ZeroSegs { void* p[2]; size_t bytes[2]; };
+__global__ void __launch_bounds__(512) zero_fill_kernel(ZeroSegs z) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    uint4* p = reinterpret_cast<uint4*>(z.p[k]);
+    const size_t nv = z.bytes[k] >> 4;
+    size_t i = t0;
+    for (; i + 3 * stride < nv; i += 4 * stride) {
+      __stcs(p + i, zero); __stcs(p + i + stride, zero); __stcs(p + i + 2 * stride, zero); __stcs(p + i + 3 * stride, zero);
+    }
+    for (; i < nv; i += stride) __stcs(p + i, zero);
+  }
+}
+
 __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
   const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
   for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
