@@ -309,6 +309,9 @@ def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.
     """
     if (ref_logits is None) == (h_ref_frozen is None):
         raise ValueError("give exactly one of h_ref_frozen (+ W_ref) and ref_logits")
+    grad_scale_hint = float(grad_scale_hint)
+    if grad_scale_hint != grad_scale_hint or abs(grad_scale_hint) == float("inf") or grad_scale_hint == 0.0:
+        raise ValueError("grad_scale_hint must be a finite, non-zero number (the expected upstream gradient of the loss)")
     if ref_logits is not None:
         if W_ref is not None:
             raise ValueError("W_ref has no meaning together with ref_logits")
@@ -341,8 +344,6 @@ def dpa_loss(h_pair: torch.Tensor, labels_pair: torch.Tensor, signs_pair: torch.
         for name, t in (("norm_weight", norm_weight), ("norm_weight_ref", norm_weight_ref)):
             if not t.is_cuda or t.dtype != torch.bfloat16 or t.numel() != h_pair.shape[2]:
                 raise TypeError(f"{name} must be a CUDA bf16 tensor of H elements")
-    if not (grad_scale_hint == grad_scale_hint and abs(grad_scale_hint) != float("inf")) or grad_scale_hint == 0:
-        raise ValueError("grad_scale_hint must be a finite, non-zero number (the expected upstream gradient of the loss)")
     if backward not in ("auto", "recompute", "fused"):
         raise ValueError("backward must be 'auto', 'recompute' or 'fused'")
     fp32 = h_pair.dtype == torch.float32

@@ -83,6 +83,45 @@ def test_workspace_query_fp32_inputs_and_flag_conflicts():
         assert b"fp32 inputs" in lib.dpa_last_error()
 
 
+def test_workspace_follows_the_chunk_and_unit_rules(monkeypatch):
+    """Host-side layout rules, visible through dpa_query_workspace without a GPU: the default row chunk doubles for batches of
+    more than 131072 positions (halva_b200._lib.default_chunk_rows states the same rule), and a small vocabulary shard takes
+    single-tile work units (one partial-statistics record per row and 256 columns instead of per 1280)."""
+    from halva_b200._lib import FLAG_FUSED_GRAD, FLAG_NEED_DW, FLAG_ROUND_LOGITS, Shape, Workspace, default_chunk_rows
+    lib = _lib()
+    monkeypatch.delenv("DPA_TPU", raising=False)
+    fl = FLAG_FUSED_GRAD | FLAG_NEED_DW | FLAG_ROUND_LOGITS
+
+    def fused(chunk_rows=0, **over):
+        kw = dict(B=16, T=2048, B_ref=16, T_ref=2048, H=4096, V=32000, V_local=32000, v_offset=0, dtype=0, index_dtype=0, flags=fl)
+        kw.update(over)
+        ws = Workspace()
+        assert lib.dpa_query_workspace(C.byref(Shape(chunk_rows=chunk_rows, **kw)), C.byref(ws)) == 0, lib.dpa_last_error()
+        return ws
+    # cfg-2 (98 K positions): 32768-row chunks; cfg-4 (196 K positions): 65536
+    assert default_chunk_rows(32 * 2047, 16 * 2047) == 32768 and default_chunk_rows(32 * 4095, 16 * 4095) == 65536
+    assert fused().fused_bytes == fused(32768).fused_bytes < fused(65536).fused_bytes
+    big = dict(T=4096, T_ref=4096, H=5120)
+    assert fused(**big).fused_bytes == fused(65536, **big).fused_bytes > fused(32768, **big).fused_bytes
+    # the boundary itself: 4 x 32768 positions (padded to 256 per segment) still take the small chunk
+    edge = dict(B=16, T=2049, B_ref=32, T_ref=2049)                    # 32 * 2048 + 32 * 2048 = 131072
+    assert default_chunk_rows(32 * 2048, 32 * 2048) == 32768 and fused(**edge).fused_bytes == fused(32768, **edge).fused_bytes
+    # statistics partials of a V / 8 shard: 16 column groups of one tile (forced groups of five: 4)
+    shard = dict(H=5120, V=32000, V_local=4000, v_offset=4000, flags=FLAG_NEED_DW)
+    one = fused(**shard).fwd_bytes
+    monkeypatch.setenv("DPA_TPU", "5")
+    five = fused(**shard).fwd_bytes
+    monkeypatch.setenv("DPA_TPU", "1")
+    assert fused(**shard).fwd_bytes == one > five
+    cap_pair, cap_ref = -(-32 * 2047 // 256) * 256, -(-16 * 2047 // 256) * 256
+    assert one - five == (16 - 4) * (cap_pair * 16 + cap_ref * 16 + cap_ref * 4)
+    # the full vocabulary keeps groups of five: 25 groups
+    monkeypatch.delenv("DPA_TPU")
+    full = fused(flags=FLAG_NEED_DW).fwd_bytes
+    monkeypatch.setenv("DPA_TPU", "5")
+    assert fused(flags=FLAG_NEED_DW).fwd_bytes == full
+
+
 def test_python_op_argument_validation_without_gpu():
     """The two forms of the frozen branch are exclusive, and ref_logits belongs to the chunked bf16 pass."""
     import torch
@@ -99,6 +138,9 @@ def test_python_op_argument_validation_without_gpu():
         dpa_loss(h, y, y, h[:1], y[:1], W, ref_logits=z, alpha=0.4, round_logits=False)
     with pytest.raises(ValueError, match="ref_logits must be"):
         dpa_loss(h, y, y, h[:1], y[:1], W, ref_logits=z[:, :4], alpha=0.4)
+    for bad in (0.0, float("nan"), float("inf")):
+        with pytest.raises(ValueError, match="grad_scale_hint"):
+            dpa_loss(h, y, y, h[:1], y[:1], W, h_ref_frozen=h[:1], alpha=0.4, grad_scale_hint=bad)
     with pytest.raises(TypeError):                        # mixed precisions
         dpa_loss(h.float(), y, y, h[:1], y[:1], W, h_ref_frozen=h[:1], alpha=0.4)
     with pytest.raises(ValueError, match="fp32 inputs"):
