@@ -911,7 +911,7 @@ struct Plan {
     return m;
   }
   // split-bf16 GEMM configurations (fp32 inputs): 128-column accumulators (the K-chunk promotion keeps them in registers);
-  // the column groups of the statistics stay the 1280 columns of the bf16 tilings
+  // the column groups of the statistics stay those of the bf16 tilings (256 * Layout::tpu columns)
   static constexpr int kBnSplit = 128, kBnSplitDual = 64;
   int tpu_pair() const { return L.tpu; }                                  // tiles per unit of each tiling: the same columns
   int tpu_ref() const { return L.tpu * (kBnPair / kBnRef); }
@@ -1041,13 +1041,13 @@ struct Plan {
     {
       ProfScope ps(PK_STASH_REF, given ? 1 : 2, st);
       GemmWork wp{meta, KIND_STASH_POL, ch, L.chunk_rows, 0, s.V_local, s.H, tpu_pair(), super_m().stats, hint_stats().a, hint_stats().b};
-    set_sync(wp, ksync_stats(L.tpu));
+      set_sync(wp, ksync_stats(L.tpu));
       typename Epi::Params epp{meta, part2, dz_of(ch), L.cap_ref, s.V_local, L.ldz, ch * L.chunk_rows, 0};
       int rc = launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHp, tmW256, tmW128, wp, epp, "stash_pol");
       if (rc) return rc;
       if (!given) {
         GemmWork wf{meta, KIND_STASH_FRZ, ch, L.chunk_rows, 0, s.V_local, s.H, tpu_pair(), super_m().stats, hint_stats().a, hint_stats().b};
-    set_sync(wf, ksync_stats(L.tpu));
+        set_sync(wf, ksync_stats(L.tpu));
         typename Epi::Params epf{meta, part2, zr, L.cap_ref, s.V_local, L.ldz, ch * L.chunk_rows, 1};
         return launch_single<Epi, KMAJOR, KMAJOR>(st, d, tmHf, tmWr256, tmWr128, wf, epf, "stash_frz");
       }
