@@ -101,3 +101,64 @@ def test_oracle_given_frozen_logits_equals_hidden_state_form(golden):
                                 float(g["alpha"]), mode=mode, ref_logits=zr)
         assert a["loss"] == b["loss"] and a["div"] == b["div"]
         assert np.array_equal(a["dH_ref"], b["dH_ref"]) and np.array_equal(a["dW"], b["dW"])
+
+
+@pytest.mark.parametrize("i", range(10))
+def test_live_reference_random_sweep(i):
+    """Build container only (/root/reference present): the numpy oracle AND the torch port against the lifted, unmodified
+    reference on random shapes -- B != B_ref, T != T_ref, 1..5 phrases per sample with gaps in the id range, phrase ids that
+    may or may not include 0 positions, every-label-ignored sequences -- in fp32, forward and autograd backward.
+    Pins the checker beyond the committed fixtures; the fixtures remain what travels to the GPU box."""
+    from oracle.lift_reference import reference_available, run_reference
+    if not reference_available():
+        pytest.skip("no /root/reference here")
+    import torch
+    from oracle import dpa_port
+    rng = np.random.default_rng(4200 + i)
+    B, Br = int(rng.integers(1, 4)), int(rng.integers(1, 4))
+    T, Tr = int(rng.integers(6, 40)), int(rng.integers(4, 30))
+    H, V = int(rng.choice([16, 48])), int(rng.choice([37, 96, 130]))
+    K = int(rng.integers(1, 6))
+    ids = np.sort(rng.choice(np.arange(1, 12), size=K, replace=False))           # sparse phrase ids, same set for every sequence
+    labels = np.full((2 * B, T), -100, np.int64)
+    signs = np.zeros((2 * B, T), np.int64)
+    for s in range(2 * B):
+        t0 = int(rng.integers(1, max(2, T // 3)))
+        labels[s, t0:] = rng.integers(0, V, T - t0)
+        signs[s, :t0] = -100 if rng.random() < 0.5 else 0
+        pos = rng.permutation(np.arange(t0, T))[:max(K, (T - t0) // 2)]
+        for n, p in enumerate(pos):
+            signs[s, p] = ids[n % K]                                              # every id present in every half
+        if rng.random() < 0.3:
+            labels[s, T - 1] = -100
+    labels_ref = np.full((Br, Tr), -100, np.int64)
+    for s in range(Br):
+        if rng.random() < 0.2:
+            continue                                                              # a reference sample with no supervised token
+        t0 = int(rng.integers(1, Tr - 1))
+        labels_ref[s, t0:] = rng.integers(0, V, Tr - t0)
+    f32 = lambda *s: torch.from_numpy(rng.standard_normal(s).astype(np.float32))
+    W = 0.3 * f32(V, H)
+    W_ref = W if i % 2 == 0 else W + 0.05 * f32(V, H)
+    h_pair, h_ref_pol = f32(2 * B, T, H), f32(Br, Tr, H)
+    h_ref_frz = h_ref_pol + 0.2 * f32(Br, Tr, H)
+    alpha = float(rng.choice([0.0, 0.2, 0.4, 0.5]))
+    lt, st_, lrt = torch.from_numpy(labels), torch.from_numpy(signs), torch.from_numpy(labels_ref)
+    r = run_reference(h_pair, lt, st_, h_ref_pol, h_ref_frz, lrt, W, W_ref, alpha=alpha)
+    n = lambda t: t.numpy().astype(np.float64)
+    o = dpa_oracle.dpa_loss(n(h_pair), labels, signs, n(h_ref_pol), n(h_ref_frz), labels_ref, n(W), n(W_ref), alpha, mode="fp64")
+    ref_loss = r["loss"].item()
+    assert abs(o["loss"] - ref_loss) <= 1e-5 * abs(ref_loss), (o["loss"], ref_loss)
+    for k in ("dH_pair", "dH_ref", "dW"):
+        g = r[k].numpy()
+        if np.linalg.norm(g) == 0:
+            assert not o[k].any(), k
+        else:
+            assert rel(o[k], g) <= 1e-4, (k, rel(o[k], g))
+    # the torch port (the CPU baseline of bench.py and the GPU op-chain comparator) issues the reference's op sequence
+    hp, hr, Wp = h_pair.clone().requires_grad_(True), h_ref_pol.clone().requires_grad_(True), W.clone().requires_grad_(True)
+    lp, _, _ = dpa_port.dpa_loss_torch(hp, lt, st_, hr, h_ref_frz, lrt, Wp, W_ref if W_ref is not W else Wp, alpha)
+    lp.backward()
+    assert abs(lp.item() - ref_loss) <= 1e-6 * abs(ref_loss) + 1e-7
+    for k, g in (("dH_pair", hp.grad), ("dH_ref", hr.grad), ("dW", Wp.grad)):
+        assert torch.allclose(g, r[k], rtol=1e-4, atol=1e-6), k
