@@ -162,3 +162,37 @@ def test_live_reference_random_sweep(i):
     assert abs(lp.item() - ref_loss) <= 1e-6 * abs(ref_loss) + 1e-7
     for k, g in (("dH_pair", hp.grad), ("dH_ref", hr.grad), ("dW", Wp.grad)):
         assert torch.allclose(g, r[k], rtol=1e-4, atol=1e-6), k
+
+
+@pytest.mark.parametrize("i", range(4))
+def test_live_reference_random_sweep_bf16(i):
+    """The same idea in the trainer's precision: the lifted reference executed in bf16 (bf16 lm_head output, fp32 softmax
+    maths, bf16 autograd GEMMs) against the oracle's bf16 mode -- the north star's bf16 tolerances."""
+    from oracle.lift_reference import reference_available, run_reference
+    if not reference_available():
+        pytest.skip("no /root/reference here")
+    import torch
+    rng = np.random.default_rng(7700 + i)
+    B, Br, T, Tr, H, V, K = 2, int(rng.integers(1, 3)), int(rng.integers(10, 30)), int(rng.integers(8, 24)), 64, int(rng.choice([96, 200])), int(rng.integers(1, 4))
+    labels = np.full((2 * B, T), -100, np.int64)
+    signs = np.zeros((2 * B, T), np.int64)
+    for s in range(2 * B):
+        t0 = int(rng.integers(1, T // 3))
+        labels[s, t0:] = rng.integers(0, V, T - t0)
+        for n, p in enumerate(rng.permutation(np.arange(t0, T))[:max(K, (T - t0) // 2)]):
+            signs[s, p] = 1 + n % K
+    labels_ref = np.full((Br, Tr), -100, np.int64)
+    for s in range(Br):
+        t0 = int(rng.integers(1, Tr - 1))
+        labels_ref[s, t0:] = rng.integers(0, V, Tr - t0)
+    bf = lambda *s: torch.from_numpy(rng.standard_normal(s).astype(np.float32)).to(torch.bfloat16)
+    W = (0.2 * bf(V, H).float()).to(torch.bfloat16)
+    h_pair, h_ref_pol = bf(2 * B, T, H), bf(Br, Tr, H)
+    h_ref_frz = (h_ref_pol.float() + 0.2 * bf(Br, Tr, H).float()).to(torch.bfloat16)
+    lt, st_, lrt = torch.from_numpy(labels), torch.from_numpy(signs), torch.from_numpy(labels_ref)
+    r = run_reference(h_pair, lt, st_, h_ref_pol, h_ref_frz, lrt, W, W, alpha=0.4)
+    n = lambda t: t.float().numpy().astype(np.float64)
+    o = dpa_oracle.dpa_loss(n(h_pair), labels, signs, n(h_ref_pol), n(h_ref_frz), labels_ref, n(W), n(W), 0.4, mode="bf16")
+    assert abs(o["loss"] - r["loss"].item()) <= 1e-3 * abs(r["loss"].item())
+    for k in ("dH_pair", "dH_ref", "dW"):
+        assert rel(o[k], n(r[k])) <= 1e-2, (k, rel(o[k], n(r[k])))
