@@ -165,3 +165,26 @@ def test_missing_library_fails_loudly():
             "try:\n    _lib.load()\nexcept _lib.DPAError as e:\n    print('RAISED', 'no CPU or PyTorch fallback' in str(e))\n" % ROOT)
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
     assert out.stdout.strip() == "RAISED True", (out.stdout, out.stderr[-500:])
+
+
+def test_gemm_kernels_are_tcgen05_tma_in_sass():
+    """Static check of the built library (cuobjdump, no GPU): every GEMM kernel of the path issues tcgen05.mma (UTCHMMA; the
+    CTA-pair configurations as .2CTA), TMA tensor loads (UTMALDG) and tcgen05.ld (LDTM) -- and none falls back to the legacy
+    mma.sync path (HMMA).  /opt/skills/guides/B200_PROFILING.md names these mnemonics as the proof."""
+    import shutil
+    import subprocess
+    _lib()
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("no cuobjdump here")
+    lib = os.path.join(ROOT, "halva_b200", "libhalva_dpa.so")
+    sass = subprocess.run([exe, "-sass", lib], capture_output=True, text=True, timeout=300).stdout
+    blocks = [b for b in sass.split("Function : ")[1:] if "dpa_gemm" in b.split()[0]]
+    assert len(blocks) >= 20, len(blocks)                      # every (tile, operand majors, cta_group, epilogue) instantiation
+    pairs = 0
+    for b in blocks:
+        name = b.split()[0]
+        assert re.search(r"\bUTCHMMA\b", b) and re.search(r"\bUTMALDG\b", b) and re.search(r"\bLDTM\b", b), name
+        assert not re.search(r"\bHMMA\b", b), name
+        pairs += bool(re.search(r"UTCHMMA\.2CTA", b))
+    assert pairs >= len(blocks) // 2                           # the default configurations are CTA pairs (cta_group::2)
